@@ -1,0 +1,50 @@
+"""ctypes binding of the clipk C ABI (include/clipk.h).  The product path has NO fallback: if the shared
+library is missing or a call fails, an exception is raised."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libclipk.so")
+
+EPI_LINEAR, EPI_QUICK_GELU, EPI_ERF_GELU, EPI_DQUICK_GELU, EPI_DERF_GELU, EPI_ATOMIC_ADD = range(6)
+BF16, F32 = 0, 1
+
+
+class ClipkError(RuntimeError):
+    pass
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("mode", C.c_int), ("out_dtype", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int),
+                ("out2", C.c_void_p), ("ldo2", C.c_int), ("bias", C.c_void_p), ("residual", C.c_void_p),
+                ("ldr", C.c_int), ("aux", C.c_void_p), ("ldaux", C.c_int), ("alpha", C.c_float)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ClipkError(f"{LIB_PATH} not found: build it with `python -m easynlp_b200.build` "
+                             "(there is no CPU / PyTorch fallback on the product path)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.clipk_last_error.restype = C.c_char_p
+        _lib.clipk_launch_count.restype = C.c_int64
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    L.clipk_gemm_bf16.argtypes = [vp, i, i, vp, i, i, i, i, i, C.POINTER(Epilogue), i, vp]
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise ClipkError(f"{what} failed ({rc}): {lib().clipk_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().clipk_launch_count())

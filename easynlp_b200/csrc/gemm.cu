@@ -1,0 +1,316 @@
+// Persistent warp-specialised bf16 GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   D[M,N] = epilogue( A (*) B )      fp32 accumulation in TMEM
+//
+// Operand storage (both bf16, leading dimension in elements, multiple of 8):
+//   A K-major  : A[M, K] row-major (the activation in y = x W^T)           a_mn_major = 0
+//   A MN-major : A[K, M] row-major (dY in dW = dY^T X, contraction on rows) a_mn_major = 1
+//   B K-major  : B[N, K] row-major (an nn.Linear weight [out, in])          b_mn_major = 0
+//   B MN-major : B[K, N] row-major (W in dX = dY W, X in dW = dY^T X)       b_mn_major = 1
+// This covers every GEMM of the CLIP towers (reference ops K1, K3, K4, K8-K10 of SURVEY.md 2.3 and their
+// autograd counterparts) without materialising a transpose.
+//
+// Structure: grid = #SMs, static tile scheduler, 128 x BN output tile, BK = 64, 4-stage TMA->smem ring
+// (SWIZZLE_128B), one MMA-issuing thread (tcgen05.mma cta_group::1, M=128, N=BN, K=16), accumulators double-buffered
+// in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp 0: TMA producer   warp 1: MMA issuer + TMEM owner   warps 2-5: epilogue (TMEM -> registers -> global)
+#include "common.cuh"
+#include "../../include/clipk.h"
+
+namespace clipk {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles, splits, k_per_split;  // k_per_split multiple of BK
+  clipk_epilogue_t epi;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+};
+
+__device__ __forceinline__ void epi_store8(const GemmParams& p, int row, int col, float* v) {
+  const clipk_epilogue_t& e = p.epi;
+  if (e.bias) {
+    float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+    float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (e.mode == CLIPK_EPI_ATOMIC_ADD) {
+    float* o = reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col;
+    atomicAdd(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
+    atomicAdd(reinterpret_cast<float4*>(o + 4), make_float4(v[4], v[5], v[6], v[7]));
+    return;
+  }
+  if (e.mode == CLIPK_EPI_QUICK_GELU || e.mode == CLIPK_EPI_ERF_GELU) {
+    // out = pre-activation z (bf16, kept for backward), out2 = act(z) (bf16, next GEMM's operand)
+    uint4 z, a;
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // activation is evaluated on the bf16-rounded z so that backward (which only has bf16 z) is consistent
+      float zr = __bfloat162float(__float2bfloat16_rn(v[j]));
+      g[j] = (e.mode == CLIPK_EPI_QUICK_GELU) ? quick_gelu_f(zr) : erf_gelu_f(zr);
+    }
+    z.x = pack_bf16x2(v[0], v[1]); z.y = pack_bf16x2(v[2], v[3]); z.z = pack_bf16x2(v[4], v[5]); z.w = pack_bf16x2(v[6], v[7]);
+    a.x = pack_bf16x2(g[0], g[1]); a.y = pack_bf16x2(g[2], g[3]); a.z = pack_bf16x2(g[4], g[5]); a.w = pack_bf16x2(g[6], g[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = z;
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out2) + (size_t)row * e.ldo2 + col) = a;
+    return;
+  }
+  if (e.mode == CLIPK_EPI_DQUICK_GELU || e.mode == CLIPK_EPI_DERF_GELU) {
+    uint4 zz = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.aux) + (size_t)row * e.ldaux + col);
+    const __nv_bfloat162* zp = reinterpret_cast<const __nv_bfloat162*>(&zz);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 zf = __bfloat1622float2(zp[j]);
+      if (e.mode == CLIPK_EPI_DQUICK_GELU) {
+        v[2 * j] *= quick_gelu_grad_f(zf.x); v[2 * j + 1] *= quick_gelu_grad_f(zf.y);
+      } else {
+        v[2 * j] *= erf_gelu_grad_f(zf.x); v[2 * j + 1] *= erf_gelu_grad_f(zf.y);
+      }
+    }
+  }
+  if (e.residual) {
+    const float* r = e.residual + (size_t)row * e.ldr + col;
+    float4 r0 = *reinterpret_cast<const float4*>(r);
+    float4 r1 = *reinterpret_cast<const float4*>(r + 4);
+    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+  }
+  if (e.out_dtype == CLIPK_F32) {
+    float* o = reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col;
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = o;
+  }
+  if (e.out2 && e.mode == CLIPK_EPI_LINEAR) {  // optional bf16 shadow copy of an fp32 result
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out2) + (size_t)row * e.ldo2 + col) = o;
+  }
+}
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using L = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int num_tiles = tiles_mn * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int ks = tile / tiles_mn;
+        const int mn = tile - ks * tiles_mn;
+        const int m0 = (mn / p.n_tiles) * BM;
+        const int n0 = (mn % p.n_tiles) * BN;
+        const int k_begin = ks * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * L::STAGE_BYTES;
+          uint8_t* sB = sA + L::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int ks = tile / tiles_mn;
+        const int k_begin = ks * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accumulate = 0;
+        for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sB = sA + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_smem_desc(sA + k * 2048, BK * 128, 1024) : umma_smem_desc(sA + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_smem_desc(sB + k * 2048, BK * 128, 1024) : umma_smem_desc(sB + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);      // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================ epilogue warps (TMEM lane quarter = warp % 4)
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int ks = tile / tiles_mn;
+      const int mn = tile - ks * tiles_mn;
+      const int m0 = (mn / p.n_tiles) * BM;
+      const int n0 = (mn % p.n_tiles) * BN;
+      const int k_begin = ks * p.k_per_split;
+      const bool has_k = k_begin < p.K;   // an empty split contributes nothing (host never creates one, but be safe)
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c * 32, r);
+        tmem_wait_ld();
+        if (row < p.M && has_k) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const int col = n0 + c * 32 + s * 8;
+            if (col < p.N) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[s * 8 + j]) * p.epi.alpha;
+              epi_store8(p, row, col, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+template <int BN, int A_MN, int B_MN>
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  const int smem = GemmSmem<BN>::TOTAL;
+  if (!configured) {
+    CLIPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(tA, tB, p);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace clipk
+
+using namespace clipk;
+
+extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N,
+                               int K, const clipk_epilogue_t* epi, int splits, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) { set_error("clipk_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K); return CLIPK_ERR_ARG; }
+  if ((lda % 8) || (ldb % 8) || (N % 8)) { set_error("clipk_gemm_bf16: lda/ldb/N must be multiples of 8 (lda=%d ldb=%d N=%d)", lda, ldb, N); return CLIPK_ERR_ARG; }
+  if (!epi || !epi->out) { set_error("clipk_gemm_bf16: epilogue output missing"); return CLIPK_ERR_ARG; }
+  if (splits < 1) splits = 1;
+  if (splits > 1 && epi->mode != CLIPK_EPI_ATOMIC_ADD) { set_error("clipk_gemm_bf16: split-K requires CLIPK_EPI_ATOMIC_ADD"); return CLIPK_ERR_ARG; }
+  if (epi->mode == CLIPK_EPI_ATOMIC_ADD && epi->out_dtype != CLIPK_F32) { set_error("clipk_gemm_bf16: atomic epilogue needs fp32 output"); return CLIPK_ERR_ARG; }
+  if ((epi->mode == CLIPK_EPI_QUICK_GELU || epi->mode == CLIPK_EPI_ERF_GELU) && !epi->out2) { set_error("clipk_gemm_bf16: GELU epilogue needs out2"); return CLIPK_ERR_ARG; }
+  if ((epi->mode == CLIPK_EPI_DQUICK_GELU || epi->mode == CLIPK_EPI_DERF_GELU) && !epi->aux) { set_error("clipk_gemm_bf16: dGELU epilogue needs aux"); return CLIPK_ERR_ARG; }
+
+  const int BN = (N % 256 == 0 || N > 512) ? 256 : 128;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + BN - 1) / BN;
+  int kblocks = (K + BK - 1) / BK;
+  if (splits > kblocks) splits = kblocks;
+  int kb_per = (kblocks + splits - 1) / splits;
+  splits = (kblocks + kb_per - 1) / kb_per;   // no empty split
+  p.splits = splits;
+  p.k_per_split = kb_per * BK;
+  p.epi = *epi;
+  if (p.epi.alpha == 0.0f) p.epi.alpha = 1.0f;
+
+  CUtensorMap tA, tB;
+  int rc;
+  if (a_mn_major) rc = make_tmap_2d_bf16(&tA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+  else            rc = make_tmap_2d_bf16(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+  if (rc) return rc;
+  if (b_mn_major) rc = make_tmap_2d_bf16(&tB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  else            rc = make_tmap_2d_bf16(&tB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN);
+  if (rc) return rc;
+
+#define CLIPK_DISPATCH(BN_)                                                          \
+  if (a_mn_major) {                                                                  \
+    if (b_mn_major) return launch_gemm<BN_, 1, 1>(tA, tB, p, stream);                \
+    return launch_gemm<BN_, 1, 0>(tA, tB, p, stream);                                \
+  } else {                                                                           \
+    if (b_mn_major) return launch_gemm<BN_, 0, 1>(tA, tB, p, stream);                \
+    return launch_gemm<BN_, 0, 0>(tA, tB, p, stream);                                \
+  }
+  if (BN == 256) { CLIPK_DISPATCH(256) } else { CLIPK_DISPATCH(128) }
+#undef CLIPK_DISPATCH
+}
