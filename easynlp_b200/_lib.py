@@ -38,7 +38,26 @@ def lib():
 
 def _declare(L):
     vp, i, f = C.c_void_p, C.c_int, C.c_float
+    ll = C.c_longlong
     L.clipk_gemm_bf16.argtypes = [vp, i, i, vp, i, i, i, i, i, C.POINTER(Epilogue), i, vp]
+    L.clipk_attention_fwd.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
+    L.clipk_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
+    L.clipk_layernorm_fwd.argtypes = [vp, ll, vp, vp, f, vp, vp, vp, vp, i, i, vp]
+    L.clipk_layernorm_bwd.argtypes = [vp, i, vp, vp, ll, vp, vp, vp, vp, vp, ll, vp, vp, vp, vp, i, i, vp]
+    L.clipk_colsum.argtypes = [vp, i, ll, vp, i, i, vp]
+    L.clipk_im2col_patches.argtypes = [vp, vp, i, i, i, vp]
+    L.clipk_vit_assemble.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+    L.clipk_vit_assemble_bwd.argtypes = [vp, vp, i, i, i, vp]
+    L.clipk_bert_embed.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp]
+    L.clipk_bert_embed_bwd.argtypes = [vp, vp, vp, i, i, i, vp]
+    L.clipk_l2norm_fwd.argtypes = [vp, vp, vp, i, i, vp]
+    L.clipk_l2norm_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, vp]
+    L.clipk_cast_bf16.argtypes = [vp, vp, ll, vp]
+    L.clipk_ce_strip_fwd.argtypes = [vp, vp, vp, i, vp, ll, i, vp, vp, i, i, i, vp]
+    L.clipk_ce_strip_bwd.argtypes = [vp, vp, vp, vp, i, f, i, vp, i, vp, i, i, i, vp]
+    L.clipk_reduce_sum.argtypes = [vp, i, f, vp, i, vp]
+    L.clipk_grad_norm.argtypes = [vp, ll, f, vp, i, vp, vp]
+    L.clipk_adamw_step.argtypes = [vp, vp, vp, vp, vp, ll, f, f, f, f, f, i, vp, vp]
 
 
 def check(rc: int, what: str = ""):

@@ -1,0 +1,447 @@
+// Multi-head self-attention (head dim 64) forward and backward on tcgen05 tensor cores, one-shot over the whole key
+// range (sequences on this path are 197 / 77 / <= 256 tokens, so K and V of one head live in shared memory).
+//
+//   forward : S = Q K^T (TMEM) -> row softmax in registers (one thread per query row, straight from TMEM)
+//             -> P (bf16, SWIZZLE_128B in smem) -> O = P V (TMEM) -> ctx, log-sum-exp
+//   backward: per 128-query tile: S -> P ; dP = dO V^T ; dV += P^T dO ; dS = scale * P o (dP - D) ;
+//             dQ = dS K ; dK += dS^T Q      (dV / dK stay resident in TMEM across query tiles)
+//
+// Replaces nn.MultiheadAttention's SDPA (modeling_chineseclip.py:188,198-200) and BertSelfAttention's unfused
+// QK^T / +mask / softmax / PV chain (modeling_bert.py:210-244, additive key mask (1-m)*-10000 from
+// modeling_utils.py:438-439), which materialises [B,12,L,L] scores in HBM.
+//
+// Input layout: packed projections qkv[B*L, 3*d] bf16 (Q | K | V column blocks, head h at columns h*64 of each block),
+// i.e. exactly the output of the in_proj / fused query-key-value GEMM; output ctx[B*L, d].
+#include "common.cuh"
+#include "../../include/clipk.h"
+
+namespace clipk {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct AttnParams {
+  int B, L, H, d;
+  int lk_pad;          // keys padded to a multiple of 16 (<= 256)
+  int q_tiles;         // ceil(L / 128)
+  float scale;         // 1/sqrt(64)
+  const float* mask;   // [B, L] additive key mask or null
+  bf16* ctx;           // fwd out [B*L, d]
+  float* lse;          // [B, H, L] natural-log LSE of the scaled+masked scores
+  const bf16* ctx_in;  // bwd in
+  const bf16* dctx;    // bwd in  [B*L, d]
+  bf16* dqkv;          // bwd out [B*L, 3d]
+};
+
+__device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return umma_smem_desc(addr, 16, 1024); }                // K-major
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo) { return umma_smem_desc(addr, lbo, 1024); }  // MN-major
+
+__device__ __forceinline__ void store_row8_sw128(uint8_t* tile_base, int row, int col, const float* v) {
+  // 8 consecutive bf16 (cols col..col+7, col % 8 == 0) of row `row` in a [128-row x 64-col]-blocked SWIZZLE_128B tile
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(tile_base + (col >> 6) * 16384 + sw128_offset(row, (col & 63) >> 3)) = o;
+}
+
+// ====================================================================================================== forward
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int k_bytes = p.lk_pad * 128;
+  const int p_bytes = ((p.lk_pad + 63) >> 6) * 16384;
+  const int v_off = max(p_bytes, 16384 + k_bytes);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sP = smem;             // overlays Q and K once S = Q K^T has completed
+  uint8_t* sV = smem + v_off;
+  float* smask = reinterpret_cast<float*>(sV + k_bytes);          // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smask + 256);      // load, s, o
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const uint32_t ncols = p.lk_pad > 128 ? 256 : (p.lk_pad > 64 ? 128 : 64);
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_holder, ncols);
+  for (int j = tid; j < 256; j += 128)
+    smask[j] = (j < p.L) ? (p.mask ? p.mask[(long long)b * p.L + j] * LOG2E : 0.f) : -INFINITY;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], 16384 + 2 * k_bytes);
+    tma_load_2d(sQ, &tmQ, &bars[0], h * 64, b * p.L + qt * 128);
+    tma_load_2d(sK, &tmKV, &bars[0], p.d + h * 64, b * p.L);
+    tma_load_2d(sV, &tmKV, &bars[0], 2 * p.d + h * 64, b * p.L);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, p.lk_pad, 0, 0);
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_k(aQ + k * 32), desc_k(aK + k * 32), idesc, k > 0);
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+
+  const int row = tid;
+  const int q = qt * 128 + row;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const float sc = p.scale * LOG2E;
+  float mx = -INFINITY;
+  for (int c0 = 0; c0 < p.lk_pad; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld_x16(t_row + c0, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]) * sc + smask[c0 + j]);
+  }
+  float sum = 0.f;
+  for (int c0 = 0; c0 < p.lk_pad; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld_x16(t_row + c0, r);
+    tmem_wait_ld();
+    float pv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      pv[j] = exp2f(__uint_as_float(r[j]) * sc + smask[c0 + j] - mx);
+      sum += pv[j];
+    }
+    store_row8_sw128(sP, row, c0, pv);
+    store_row8_sw128(sP, row, c0 + 8, pv + 8);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+    const uint32_t aP = smem_u32(sP), aV = smem_u32(sV);
+    const int ksteps = p.lk_pad >> 4;
+    for (int t = 0; t < ksteps; ++t)
+      umma_bf16(tmem, desc_k(aP + (t >> 2) * 16384 + (t & 3) * 32), desc_mn(aV + t * 2048, 16384), idesc, t > 0);
+    umma_commit(&bars[2]);
+  }
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  {
+    const float inv = 1.0f / sum;
+    bf16* dst = p.ctx + (long long)(b * p.L + q) * p.d + h * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(t_row + c * 32, r);
+      tmem_wait_ld();
+      if (q < p.L) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(r[s * 8 + 0]) * inv, __uint_as_float(r[s * 8 + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(r[s * 8 + 2]) * inv, __uint_as_float(r[s * 8 + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(r[s * 8 + 4]) * inv, __uint_as_float(r[s * 8 + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(r[s * 8 + 6]) * inv, __uint_as_float(r[s * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 32 + s * 8) = o;
+        }
+      }
+    }
+    if (q < p.L && p.lse) p.lse[((long long)b * p.H + h) * p.L + q] = (mx + log2f(sum)) * LN2;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, ncols); }
+}
+
+// ====================================================================================================== backward
+// TMEM map (512 columns): [0,256) S -> dP -> dQ(64) ; [256,384) dV key-tiles 0,1 ; [384,512) dK key-tiles 0,1
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmDO,
+                const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int k_bytes = p.lk_pad * 128;
+  const int n_kt = p.lk_pad > 128 ? 2 : 1;       // 128-key tiles of dK / dV
+  const int kt_pad = n_kt * 128;
+  const int ps_bytes = n_kt * 2 * 16384;         // P / dS tiles: 64-key blocks of [128 x 128 B]
+  uint8_t* sQ = smem;
+  uint8_t* sDO = sQ + 16384;
+  uint8_t* sK = sDO + 16384;
+  uint8_t* sV = sK + k_bytes;
+  uint8_t* sP = sV + k_bytes;
+  uint8_t* sDS = sP + ps_bytes;
+  float* smask = reinterpret_cast<float*>(sDS + ps_bytes);        // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smask + 256);      // kv, qdo, s, dp, dq
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmDO);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_holder, 512);
+  for (int j = tid; j < 256; j += 128)
+    smask[j] = (j < p.L) ? (p.mask ? p.mask[(long long)b * p.L + j] * LOG2E : 0.f) : -INFINITY;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sDS);
+  const float sc = p.scale * LOG2E;
+  const int ksteps = p.lk_pad >> 4;
+
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], 2 * k_bytes);
+    tma_load_2d(sK, &tmKV, &bars[0], p.d + h * 64, b * p.L);
+    tma_load_2d(sV, &tmKV, &bars[0], 2 * p.d + h * 64, b * p.L);
+  }
+
+  for (int qt = 0; qt < p.q_tiles; ++qt) {
+    const uint32_t ph = qt & 1;
+    const int row = tid;
+    const int q = qt * 128 + row;
+    const bool qvalid = q < p.L;
+    // ---- loads + S = Q K^T
+    if (tid == 0) {
+      mbar_expect_tx(&bars[1], 2 * 16384);
+      tma_load_2d(sQ, &tmQ, &bars[1], h * 64, b * p.L + qt * 128);
+      tma_load_2d(sDO, &tmDO, &bars[1], h * 64, b * p.L + qt * 128);
+      if (qt == 0) mbar_wait(&bars[0], 0);
+      mbar_wait(&bars[1], ph);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(128, p.lk_pad, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_k(aQ + k * 32), desc_k(aK + k * 32), idesc, k > 0);
+      umma_commit(&bars[2]);
+    }
+    // D = rowsum(dO o O) and the row's LSE, straight from global memory while the MMA runs
+    float Dq = 0.f, lse2 = 0.f;
+    if (qvalid) {
+      const uint4* po = reinterpret_cast<const uint4*>(p.ctx_in + (long long)(b * p.L + q) * p.d + h * 64);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + (long long)(b * p.L + q) * p.d + h * 64);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 o = po[i], g = pd[i];
+        const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&o);
+        const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 a = __bfloat1622float2(o2[j]), c = __bfloat1622float2(g2[j]);
+          Dq += a.x * c.x + a.y * c.y;
+        }
+      }
+      lse2 = p.lse[((long long)b * p.H + h) * p.L + q] * LOG2E;
+    }
+    mbar_wait(&bars[2], ph);
+    tc_fence_after();
+    // ---- pass 1: P = exp(S - lse)  (rows beyond L and keys beyond L are exactly zero)
+    for (int c0 = 0; c0 < kt_pad; c0 += 16) {
+      float pv[16];
+      if (c0 < p.lk_pad) {
+        uint32_t r[16];
+        tmem_ld_x16(t_row + c0, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pv[j] = qvalid ? exp2f(__uint_as_float(r[j]) * sc + smask[c0 + j] - lse2) : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pv[j] = 0.f;
+      }
+      store_row8_sw128(sP, row, c0, pv);
+      store_row8_sw128(sP, row, c0 + 8, pv + 8);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- dP = dO V^T (overwrites S) ; dV += P^T dO
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t idesc_dp = umma_idesc_bf16(128, p.lk_pad, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_k(aDO + k * 32), desc_k(aV + k * 32), idesc_dp, k > 0);
+      const uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);
+      for (int mt = 0; mt < n_kt; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_bf16(tmem + 256 + mt * 64, desc_mn(aP + mt * 32768 + ks * 2048, 16384), desc_mn(aDO + ks * 2048, 16384), idesc_t,
+                    (qt > 0 || ks > 0) ? 1u : 0u);
+      umma_commit(&bars[3]);
+    }
+    mbar_wait(&bars[3], ph);
+    tc_fence_after();
+    // ---- pass 2: dS = scale * P o (dP - D)
+    for (int c0 = 0; c0 < kt_pad; c0 += 16) {
+      float dv[16];
+      if (c0 < p.lk_pad) {
+        uint32_t r[16];
+        tmem_ld_x16(t_row + c0, r);
+        tmem_wait_ld();
+        uint4 pa = *reinterpret_cast<const uint4*>(sP + (c0 >> 6) * 16384 + sw128_offset(row, (c0 & 63) >> 3));
+        uint4 pb = *reinterpret_cast<const uint4*>(sP + (c0 >> 6) * 16384 + sw128_offset(row, ((c0 + 8) & 63) >> 3));
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&pa);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&pb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 x = __bfloat1622float2(a2[j]), y = __bfloat1622float2(b2[j]);
+          dv[2 * j] = p.scale * x.x * (__uint_as_float(r[2 * j]) - Dq);
+          dv[2 * j + 1] = p.scale * x.y * (__uint_as_float(r[2 * j + 1]) - Dq);
+          dv[8 + 2 * j] = p.scale * y.x * (__uint_as_float(r[8 + 2 * j]) - Dq);
+          dv[8 + 2 * j + 1] = p.scale * y.y * (__uint_as_float(r[8 + 2 * j + 1]) - Dq);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dv[j] = 0.f;
+      }
+      store_row8_sw128(sDS, row, c0, dv);
+      store_row8_sw128(sDS, row, c0 + 8, dv + 8);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- dQ = dS K (overwrites dP) ; dK += dS^T Q
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);
+      for (int t = 0; t < ksteps; ++t)
+        umma_bf16(tmem, desc_k(aDS + (t >> 2) * 16384 + (t & 3) * 32), desc_mn(aK + t * 2048, 16384), idesc_dq, t > 0);
+      const uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);
+      for (int mt = 0; mt < n_kt; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_bf16(tmem + 384 + mt * 64, desc_mn(aDS + mt * 32768 + ks * 2048, 16384), desc_mn(aQ + ks * 2048, 16384), idesc_t,
+                    (qt > 0 || ks > 0) ? 1u : 0u);
+      umma_commit(&bars[4]);
+    }
+    mbar_wait(&bars[4], ph);
+    tc_fence_after();
+    {
+      bf16* dst = p.dqkv + (long long)(b * p.L + q) * (3 * p.d) + h * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c * 32, r);
+        tmem_wait_ld();
+        if (qvalid) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[s * 8 + 0]), __uint_as_float(r[s * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(r[s * 8 + 2]), __uint_as_float(r[s * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(r[s * 8 + 4]), __uint_as_float(r[s * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(r[s * 8 + 6]), __uint_as_float(r[s * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + c * 32 + s * 8) = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // TMEM [0,256) and the Q/dO/P/dS tiles are free for the next query tile
+    tc_fence_after();
+  }
+
+  // ---- epilogue: dK, dV rows (one thread per key)
+  for (int mt = 0; mt < n_kt; ++mt) {
+    const int key = mt * 128 + tid;
+    const bool kvalid = key < p.L;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {   // 0: dV -> V block, 1: dK -> K block
+      bf16* dst = p.dqkv + (long long)(b * p.L + key) * (3 * p.d) + (which == 0 ? 2 : 1) * p.d + h * 64;
+      const uint32_t tcol = (which == 0 ? 256 : 384) + mt * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(t_row + tcol + c * 32, r);
+        tmem_wait_ld();
+        if (kvalid) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[s * 8 + 0]), __uint_as_float(r[s * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(r[s * 8 + 2]), __uint_as_float(r[s * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(r[s * 8 + 4]), __uint_as_float(r[s * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(r[s * 8 + 6]), __uint_as_float(r[s * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + c * 32 + s * 8) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+static int check_shapes(const char* who, int B, int L, int H, int d) {
+  if (B <= 0 || L <= 0 || H <= 0 || d != H * 64) { set_error("%s: need d == 64*H (B=%d L=%d H=%d d=%d)", who, B, L, H, d); return CLIPK_ERR_ARG; }
+  if (L > 256) { set_error("%s: sequence length %d > 256 is not supported by the one-shot kernel yet", who, L); return CLIPK_ERR_UNSUPPORTED; }
+  return 0;
+}
+
+}  // namespace clipk
+
+using namespace clipk;
+
+extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void* ctx, float* lse, int B, int L, int H, int d,
+                                   cudaStream_t stream) {
+  int rc = check_shapes("attention_fwd", B, L, H, d);
+  if (rc) return rc;
+  AttnParams p{};
+  p.B = B; p.L = L; p.H = H; p.d = d;
+  p.lk_pad = (L + 15) & ~15;
+  p.q_tiles = (L + 127) / 128;
+  p.scale = 0.125f;
+  p.mask = key_mask; p.ctx = (bf16*)ctx; p.lse = lse;
+  CUtensorMap tQ, tKV;
+  if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, p.lk_pad))) return rc;
+  const int k_bytes = p.lk_pad * 128;
+  const int p_bytes = ((p.lk_pad + 63) >> 6) * 16384;
+  const int v_off = p_bytes > 16384 + k_bytes ? p_bytes : 16384 + k_bytes;
+  const int smem = v_off + k_bytes + 1024 + 64 + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    CLIPK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  attn_fwd_kernel<<<dim3(p.q_tiles, H, B), 128, smem, stream>>>(tQ, tKV, p);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
+                                   int B, int L, int H, int d, cudaStream_t stream) {
+  int rc = check_shapes("attention_bwd", B, L, H, d);
+  if (rc) return rc;
+  AttnParams p{};
+  p.B = B; p.L = L; p.H = H; p.d = d;
+  p.lk_pad = (L + 15) & ~15;
+  p.q_tiles = (L + 127) / 128;
+  p.scale = 0.125f;
+  p.mask = key_mask; p.lse = const_cast<float*>(lse);
+  p.ctx_in = (const bf16*)ctx; p.dctx = (const bf16*)dctx; p.dqkv = (bf16*)dqkv;
+  CUtensorMap tQ, tKV, tDO;
+  if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, p.lk_pad))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tDO, dctx, (uint64_t)d, (uint64_t)B * L, (uint64_t)d, 64, 128))) return rc;
+  const int k_bytes = p.lk_pad * 128;
+  const int n_kt = p.lk_pad > 128 ? 2 : 1;
+  const int smem = 2 * 16384 + 2 * k_bytes + 2 * (n_kt * 2 * 16384) + 1024 + 64 + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    CLIPK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  attn_bwd_kernel<<<dim3(H, B), 128, smem, stream>>>(tQ, tKV, tDO, p);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,411 @@
+// HBM-bound kernels of the CLIP towers: LayerNorm fwd/bwd, patch im2col, ViT token assembly, BERT embedding
+// gather/scatter, column sums (bias grads), L2 normalisation.  One warp owns one row; a lane owns the float4
+// column groups {lane + 32 i}, so per-column reductions over rows (dgamma, dbeta, dbias) stay in registers.
+#include "common.cuh"
+#include "../../include/clipk.h"
+
+namespace clipk {
+
+constexpr int LN_MAXV = 8;  // float4 per lane -> d <= 1024, d % 128 == 0
+
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st_bf4(bf16* p, float4 v) {
+  uint2 o; o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+__device__ __forceinline__ float4 ld_bf4(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
+  float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm fwd
+// reference: modeling_chineseclip.py:170-176 (fp32 LN, eps 1e-5) and nn.LayerNorm(eps=1e-12) in modeling_bert.py:84,266,344
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, bf16* __restrict__ y_bf16,
+                                                            float* __restrict__ y_f32, float* __restrict__ mean_out,
+                                                            float* __restrict__ rstd_out, int rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * ldx;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = ld_f4(xr + (lane + 32 * i) * 4);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+    q += a * a + b * b + c * c + e * e;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    float4 g = ld_f4(gamma + c), b = ld_f4(beta + c), o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (y_f32) st_f4(y_f32 + (long long)row * d + c, o);
+    if (y_bf16) st_bf4(y_bf16 + (long long)row * d + c, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm bwd
+//   g   = (dy [+ dy_add]) * gamma
+//   dx  = rstd * (g - mean_d(g) - xhat * mean_d(g * xhat))  [+ dx_add]
+//   dgamma += sum_rows (dy+dy_add) * xhat ; dbeta += sum_rows (dy+dy_add) ; dbias += sum_rows dx   (fp32 atomics)
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_is_f32, const float* __restrict__ dy_add,
+                                                            const float* __restrict__ x, long long ldx,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in, const float* __restrict__ dx_add,
+                                                            float* __restrict__ dx_f32, long long lddx, bf16* __restrict__ dx_bf16,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            float* __restrict__ dbias, int rows, int d) {
+  __shared__ float red[3][8][32 * 4];  // [which][warp][lane*4]  (per i iteration)
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarp = blockDim.x >> 5;
+  float4 ag[NV], ab[NV], ad[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gm[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) gm[i] = ld_f4(gamma + (lane + 32 * i) * 4);
+
+  for (int row = blockIdx.x * nwarp + warp; row < rows; row += gridDim.x * nwarp) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float* xr = x + (long long)row * ldx;
+    float4 xh[NV], g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      float4 xv = ld_f4(xr + c);
+      float4 dv = dy_is_f32 ? ld_f4(reinterpret_cast<const float*>(dy) + (long long)row * d + c)
+                            : ld_bf4(reinterpret_cast<const bf16*>(dy) + (long long)row * d + c);
+      if (dy_add) { float4 a = ld_f4(dy_add + (long long)row * d + c); dv.x += a.x; dv.y += a.y; dv.z += a.z; dv.w += a.w; }
+      xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd; xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
+      ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+      ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+      g[i].x = dv.x * gm[i].x; g[i].y = dv.y * gm[i].y; g[i].z = dv.z * gm[i].z; g[i].w = dv.w * gm[i].w;
+      s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+      s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      float4 o;
+      o.x = rstd * (g[i].x - s1 - xh[i].x * s2);
+      o.y = rstd * (g[i].y - s1 - xh[i].y * s2);
+      o.z = rstd * (g[i].z - s1 - xh[i].z * s2);
+      o.w = rstd * (g[i].w - s1 - xh[i].w * s2);
+      if (dx_add) { float4 a = ld_f4(dx_add + (long long)row * d + c); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+      ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;
+      if (dx_f32) st_f4(dx_f32 + (long long)row * lddx + c, o);
+      if (dx_bf16) st_bf4(dx_bf16 + (long long)row * d + c, o);
+    }
+  }
+  // cross-warp reduction of the per-column partials, then one atomic per column per CTA
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    __syncthreads();
+    st_f4(&red[0][warp][lane * 4], ag[i]);
+    st_f4(&red[1][warp][lane * 4], ab[i]);
+    st_f4(&red[2][warp][lane * 4], ad[i]);
+    __syncthreads();
+    for (int t = threadIdx.x; t < 3 * 128; t += blockDim.x) {
+      const int which = t / 128, cc = t % 128;
+      float s = 0.f;
+      for (int w = 0; w < nwarp; ++w) s += red[which][w][cc];
+      const int col = (cc >> 2) * 4 + 128 * i + (cc & 3);  // lane*4 + 128*i + component
+      float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+      if (dst) atomicAdd(dst + col, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column sum
+// out[n] += sum_rows x[rows, n]  (bias gradients; also d(pos-embed), d(type-embed)); n % 4 == 0
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x, int is_f32, long long ldx, float* __restrict__ out,
+                                                     int rows, int n, int rows_per_cta) {
+  const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c4 >= n) return;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0; r < r1; ++r) {
+    float4 v = is_f32 ? ld_f4(reinterpret_cast<const float*>(x) + (long long)r * ldx + c4)
+                      : ld_bf4(reinterpret_cast<const bf16*>(x) + (long long)r * ldx + c4);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  atomicAdd(out + c4, a.x); atomicAdd(out + c4 + 1, a.y); atomicAdd(out + c4 + 2, a.z); atomicAdd(out + c4 + 3, a.w);
+}
+
+// ------------------------------------------------------------------------------------------------ patch im2col
+// pixels f32 [B,3,R,R] -> patches bf16 [B*g*g, 3*P*P], column = c*P*P + i*P + j  (== conv1.weight.view(W, -1) order,
+// modeling_chineseclip.py:224,237).  P % 2 == 0.
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ pix, bf16* __restrict__ out, int B, int R, int P, int g) {
+  const int kdim = 3 * P * P;
+  const long long total2 = (long long)B * g * g * kdim / 2;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total2; t += (long long)gridDim.x * blockDim.x) {
+    const long long e = t * 2;
+    const int col = (int)(e % kdim);
+    const long long rowi = e / kdim;
+    const int px = (int)(rowi % g), py = (int)((rowi / g) % g), b = (int)(rowi / ((long long)g * g));
+    const int c = col / (P * P), i = (col / P) % P, j = col % P;
+    const float2 v = *reinterpret_cast<const float2*>(pix + (((long long)b * 3 + c) * R + (py * P + i)) * R + px * P + j);
+    *reinterpret_cast<uint32_t*>(out + e) = pack_bf16x2(v.x, v.y);
+  }
+}
+
+// x0[b, l, :] = (l == 0 ? class_embedding : patch[b, l-1, :]) + positional_embedding[l]   (modeling_chineseclip.py:238-241)
+__global__ void __launch_bounds__(256) vit_assemble_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                                                           const float* __restrict__ pos, float* __restrict__ x0, int B, int L, int W) {
+  const long long total4 = (long long)B * L * W / 4;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
+    const long long e = t * 4;
+    const int c = (int)(e % W);
+    const long long rl = e / W;
+    const int l = (int)(rl % L);
+    const long long b = rl / L;
+    float4 v = l == 0 ? ld_f4(cls + c) : ld_f4(patch + ((b * (L - 1) + (l - 1)) * W + c));
+    float4 p = ld_f4(pos + (long long)l * W + c);
+    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    st_f4(x0 + e, v);
+  }
+}
+// backward of the assembly: dpatch bf16 [B*(L-1), W] = dx0[b, 1+p, :]  (dpos / dcls are column sums taken by the host wrapper)
+__global__ void __launch_bounds__(256) vit_assemble_bwd_kernel(const float* __restrict__ dx0, bf16* __restrict__ dpatch, int B, int L, int W) {
+  const long long total4 = (long long)B * (L - 1) * W / 4;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
+    const long long e = t * 4;
+    const int c = (int)(e % W);
+    const long long rl = e / W;
+    const int p = (int)(rl % (L - 1));
+    const long long b = rl / (L - 1);
+    st_bf4(dpatch + e, ld_f4(dx0 + ((b * L + p + 1) * W + c)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BERT embeddings
+// e[b,l,:] = word[ids[b,l]] + type[0] + pos[l]       (modeling_bert.py:95-129; LN applied by layernorm_fwd)
+__global__ void __launch_bounds__(256) bert_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
+                                                         const float* __restrict__ pos, const float* __restrict__ type0,
+                                                         float* __restrict__ e, int rows, int L, int H, int vocab) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  long long id = ids[row];
+  if (id < 0 || id >= vocab) id = 0;  // host validates; never index out of the table
+  const int l = row % L;
+  for (int c = lane * 4; c < H; c += 128) {
+    float4 w = ld_f4(word + id * H + c), p = ld_f4(pos + (long long)l * H + c), t = ld_f4(type0 + c);
+    st_f4(e + (long long)row * H + c, make_float4(w.x + p.x + t.x, w.y + p.y + t.y, w.z + p.z + t.z, w.w + p.w + t.w));
+  }
+}
+// dword[ids] += de (row 0 = padding_idx gets no gradient, modeling_bert.py:77)
+__global__ void __launch_bounds__(256) bert_embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ de,
+                                                             float* __restrict__ dword, int rows, int H, int vocab) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long id = ids[row];
+  if (id <= 0 || id >= vocab) return;
+  for (int c = lane * 4; c < H; c += 128) {
+    float4 v = ld_f4(de + (long long)row * H + c);
+    atomicAdd(reinterpret_cast<float4*>(dword + id * H + c), v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ L2 normalise
+// y = x / ||x||  (modeling_chineseclip.py:360,363); bwd: dx = (dy - y * <dy, y>) / ||x||
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ norm_out,
+                                                         int rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane * 4; c < d; c += 128) { float4 v = ld_f4(x + (long long)row * d + c); s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+  const float nrm = sqrtf(warp_sum(s));
+  const float inv = 1.0f / nrm;
+  if (lane == 0 && norm_out) norm_out[row] = nrm;
+  for (int c = lane * 4; c < d; c += 128) {
+    float4 v = ld_f4(x + (long long)row * d + c);
+    st_f4(y + (long long)row * d + c, make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv));
+  }
+}
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ norm,
+                                                         float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16, int rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane * 4; c < d; c += 128) {
+    float4 a = ld_f4(dy + (long long)row * d + c), b = ld_f4(y + (long long)row * d + c);
+    s += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+  }
+  s = warp_sum(s);
+  const float inv = 1.0f / norm[row];
+  for (int c = lane * 4; c < d; c += 128) {
+    float4 a = ld_f4(dy + (long long)row * d + c), b = ld_f4(y + (long long)row * d + c);
+    float4 o = make_float4((a.x - b.x * s) * inv, (a.y - b.y * s) * inv, (a.z - b.z * s) * inv, (a.w - b.w * s) * inv);
+    if (dx_f32) st_f4(dx_f32 + (long long)row * d + c, o);
+    if (dx_bf16) st_bf4(dx_bf16 + (long long)row * d + c, o);
+  }
+}
+
+// f32 -> bf16 cast of a contiguous buffer (n % 4 == 0)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n4) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x)
+    st_bf4(y + t * 4, ld_f4(x + t * 4));
+}
+
+static inline int grid_for(long long work_items, int per_cta) {
+  long long g = (work_items + per_cta - 1) / per_cta;
+  long long cap = (long long)sm_count() * 8;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace clipk
+
+using namespace clipk;
+
+#define LN_DISPATCH(NV, ...)                                       \
+  switch (NV) {                                                    \
+    case 1: __VA_ARGS__(1); break; case 2: __VA_ARGS__(2); break;  \
+    case 3: __VA_ARGS__(3); break; case 4: __VA_ARGS__(4); break;  \
+    case 5: __VA_ARGS__(5); break; case 6: __VA_ARGS__(6); break;  \
+    case 7: __VA_ARGS__(7); break; case 8: __VA_ARGS__(8); break;  \
+    default: set_error("layernorm: d=%d unsupported (d %% 128 == 0, d <= 1024)", d); return CLIPK_ERR_UNSUPPORTED; }
+
+extern "C" int clipk_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y_bf16,
+                                   float* y_f32, float* mean, float* rstd, int rows, int d, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (d % 128 || d > 128 * LN_MAXV || (ldx % 4)) { set_error("layernorm_fwd: d=%d ldx=%lld unsupported", d, ldx); return CLIPK_ERR_UNSUPPORTED; }
+  const int nv = d / 128;
+  dim3 grid((rows + 7) / 8), block(256);
+#define LAUNCH(NV) layernorm_fwd_kernel<NV><<<grid, block, 0, stream>>>(x, ldx, gamma, beta, eps, (bf16*)y_bf16, y_f32, mean, rstd, rows, d)
+  LN_DISPATCH(nv, LAUNCH)
+#undef LAUNCH
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_layernorm_bwd(const void* dy, int dy_is_f32, const float* dy_add, const float* x, long long ldx, const float* gamma,
+                                   const float* mean, const float* rstd, const float* dx_add, float* dx_f32, long long lddx,
+                                   void* dx_bf16, float* dgamma, float* dbeta, float* dbias, int rows, int d, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (d % 128 || d > 128 * LN_MAXV || (ldx % 4) || (lddx % 4)) { set_error("layernorm_bwd: d=%d unsupported", d); return CLIPK_ERR_UNSUPPORTED; }
+  const int nv = d / 128;
+  int g = (rows + 7) / 8;
+  const int cap = sm_count() * 4;
+  if (g > cap) g = cap;
+  dim3 grid(g), block(256);
+#define LAUNCH(NV) layernorm_bwd_kernel<NV><<<grid, block, 0, stream>>>(dy, dy_is_f32, dy_add, x, ldx, gamma, mean, rstd, dx_add, dx_f32, lddx, (bf16*)dx_bf16, dgamma, dbeta, dbias, rows, d)
+  LN_DISPATCH(nv, LAUNCH)
+#undef LAUNCH
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_colsum(const void* x, int is_f32, long long ldx, float* out, int rows, int n, cudaStream_t stream) {
+  if (rows <= 0 || n <= 0) return 0;
+  if (n % 4 || ldx % 4) { set_error("colsum: n=%d ldx=%lld must be multiples of 4", n, ldx); return CLIPK_ERR_ARG; }
+  const int bx = (n / 4 + 255) / 256;
+  int by = (sm_count() * 8 + bx - 1) / bx;
+  int rows_per = (rows + by - 1) / by;
+  if (rows_per < 16) rows_per = 16;
+  by = (rows + rows_per - 1) / rows_per;
+  colsum_kernel<<<dim3(bx, by), 256, 0, stream>>>(x, is_f32, ldx, out, rows, n, rows_per);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_im2col_patches(const float* pixels, void* patches_bf16, int B, int R, int P, cudaStream_t stream) {
+  if (R % P || P % 2) { set_error("im2col: R=%d P=%d unsupported", R, P); return CLIPK_ERR_UNSUPPORTED; }
+  const int g = R / P;
+  const long long total2 = (long long)B * g * g * 3 * P * P / 2;
+  im2col_kernel<<<grid_for(total2, 256 * 4), 256, 0, stream>>>(pixels, (bf16*)patches_bf16, B, R, P, g);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_vit_assemble(const float* patch, const float* cls, const float* pos, float* x0, int B, int L, int W, cudaStream_t stream) {
+  if (W % 4) { set_error("vit_assemble: W %% 4 != 0"); return CLIPK_ERR_ARG; }
+  vit_assemble_kernel<<<grid_for((long long)B * L * W / 4, 256 * 4), 256, 0, stream>>>(patch, cls, pos, x0, B, L, W);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_vit_assemble_bwd(const float* dx0, void* dpatch_bf16, int B, int L, int W, cudaStream_t stream) {
+  if (W % 4) { set_error("vit_assemble_bwd: W %% 4 != 0"); return CLIPK_ERR_ARG; }
+  vit_assemble_bwd_kernel<<<grid_for((long long)B * (L - 1) * W / 4, 256 * 4), 256, 0, stream>>>(dx0, (bf16*)dpatch_bf16, B, L, W);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0, float* e, int rows, int L,
+                                int H, int vocab, cudaStream_t stream) {
+  if (H % 4) { set_error("bert_embed: H %% 4 != 0"); return CLIPK_ERR_ARG; }
+  bert_embed_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, word, pos, type0, e, rows, L, H, vocab);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_bert_embed_bwd(const long long* ids, const float* de, float* dword, int rows, int H, int vocab, cudaStream_t stream) {
+  if (H % 4) { set_error("bert_embed_bwd: H %% 4 != 0"); return CLIPK_ERR_ARG; }
+  bert_embed_bwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, de, dword, rows, H, vocab);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_l2norm_fwd(const float* x, float* y, float* norm, int rows, int d, cudaStream_t stream) {
+  if (d % 4) { set_error("l2norm: d %% 4 != 0"); return CLIPK_ERR_ARG; }
+  l2norm_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, y, norm, rows, d);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_l2norm_bwd(const float* dy, const float* y, const float* norm, float* dx_f32, void* dx_bf16, int rows, int d,
+                                cudaStream_t stream) {
+  if (d % 4) { set_error("l2norm: d %% 4 != 0"); return CLIPK_ERR_ARG; }
+  l2norm_bwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(dy, y, norm, dx_f32, (bf16*)dx_bf16, rows, d);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_cast_bf16(const float* x, void* y, long long n, cudaStream_t stream) {
+  if (n % 4) { set_error("cast_bf16: n %% 4 != 0"); return CLIPK_ERR_ARG; }
+  if (n == 0) return 0;
+  cast_bf16_kernel<<<grid_for(n / 4, 256 * 4), 256, 0, stream>>>(x, (bf16*)y, n / 4);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}

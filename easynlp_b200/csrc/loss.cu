@@ -1,0 +1,228 @@
+// Fused contrastive-logit strip kernels: logits = scale * Q K^T, row softmax cross-entropy against the diagonal
+// (label = label_offset + row), streamed over the gallery with an online log-sum-exp -- the [B_local, B_global]
+// matrix is only written when the caller asks for it (CLIPApp.forward returns logits_per_text).
+//   reference: appzoo/clip/model.py:148-149 (logits), :154-160 (clip_loss = (CE(S) + CE(S^T)) / 2)
+// fp32 CUDA-core math on purpose: the logits/loss parity budget (rtol 1e-3) does not survive bf16 embeddings,
+// and the op is 2*Bl*Bg*E flops (0.07 GF at B=256; 4.3 GF for a 512 x 4096 strip).
+// A CTA owns 32 rows (8 warps x 4 rows, rows cached in registers); the other operand is streamed through shared
+// memory in 32-row tiles.  A lane owns the float4 column groups {lane + 32 t}.
+#include "common.cuh"
+#include "../../include/clipk.h"
+
+namespace clipk {
+
+constexpr int CE_ROWS_PER_WARP = 4;
+constexpr int CE_WARPS = 8;
+constexpr int CE_ROWS = CE_ROWS_PER_WARP * CE_WARPS;  // 32
+constexpr int CE_TILE = 32;
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+template <int NV>
+__global__ void __launch_bounds__(256) ce_strip_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ logit_scale_log,
+                                                           int label_offset, float* __restrict__ S_out, long long lds, int transpose_out,
+                                                           float* __restrict__ lse_out, float* __restrict__ loss_rows, int nq, int nk, int E) {
+  extern __shared__ float ktile[];  // [CE_TILE][E]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float scale = __expf(*logit_scale_log);
+  const int row0 = blockIdx.x * CE_ROWS + warp * CE_ROWS_PER_WARP;
+  float4 q[CE_ROWS_PER_WARP][NV];
+#pragma unroll
+  for (int r = 0; r < CE_ROWS_PER_WARP; ++r)
+#pragma unroll
+    for (int t = 0; t < NV; ++t)
+      q[r][t] = (row0 + r < nq) ? *reinterpret_cast<const float4*>(Q + (long long)(row0 + r) * E + (lane + 32 * t) * 4) : make_float4(0, 0, 0, 0);
+  float mx[CE_ROWS_PER_WARP], sm[CE_ROWS_PER_WARP], lab[CE_ROWS_PER_WARP];
+#pragma unroll
+  for (int r = 0; r < CE_ROWS_PER_WARP; ++r) { mx[r] = -INFINITY; sm[r] = 0.f; lab[r] = 0.f; }
+
+  for (int k0 = 0; k0 < nk; k0 += CE_TILE) {
+    __syncthreads();
+    const int nrows = min(CE_TILE, nk - k0);
+    for (int idx = threadIdx.x; idx < nrows * (E / 4); idx += blockDim.x)
+      reinterpret_cast<float4*>(ktile)[idx] = reinterpret_cast<const float4*>(K + (long long)k0 * E)[idx];
+    __syncthreads();
+    for (int j = 0; j < nrows; ++j) {
+      float p[CE_ROWS_PER_WARP];
+#pragma unroll
+      for (int r = 0; r < CE_ROWS_PER_WARP; ++r) p[r] = 0.f;
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        const float4 kv = *reinterpret_cast<const float4*>(ktile + j * E + (lane + 32 * t) * 4);
+#pragma unroll
+        for (int r = 0; r < CE_ROWS_PER_WARP; ++r) p[r] += dot4(q[r][t], kv);
+      }
+#pragma unroll
+      for (int r = 0; r < CE_ROWS_PER_WARP; ++r) {
+        const float s = warp_sum(p[r]) * scale;
+        const int col = k0 + j;
+        if (col == label_offset + row0 + r) lab[r] = s;
+        if (s > mx[r]) { sm[r] = sm[r] * __expf(mx[r] - s) + 1.f; mx[r] = s; }
+        else sm[r] += __expf(s - mx[r]);
+        if (S_out && lane == 0 && row0 + r < nq) {
+          if (transpose_out) S_out[(long long)col * lds + row0 + r] = s;
+          else S_out[(long long)(row0 + r) * lds + col] = s;
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < CE_ROWS_PER_WARP; ++r)
+      if (row0 + r < nq) {
+        const float lse = mx[r] + __logf(sm[r]);
+        lse_out[row0 + r] = lse;
+        loss_rows[row0 + r] = lse - lab[r];
+      }
+  }
+}
+
+// Gradient of  coef * sum_i CE_i  w.r.t. the OWNED operand rows.
+//   own_is_query = 1: own = Q rows i (lse/label indexed by own row),   out_i += scale * sum_j dS_ij K_j
+//   own_is_query = 0: own = K rows j (lse/label indexed by streamed i), out_j += scale * sum_i dS_ij Q_i
+//   dS_ij = coef * (exp(s_ij - lse_i) - [j == label_offset + i]);  dscale_log += sum dS_ij * s_ij (query mode only)
+template <int NV>
+__global__ void __launch_bounds__(256) ce_strip_bwd_kernel(const float* __restrict__ OWN, const float* __restrict__ STR,
+                                                           const float* __restrict__ logit_scale_log, const float* __restrict__ lse,
+                                                           int label_offset, float coef, int own_is_query, float* __restrict__ out,
+                                                           int accumulate, float* __restrict__ dscale_log, int n_own, int n_str, int E) {
+  extern __shared__ float stile[];  // [CE_TILE][E]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float scale = __expf(*logit_scale_log);
+  const int row0 = blockIdx.x * CE_ROWS + warp * CE_ROWS_PER_WARP;
+  float4 o[CE_ROWS_PER_WARP][NV], acc[CE_ROWS_PER_WARP][NV];
+  float own_lse[CE_ROWS_PER_WARP];
+#pragma unroll
+  for (int r = 0; r < CE_ROWS_PER_WARP; ++r) {
+    own_lse[r] = (own_is_query && row0 + r < n_own) ? lse[row0 + r] : 0.f;
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+      o[r][t] = (row0 + r < n_own) ? *reinterpret_cast<const float4*>(OWN + (long long)(row0 + r) * E + (lane + 32 * t) * 4) : make_float4(0, 0, 0, 0);
+      acc[r][t] = make_float4(0, 0, 0, 0);
+    }
+  }
+  float dsc = 0.f;
+  for (int k0 = 0; k0 < n_str; k0 += CE_TILE) {
+    __syncthreads();
+    const int nrows = min(CE_TILE, n_str - k0);
+    for (int idx = threadIdx.x; idx < nrows * (E / 4); idx += blockDim.x)
+      reinterpret_cast<float4*>(stile)[idx] = reinterpret_cast<const float4*>(STR + (long long)k0 * E)[idx];
+    __syncthreads();
+    for (int j = 0; j < nrows; ++j) {
+      float p[CE_ROWS_PER_WARP];
+      float4 sv[NV];
+#pragma unroll
+      for (int r = 0; r < CE_ROWS_PER_WARP; ++r) p[r] = 0.f;
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        sv[t] = *reinterpret_cast<const float4*>(stile + j * E + (lane + 32 * t) * 4);
+#pragma unroll
+        for (int r = 0; r < CE_ROWS_PER_WARP; ++r) p[r] += dot4(o[r][t], sv[t]);
+      }
+      const int sidx = k0 + j;
+      const float str_lse = own_is_query ? 0.f : lse[sidx];
+#pragma unroll
+      for (int r = 0; r < CE_ROWS_PER_WARP; ++r) {
+        const float s = warp_sum(p[r]) * scale;
+        const int own_idx = row0 + r;
+        const int qi = own_is_query ? own_idx : sidx;
+        const int kj = own_is_query ? sidx : own_idx;
+        const float l = own_is_query ? own_lse[r] : str_lse;
+        float ds = coef * (__expf(s - l) - ((kj == label_offset + qi) ? 1.f : 0.f));
+        if (own_idx >= n_own) ds = 0.f;
+        dsc += ds * s;
+        const float w = ds * scale;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+          acc[r][t].x += w * sv[t].x; acc[r][t].y += w * sv[t].y; acc[r][t].z += w * sv[t].z; acc[r][t].w += w * sv[t].w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < CE_ROWS_PER_WARP; ++r)
+    if (row0 + r < n_own)
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        float4* dst = reinterpret_cast<float4*>(out + (long long)(row0 + r) * E + (lane + 32 * t) * 4);
+        float4 v = acc[r][t];
+        if (accumulate) { float4 c = *dst; v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
+        *dst = v;
+      }
+  if (own_is_query && dscale_log && lane == 0) atomicAdd(dscale_log, dsc);  // dsc identical on all lanes
+}
+
+// out[0] (+)= scale * sum(x[0:n])   single CTA, deterministic order
+__global__ void __launch_bounds__(256) reduce_sum_kernel(const float* __restrict__ x, int n, float scale, float* __restrict__ out, int accumulate) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[0] = (accumulate ? out[0] : 0.f) + t * scale;
+  }
+}
+
+}  // namespace clipk
+
+using namespace clipk;
+
+#define CE_DISPATCH(NV, ...)                                        \
+  switch (NV) {                                                     \
+    case 1: __VA_ARGS__(1); break; case 2: __VA_ARGS__(2); break;   \
+    case 4: __VA_ARGS__(4); break; case 6: __VA_ARGS__(6); break;   \
+    case 8: __VA_ARGS__(8); break;                                  \
+    default: set_error("clip_ce: embed dim %d unsupported (128,256,512,768,1024)", E); return CLIPK_ERR_UNSUPPORTED; }
+
+extern "C" int clipk_ce_strip_fwd(const float* Q, const float* K, const float* logit_scale_log, int label_offset, float* S_out,
+                                  long long lds, int transpose_out, float* lse, float* loss_rows, int nq, int nk, int E,
+                                  cudaStream_t stream) {
+  if (nq <= 0 || nk <= 0) return 0;
+  if (E % 128) { set_error("clip_ce: E %% 128 != 0"); return CLIPK_ERR_UNSUPPORTED; }
+  const int nv = E / 128;
+  const int smem = CE_TILE * E * 4;
+  dim3 grid((nq + CE_ROWS - 1) / CE_ROWS);
+#define LAUNCH(NV)                                                                                                         \
+  {                                                                                                                        \
+    static bool cfg = false;                                                                                               \
+    if (!cfg) { CLIPK_CUDA(cudaFuncSetAttribute(ce_strip_fwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072)); cfg = true; } \
+    ce_strip_fwd_kernel<NV><<<grid, 256, smem, stream>>>(Q, K, logit_scale_log, label_offset, S_out, lds, transpose_out, lse, loss_rows, nq, nk, E); \
+  }
+  CE_DISPATCH(nv, LAUNCH)
+#undef LAUNCH
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_ce_strip_bwd(const float* own, const float* streamed, const float* logit_scale_log, const float* lse, int label_offset,
+                                  float coef, int own_is_query, float* out, int accumulate, float* dscale_log, int n_own, int n_streamed,
+                                  int E, cudaStream_t stream) {
+  if (n_own <= 0 || n_streamed <= 0) return 0;
+  if (E % 128) { set_error("clip_ce: E %% 128 != 0"); return CLIPK_ERR_UNSUPPORTED; }
+  const int nv = E / 128;
+  const int smem = CE_TILE * E * 4;
+  dim3 grid((n_own + CE_ROWS - 1) / CE_ROWS);
+#define LAUNCH(NV)                                                                                                         \
+  {                                                                                                                        \
+    static bool cfg = false;                                                                                               \
+    if (!cfg) { CLIPK_CUDA(cudaFuncSetAttribute(ce_strip_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072)); cfg = true; } \
+    ce_strip_bwd_kernel<NV><<<grid, 256, smem, stream>>>(own, streamed, logit_scale_log, lse, label_offset, coef, own_is_query, out, accumulate, dscale_log, n_own, n_streamed, E); \
+  }
+  CE_DISPATCH(nv, LAUNCH)
+#undef LAUNCH
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_reduce_sum(const float* x, int n, float scale, float* out, int accumulate, cudaStream_t stream) {
+  reduce_sum_kernel<<<1, 256, 0, stream>>>(x, n, scale, out, accumulate);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}

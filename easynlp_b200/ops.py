@@ -5,6 +5,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
+L_ = L
 
 
 def _ptr(t):
@@ -51,3 +52,120 @@ def gemm(a, b, out, *, a_mn_major=0, b_mn_major=0, mode=L.EPI_LINEAR, bias=None,
     L.check(L.lib().clipk_gemm_bf16(_ptr(a), a.stride(0), int(a_mn_major), _ptr(b), b.stride(0), int(b_mn_major),
                                     M, N, K, C.byref(e), int(splits), _stream()), "clipk_gemm_bf16")
     return out
+
+
+def _f32(t):
+    assert t is None or (t.dtype == torch.float32 and t.is_cuda), "expected a CUDA float32 tensor"
+    return _ptr(t)
+
+
+def _b16(t):
+    assert t is None or (t.dtype == torch.bfloat16 and t.is_cuda), "expected a CUDA bfloat16 tensor"
+    return _ptr(t)
+
+
+def attention_fwd(qkv, key_mask, ctx, lse, B, L, H):
+    d = H * 64
+    assert qkv.shape == (B * L, 3 * d) and qkv.is_contiguous() and ctx.shape == (B * L, d) and ctx.is_contiguous()
+    assert lse.numel() == B * H * L
+    L_.check(L_.lib().clipk_attention_fwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), B, L, H, d, _stream()), "attention_fwd")
+
+
+def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H):
+    d = H * 64
+    assert dqkv.shape == (B * L, 3 * d) and dqkv.is_contiguous() and dctx.shape == (B * L, d) and dctx.is_contiguous()
+    L_.check(L_.lib().clipk_attention_bwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), _b16(dctx), _b16(dqkv), B, L, H, d,
+                                          _stream()), "attention_bwd")
+
+
+def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None, rows=None, ldx=None):
+    d = gamma.numel()
+    if rows is None:
+        rows = x.numel() // d
+    if ldx is None:
+        ldx = d
+    L_.check(L_.lib().clipk_layernorm_fwd(_f32(x), ldx, _f32(gamma), _f32(beta), eps, _b16(y_bf16), _f32(y_f32), _f32(mean),
+                                          _f32(rstd), rows, d, _stream()), "layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, *, dy_add=None, dx_add=None, dx_f32=None, dx_bf16=None, dgamma=None, dbeta=None,
+                  dbias=None, rows=None, ldx=None, lddx=None):
+    d = gamma.numel()
+    if rows is None:
+        rows = mean.numel()
+    ldx = d if ldx is None else ldx
+    lddx = d if lddx is None else lddx
+    is_f32 = int(dy.dtype == torch.float32)
+    assert dy.dtype in (torch.float32, torch.bfloat16)
+    L_.check(L_.lib().clipk_layernorm_bwd(_ptr(dy), is_f32, _f32(dy_add), _f32(x), ldx, _f32(gamma), _f32(mean), _f32(rstd),
+                                          _f32(dx_add), _f32(dx_f32), lddx, _b16(dx_bf16), _f32(dgamma), _f32(dbeta),
+                                          _f32(dbias), rows, d, _stream()), "layernorm_bwd")
+
+
+def colsum(x, out, rows, n, ldx=None):
+    ldx = n if ldx is None else ldx
+    L_.check(L_.lib().clipk_colsum(_ptr(x), int(x.dtype == torch.float32), ldx, _f32(out), rows, n, _stream()), "colsum")
+
+
+def im2col_patches(pixels, patches, B, R, P):
+    L_.check(L_.lib().clipk_im2col_patches(_f32(pixels), _b16(patches), B, R, P, _stream()), "im2col")
+
+
+def vit_assemble(patch, cls, pos, x0, B, L, W):
+    L_.check(L_.lib().clipk_vit_assemble(_f32(patch), _f32(cls), _f32(pos), _f32(x0), B, L, W, _stream()), "vit_assemble")
+
+
+def vit_assemble_bwd(dx0, dpatch, B, L, W):
+    L_.check(L_.lib().clipk_vit_assemble_bwd(_f32(dx0), _b16(dpatch), B, L, W, _stream()), "vit_assemble_bwd")
+
+
+def bert_embed(ids, word, pos, type0, e, rows, L, H, vocab):
+    assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous()
+    L_.check(L_.lib().clipk_bert_embed(_ptr(ids), _f32(word), _f32(pos), _f32(type0), _f32(e), rows, L, H, vocab, _stream()),
+             "bert_embed")
+
+
+def bert_embed_bwd(ids, de, dword, rows, H, vocab):
+    L_.check(L_.lib().clipk_bert_embed_bwd(_ptr(ids), _f32(de), _f32(dword), rows, H, vocab, _stream()), "bert_embed_bwd")
+
+
+def l2norm_fwd(x, y, norm, rows, d):
+    L_.check(L_.lib().clipk_l2norm_fwd(_f32(x), _f32(y), _f32(norm), rows, d, _stream()), "l2norm_fwd")
+
+
+def l2norm_bwd(dy, y, norm, dx_f32, dx_bf16, rows, d):
+    L_.check(L_.lib().clipk_l2norm_bwd(_f32(dy), _f32(y), _f32(norm), _f32(dx_f32), _b16(dx_bf16), rows, d, _stream()), "l2norm_bwd")
+
+
+def cast_bf16(x, y):
+    assert x.numel() == y.numel()
+    L_.check(L_.lib().clipk_cast_bf16(_f32(x), _b16(y), x.numel(), _stream()), "cast_bf16")
+
+
+def ce_strip_fwd(Q, K, logit_scale_log, label_offset, lse, loss_rows, S_out=None, lds=0, transpose_out=False):
+    nq, E = Q.shape
+    nk = K.shape[0]
+    L_.check(L_.lib().clipk_ce_strip_fwd(_f32(Q), _f32(K), _f32(logit_scale_log), label_offset, _f32(S_out), lds,
+                                         int(transpose_out), _f32(lse), _f32(loss_rows), nq, nk, E, _stream()), "ce_strip_fwd")
+
+
+def ce_strip_bwd(own, streamed, logit_scale_log, lse, label_offset, coef, own_is_query, out, accumulate, dscale_log=None):
+    n_own, E = own.shape
+    L_.check(L_.lib().clipk_ce_strip_bwd(_f32(own), _f32(streamed), _f32(logit_scale_log), _f32(lse), label_offset, coef,
+                                         int(own_is_query), _f32(out), int(accumulate), _f32(dscale_log), n_own,
+                                         streamed.shape[0], E, _stream()), "ce_strip_bwd")
+
+
+def reduce_sum(x, n, scale, out, accumulate=False):
+    L_.check(L_.lib().clipk_reduce_sum(_f32(x), n, scale, _f32(out), int(accumulate), _stream()), "reduce_sum")
+
+
+def grad_norm(g, n, max_norm, workspace, norm_and_coef):
+    assert workspace.dtype == torch.float64
+    L_.check(L_.lib().clipk_grad_norm(_f32(g), n, max_norm, _ptr(workspace), workspace.numel(), _f32(norm_and_coef), _stream()),
+             "grad_norm")
+
+
+def adamw_step(p, g, m, v, w_bf16, n, lr, weight_decay, step, clip_coef=None, beta1=0.9, beta2=0.999, eps=1e-6):
+    L_.check(L_.lib().clipk_adamw_step(_f32(p), _f32(g), _f32(m), _f32(v), _b16(w_bf16), n, lr, beta1, beta2, eps, weight_decay,
+                                       step, _f32(clip_coef), _stream()), "adamw_step")

@@ -72,6 +72,77 @@ typedef struct {
 int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N, int K,
                     const clipk_epilogue_t* epi, int splits, cudaStream_t stream);
 
+/* -------------------------------------------------------------------------------------------- attention
+ * Fused softmax(Q K^T / 8 + key_mask) V for head dim 64 on packed projections qkv[B*L, 3d] (Q|K|V blocks, head h at
+ * columns h*64).  Replaces nn.MultiheadAttention's SDPA (modeling_chineseclip.py:188,198-200) and BertSelfAttention
+ * (modeling_bert.py:210-244, additive mask from modeling_utils.py:438-439).  L <= 256.
+ * key_mask: optional f32 [B, L] additive (0 / -10000).  lse: f32 [B, H, L] saved for backward.                  */
+int clipk_attention_fwd(const void* qkv, const float* key_mask, void* ctx, float* lse, int B, int L, int H, int d,
+                        cudaStream_t stream);
+/* dqkv[B*L, 3d] (bf16) from dctx[B*L, d] (bf16); ctx / lse are the forward outputs.                             */
+int clipk_attention_bwd(const void* qkv, const float* key_mask, const void* ctx, const float* lse, const void* dctx,
+                        void* dqkv, int B, int L, int H, int d, cudaStream_t stream);
+
+/* -------------------------------------------------------------------------------------------- LayerNorm
+ * y = (x - mean) * rstd * gamma + beta over the last dim d (d % 128 == 0, d <= 1024), fp32 statistics
+ * (modeling_chineseclip.py:170-176 eps 1e-5; nn.LayerNorm eps 1e-12 in modeling_bert.py:84,266,344).
+ * x: f32 rows with stride ldx; y_bf16 / y_f32 / mean / rstd optional outputs (contiguous).                     */
+int clipk_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y_bf16,
+                        float* y_f32, float* mean, float* rstd, int rows, int d, cudaStream_t stream);
+/* g = dy (+ dy_add); dx = LN'(g) (+ dx_add) -> dx_f32 (stride lddx) / dx_bf16; dgamma, dbeta, dbias(=colsum dx) are
+ * ACCUMULATED with fp32 atomics (optional).                                                                     */
+int clipk_layernorm_bwd(const void* dy, int dy_is_f32, const float* dy_add, const float* x, long long ldx,
+                        const float* gamma, const float* mean, const float* rstd, const float* dx_add, float* dx_f32,
+                        long long lddx, void* dx_bf16, float* dgamma, float* dbeta, float* dbias, int rows, int d,
+                        cudaStream_t stream);
+
+/* out[n] += sum over rows of x[rows, n] (bf16 or f32, row stride ldx): bias / positional / token-type gradients */
+int clipk_colsum(const void* x, int is_f32, long long ldx, float* out, int rows, int n, cudaStream_t stream);
+
+/* -------------------------------------------------------------------------------------------- embeddings
+ * ViT patch embed (modeling_chineseclip.py:224,237-241): pixels f32 [B,3,R,R] -> bf16 patches [B*g*g, 3*P*P]
+ * (column order of conv1.weight.view(W,-1)); then a GEMM; then token assembly x0 = [cls | patches] + pos.       */
+int clipk_im2col_patches(const float* pixels, void* patches_bf16, int B, int R, int P, cudaStream_t stream);
+int clipk_vit_assemble(const float* patch_f32, const float* cls, const float* pos, float* x0, int B, int L, int W,
+                       cudaStream_t stream);
+int clipk_vit_assemble_bwd(const float* dx0, void* dpatch_bf16, int B, int L, int W, cudaStream_t stream);
+/* BERT embeddings (modeling_bert.py:95-129): e = word[ids] + type[0] + pos[l]; backward scatters into dword
+ * (row 0 = padding_idx receives no gradient).  ids: int64 [rows] on device.                                     */
+int clipk_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0, float* e, int rows,
+                     int L, int H, int vocab, cudaStream_t stream);
+int clipk_bert_embed_bwd(const long long* ids, const float* de, float* dword, int rows, int H, int vocab,
+                         cudaStream_t stream);
+
+/* -------------------------------------------------------------------------------------------- head
+ * y = x / ||x||_2 per row (modeling_chineseclip.py:360,363) and its backward.                                   */
+int clipk_l2norm_fwd(const float* x, float* y, float* norm, int rows, int d, cudaStream_t stream);
+int clipk_l2norm_bwd(const float* dy, const float* y, const float* norm, float* dx_f32, void* dx_bf16, int rows, int d,
+                     cudaStream_t stream);
+int clipk_cast_bf16(const float* x, void* y_bf16, long long n, cudaStream_t stream);
+
+/* -------------------------------------------------------------------------------------------- contrastive loss
+ * One strip of the symmetric InfoNCE (appzoo/clip/model.py:148-164): logits = exp(logit_scale_log) * Q K^T for
+ * nq local queries against nk gallery rows, label(i) = label_offset + i; online log-sum-exp, logits optionally
+ * written (S_out[i*lds + j], or [j*lds + i] if transpose_out).  loss_rows[i] = lse_i - logit_{i,label}.         */
+int clipk_ce_strip_fwd(const float* Q, const float* K, const float* logit_scale_log, int label_offset, float* S_out,
+                       long long lds, int transpose_out, float* lse, float* loss_rows, int nq, int nk, int E,
+                       cudaStream_t stream);
+/* gradient of coef * sum_i CE_i w.r.t. the OWNED rows: own_is_query=1 -> d/dQ (lse indexed by own rows),
+ * own_is_query=0 -> d/dK (lse indexed by streamed rows).  out (+)= ...; dscale_log += sum dS*S (query mode).    */
+int clipk_ce_strip_bwd(const float* own, const float* streamed, const float* logit_scale_log, const float* lse,
+                       int label_offset, float coef, int own_is_query, float* out, int accumulate, float* dscale_log,
+                       int n_own, int n_streamed, int E, cudaStream_t stream);
+int clipk_reduce_sum(const float* x, int n, float scale, float* out, int accumulate, cudaStream_t stream);
+
+/* -------------------------------------------------------------------------------------------- optimizer
+ * Global-norm clip (core/trainer.py:325) + the reference AdamW (core/optimizers.py:437-462) over a flat buffer.
+ * norm_and_coef[0] = ||g||_2, [1] = min(1, max_norm / (norm + 1e-6)).  workspace: doubles, len >= 4*#SM.        */
+int clipk_grad_norm(const float* g, long long n, float max_norm, double* workspace, int workspace_len,
+                    float* norm_and_coef, cudaStream_t stream);
+/* p, m, v updated in place; w_bf16 (optional) = bf16(p) refreshed for the GEMMs; clip_coef optional device scalar */
+int clipk_adamw_step(float* p, const float* g, float* m, float* v, void* w_bf16, long long n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, const float* clip_coef, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,257 @@
+"""GPU unit tests: every clipk kernel (through the C ABI) against a plain PyTorch fp32 restatement of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from easynlp_b200 import _lib as L  # noqa: E402
+from easynlp_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return torch.randn(*shape, generator=g, device=DEV) * scale
+
+
+def assert_close(a, b, rtol, atol, name=""):
+    a = a.float(); b = b.float()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    assert not bool(bad.any()), f"{name}: {int(bad.sum())}/{bad.numel()} bad, max err {err.max().item():.4g}, ref max {b.abs().max().item():.4g}"
+
+
+# --------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [
+    (128, 128, 64, 0, 0), (300, 384, 192, 0, 0), (1576, 2304, 768, 0, 0), (616, 768, 3072, 0, 0),
+    (1576, 768, 3072, 0, 1), (200, 128, 512, 0, 1), (768, 768, 1576, 1, 1), (2304, 768, 616, 1, 1), (128, 512, 8, 1, 1),
+    (8, 512, 768, 0, 1), (256, 128, 136, 1, 0),
+])
+def test_gemm_variants(M, N, K, a_mn, b_mn):
+    A = rnd(M, K, seed=1).bfloat16(); B = rnd(N, K, seed=2).bfloat16()
+    ref = A.float() @ B.float().t()
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(a, b, out, a_mn_major=a_mn, b_mn_major=b_mn)
+    assert_close(out, ref, 1e-3, 1e-3 * math.sqrt(K), "gemm")
+
+
+def test_gemm_splitk_accumulates():
+    M, N, K = 768, 3072, 1576
+    A = rnd(M, K, seed=3).bfloat16(); B = rnd(N, K, seed=4).bfloat16()
+    base = rnd(M, N, seed=5)
+    out = base.clone()
+    ops.gemm(A.t().contiguous(), B.t().contiguous(), out, a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD, splits=7)
+    assert_close(out, base + A.float() @ B.float().t(), 1e-3, 1e-3 * math.sqrt(K), "splitk")
+
+
+def test_gemm_epilogues():
+    M, N, K = 394, 512, 256
+    A = rnd(M, K, seed=6).bfloat16(); W = rnd(N, K, seed=7, scale=0.1).bfloat16()
+    bias = rnd(N, seed=8); res = rnd(M, N, seed=9)
+    acc = A.float() @ W.float().t()
+    # linear + bias + residual -> f32 (+ bf16 shadow)
+    out = torch.empty(M, N, device=DEV); out2 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, W, out, bias=bias, residual=res, out2=out2)
+    assert_close(out, acc + bias + res, 1e-3, 2e-2, "linear")
+    assert_close(out2, acc + bias + res, 1e-2, 2e-2, "linear-bf16")
+    # bf16 out with alpha
+    ob = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, W, ob, bias=bias, alpha=0.5)
+    assert_close(ob, 0.5 * acc + bias, 1e-2, 2e-2, "alpha")
+    # GELUs
+    for mode, fn in ((L.EPI_QUICK_GELU, lambda z: z * torch.sigmoid(1.702 * z)), (L.EPI_ERF_GELU, torch.nn.functional.gelu)):
+        z = torch.empty(M, N, device=DEV, dtype=torch.bfloat16); a = torch.empty_like(z)
+        ops.gemm(A, W, z, bias=bias, mode=mode, out2=a)
+        assert_close(z, acc + bias, 1e-2, 2e-2, "z")
+        assert_close(a, fn(z.float()), 1e-2, 1e-2, "act")
+    # dGELUs
+    zb = (acc + bias).bfloat16()
+    for mode, fn in ((L.EPI_DQUICK_GELU, lambda z: z * torch.sigmoid(1.702 * z)), (L.EPI_DERF_GELU, torch.nn.functional.gelu)):
+        zz = zb.float().requires_grad_(True)
+        fn(zz).backward(acc)
+        o = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        ops.gemm(A, W, o, mode=mode, aux=zb)
+        assert_close(o, zz.grad, 2e-2, 3e-2, "dgelu")
+
+
+# --------------------------------------------------------------------------------------------- attention
+def attn_ref(qkv, mask, B, L, H):
+    d = H * 64
+    q, k, v = qkv.float().view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / 8.0
+    if mask is not None:
+        s = s + mask[:, None, None, :]
+    p = s.softmax(-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(B * L, d)
+    return o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,L,H,masked", [(2, 197, 12, False), (3, 77, 12, True), (2, 17, 2, False), (2, 16, 2, True), (1, 256, 2, False), (2, 128, 1, True)])
+def test_attention_fwd_bwd(B, L, H, masked):
+    d = H * 64
+    qkv = rnd(B * L, 3 * d, seed=11, scale=1.5).bfloat16()
+    mask = None
+    if masked:
+        lens = torch.randint(max(1, L // 4), L + 1, (B,), device=DEV)
+        mask = ((torch.arange(L, device=DEV)[None, :] >= lens[:, None]).float() * -10000.0).contiguous()
+    ctx = torch.zeros(B * L, d, device=DEV, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, L, device=DEV)
+    ops.attention_fwd(qkv, mask, ctx, lse, B, L, H)
+    qf = qkv.float().requires_grad_(True)
+    o_ref, lse_ref = attn_ref(qf, mask, B, L, H)
+    assert_close(ctx, o_ref, 2e-2, 2e-2, "ctx")
+    assert_close(lse, lse_ref, 1e-3, 1e-2, "lse")
+    dctx = rnd(B * L, d, seed=12).bfloat16()
+    o_ref.backward(dctx.float())
+    dqkv = torch.zeros(B * L, 3 * d, device=DEV, dtype=torch.bfloat16)
+    ops.attention_bwd(qkv, mask, ctx, lse, dctx, dqkv, B, L, H)
+    ref = qf.grad
+    scale = ref.abs().max().item()
+    assert_close(dqkv, ref, 3e-2, 2e-2 * scale, "dqkv")
+
+
+# --------------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,d,eps", [(394, 768, 1e-5), (77, 768, 1e-12), (33, 128, 1e-5), (20, 1024, 1e-5)])
+def test_layernorm_fwd_bwd(rows, d, eps):
+    x = rnd(rows, d, seed=21, scale=2.0) + 0.5
+    g = 1 + 0.1 * rnd(d, seed=22); b = 0.1 * rnd(d, seed=23)
+    yb = torch.empty(rows, d, device=DEV, dtype=torch.bfloat16); yf = torch.empty(rows, d, device=DEV)
+    mean = torch.empty(rows, device=DEV); rstd = torch.empty(rows, device=DEV)
+    ops.layernorm_fwd(x, g, b, eps, yb, yf, mean, rstd)
+    xr = x.clone().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (d,), gr, br, eps)
+    assert_close(yf, ref, 1e-4, 1e-4, "ln y")
+    assert_close(yb, ref, 1e-2, 1e-2, "ln y bf16")
+    dy = rnd(rows, d, seed=24); dy_add = rnd(rows, d, seed=25); dx_add = rnd(rows, d, seed=26)
+    ref.backward(dy + dy_add)
+    dxf = torch.empty(rows, d, device=DEV); dxb = torch.empty(rows, d, device=DEV, dtype=torch.bfloat16)
+    dg = torch.zeros(d, device=DEV); db = torch.zeros(d, device=DEV); dbias = torch.zeros(d, device=DEV)
+    ops.layernorm_bwd(dy, x, g, mean, rstd, dy_add=dy_add, dx_add=dx_add, dx_f32=dxf, dx_bf16=dxb, dgamma=dg, dbeta=db, dbias=dbias)
+    assert_close(dxf, xr.grad + dx_add, 1e-3, 1e-3, "ln dx")
+    assert_close(dxb, xr.grad + dx_add, 1e-2, 2e-2, "ln dx bf16")
+    assert_close(dg, gr.grad, 1e-3, 1e-3 * math.sqrt(rows), "ln dgamma")
+    assert_close(db, br.grad, 1e-3, 1e-3 * math.sqrt(rows), "ln dbeta")
+    assert_close(dbias, (xr.grad + dx_add).sum(0), 1e-3, 1e-3 * math.sqrt(rows), "ln dbias")
+    # bf16 dy, strided x rows (CLS pooling)
+    L_ = 5
+    xs = rnd(rows * L_, d, seed=27)
+    ops.layernorm_fwd(xs, g, b, eps, yb, None, mean, rstd, rows=rows, ldx=L_ * d)
+    assert_close(yb, torch.nn.functional.layer_norm(xs.view(rows, L_, d)[:, 0], (d,), g, b, eps), 1e-2, 1e-2, "ln strided")
+
+
+def test_colsum():
+    x = rnd(1000, 768, seed=31)
+    out = torch.ones(768, device=DEV)
+    ops.colsum(x, out, 1000, 768)
+    assert_close(out, 1 + x.sum(0), 1e-4, 1e-3, "colsum f32")
+    xb = x.bfloat16()
+    out.zero_()
+    ops.colsum(xb, out, 1000, 768)
+    assert_close(out, xb.float().sum(0), 1e-4, 1e-3, "colsum bf16")
+
+
+# --------------------------------------------------------------------------------------------- embeddings
+def test_vit_patch_pipeline():
+    B, R, P, W = 3, 64, 16, 128
+    g = R // P; Lv = g * g + 1
+    pix = rnd(B, 3, R, R, seed=41)
+    patches = torch.empty(B * g * g, 3 * P * P, device=DEV, dtype=torch.bfloat16)
+    ops.im2col_patches(pix, patches, B, R, P)
+    ref = torch.nn.functional.unfold(pix, P, stride=P).transpose(1, 2).reshape(B * g * g, 3 * P * P)
+    assert_close(patches, ref, 1e-2, 1e-2, "im2col")
+    patch_out = rnd(B * g * g, W, seed=42); cls = rnd(W, seed=43); pos = rnd(Lv, W, seed=44)
+    x0 = torch.empty(B * Lv, W, device=DEV)
+    ops.vit_assemble(patch_out, cls, pos, x0, B, Lv, W)
+    refx = torch.cat([cls.expand(B, 1, W), patch_out.view(B, g * g, W)], 1) + pos
+    assert_close(x0.view(B, Lv, W), refx, 1e-6, 1e-6, "assemble")
+    dp = torch.empty(B * g * g, W, device=DEV, dtype=torch.bfloat16)
+    ops.vit_assemble_bwd(x0, dp, B, Lv, W)
+    assert_close(dp.view(B, g * g, W), x0.view(B, Lv, W)[:, 1:], 1e-2, 1e-2, "assemble bwd")
+
+
+def test_bert_embed():
+    B, Lt, H, V = 4, 16, 128, 512
+    ids = torch.randint(0, V, (B, Lt), device=DEV)
+    ids[:, -3:] = 0
+    word = rnd(V, H, seed=51); pos = rnd(64, H, seed=52); typ = rnd(2, H, seed=53)
+    e = torch.empty(B * Lt, H, device=DEV)
+    ops.bert_embed(ids.view(-1), word, pos, typ, e, B * Lt, Lt, H, V)
+    assert_close(e.view(B, Lt, H), word[ids] + pos[:Lt] + typ[0], 1e-6, 1e-6, "embed")
+    de = rnd(B * Lt, H, seed=54)
+    dword = torch.zeros(V, H, device=DEV)
+    ops.bert_embed_bwd(ids.view(-1), de, dword, B * Lt, H, V)
+    ref = torch.zeros(V, H, device=DEV).index_add_(0, ids.view(-1), de)
+    ref[0] = 0
+    assert_close(dword, ref, 1e-5, 1e-5, "embed bwd")
+
+
+def test_l2norm():
+    x = rnd(37, 512, seed=61)
+    y = torch.empty_like(x); n = torch.empty(37, device=DEV)
+    ops.l2norm_fwd(x, y, n, 37, 512)
+    xr = x.clone().requires_grad_(True)
+    ref = xr / xr.norm(dim=-1, keepdim=True)
+    assert_close(y, ref, 1e-5, 1e-6, "l2norm")
+    dy = rnd(37, 512, seed=62)
+    ref.backward(dy)
+    dx = torch.empty_like(x); dxb = torch.empty(37, 512, device=DEV, dtype=torch.bfloat16)
+    ops.l2norm_bwd(dy, y, n, dx, dxb, 37, 512)
+    assert_close(dx, xr.grad, 1e-4, 1e-6, "l2norm bwd")
+
+
+# --------------------------------------------------------------------------------------------- loss
+@pytest.mark.parametrize("nq,nk,E,off", [(8, 8, 512, 0), (50, 200, 64 * 2, 100), (256, 256, 512, 0), (33, 70, 768, 7)])
+def test_ce_strip(nq, nk, E, off):
+    Q = torch.nn.functional.normalize(rnd(nq, E, seed=71), dim=-1)
+    K = torch.nn.functional.normalize(rnd(nk, E, seed=72), dim=-1)
+    ls = torch.tensor(math.log(1 / 0.07), device=DEV)
+    lse = torch.empty(nq, device=DEV); rows = torch.empty(nq, device=DEV)
+    S = torch.empty(nq, nk, device=DEV); St = torch.empty(nk, nq, device=DEV)
+    ops.ce_strip_fwd(Q, K, ls, off, lse, rows, S_out=S, lds=nk)
+    ops.ce_strip_fwd(Q, K, ls, off, lse, rows, S_out=St, lds=nq, transpose_out=True)
+    Qr = Q.clone().requires_grad_(True); Kr = K.clone().requires_grad_(True); lr = ls.clone().requires_grad_(True)
+    Sr = (Qr @ Kr.t()) * lr.exp()
+    lab = off + torch.arange(nq, device=DEV)
+    per = torch.nn.functional.cross_entropy(Sr, lab, reduction="none")
+    assert_close(S, Sr, 1e-5, 1e-5, "S")
+    assert_close(St.t(), Sr, 1e-5, 1e-5, "S^T")
+    assert_close(rows, per, 1e-4, 1e-5, "per-row CE")
+    assert_close(lse, torch.logsumexp(Sr, -1), 1e-5, 1e-5, "lse")
+    coef = 0.37
+    (per.sum() * coef).backward()
+    dQ = torch.ones(nq, E, device=DEV); dK = torch.zeros(nk, E, device=DEV); dls = torch.zeros(1, device=DEV)
+    ops.ce_strip_bwd(Q, K, ls, lse, off, coef, True, dQ, True, dls)
+    ops.ce_strip_bwd(K, Q, ls, lse, off, coef, False, dK, False)
+    assert_close(dQ - 1, Qr.grad, 1e-3, 1e-5, "dQ")
+    assert_close(dK, Kr.grad, 1e-3, 1e-5, "dK")
+    assert_close(dls, lr.grad.view(1), 1e-3, 1e-4, "dscale")
+    tot = torch.zeros(1, device=DEV)
+    ops.reduce_sum(rows, nq, 0.5, tot)
+    assert_close(tot, per.sum().view(1) * 0.5, 1e-5, 1e-5, "reduce")
+
+
+# --------------------------------------------------------------------------------------------- optimizer
+def test_adamw_and_gradnorm():
+    from oracle import clip_oracle as O
+    n = 4096 * 3 + 8
+    p = rnd(n, seed=81); g = rnd(n, seed=82, scale=0.01)
+    m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
+    wb = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    ws = torch.empty(1024, device=DEV, dtype=torch.float64); nc = torch.empty(2, device=DEV)
+    pr, mr, vr = p.cpu().clone(), m.cpu().clone(), v.cpu().clone()
+    for step in (1, 2, 3):
+        ops.grad_norm(g, n, 1.0, ws, nc)
+        gc = g.cpu().clone()
+        tot = O.clip_grad_norm([gc], 1.0)
+        assert_close(nc[0:1].cpu(), tot.view(1), 1e-5, 1e-6, "norm")
+        ops.adamw_step(p, g, m, v, wb, n, 1e-3, 1e-4, step, clip_coef=nc[1:])
+        O.adamw_step(pr, gc, mr, vr, step, 1e-3, 1e-4)
+        assert_close(p.cpu(), pr, 1e-5, 1e-6, "adamw p")
+        assert_close(wb.cpu(), pr, 1e-2, 1e-2, "adamw bf16 copy")
+        g = g * 1.5 + 0.001
