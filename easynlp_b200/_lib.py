@@ -48,7 +48,7 @@ def _declare(L):
     L.clipk_im2col_patches.argtypes = [vp, vp, i, i, i, vp]
     L.clipk_vit_assemble.argtypes = [vp, vp, vp, vp, i, i, i, vp]
     L.clipk_vit_assemble_bwd.argtypes = [vp, vp, i, i, i, vp]
-    L.clipk_bert_embed.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp]
+    L.clipk_bert_embed.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
     L.clipk_bert_embed_bwd.argtypes = [vp, vp, vp, i, i, i, vp]
     L.clipk_l2norm_fwd.argtypes = [vp, vp, vp, i, i, vp]
     L.clipk_l2norm_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, vp]

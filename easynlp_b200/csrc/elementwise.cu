@@ -208,12 +208,15 @@ __global__ void __launch_bounds__(256) vit_assemble_bwd_kernel(const float* __re
 // e[b,l,:] = word[ids[b,l]] + type[0] + pos[l]       (modeling_bert.py:95-129; LN applied by layernorm_fwd)
 __global__ void __launch_bounds__(256) bert_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
                                                          const float* __restrict__ pos, const float* __restrict__ type0,
-                                                         float* __restrict__ e, int rows, int L, int H, int vocab) {
+                                                         float* __restrict__ e, float* __restrict__ key_mask, int rows, int L, int H,
+                                                         int vocab) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   long long id = ids[row];
   if (id < 0 || id >= vocab) id = 0;  // host validates; never index out of the table
+  // attention_mask = ids.ne(0) (modeling_chineseclip.py:347-348) as the additive (1-m)*-10000 of modeling_utils.py:438-439
+  if (key_mask && lane == 0) key_mask[row] = (id == 0) ? -10000.0f : 0.0f;
   const int l = row % L;
   for (int c = lane * 4; c < H; c += 128) {
     float4 w = ld_f4(word + id * H + c), p = ld_f4(pos + (long long)l * H + c), t = ld_f4(type0 + c);
@@ -367,10 +370,10 @@ extern "C" int clipk_vit_assemble_bwd(const float* dx0, void* dpatch_bf16, int B
   return 0;
 }
 
-extern "C" int clipk_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0, float* e, int rows, int L,
-                                int H, int vocab, cudaStream_t stream) {
+extern "C" int clipk_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0, float* e, float* key_mask,
+                                int rows, int L, int H, int vocab, cudaStream_t stream) {
   if (H % 4) { set_error("bert_embed: H %% 4 != 0"); return CLIPK_ERR_ARG; }
-  bert_embed_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, word, pos, type0, e, rows, L, H, vocab);
+  bert_embed_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, word, pos, type0, e, key_mask, rows, L, H, vocab);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

@@ -1,0 +1,345 @@
+"""ClipEngine: host-side schedule of the chinese_clip training / encoding step over the clipk kernels.
+
+Everything numerical happens in hand-written sm_100a kernels behind the C ABI (include/clipk.h); this file only owns
+buffers (torch tensors as device memory) and the order of launches, i.e. it is the from-scratch counterpart of the
+autograd graph PyTorch builds for
+
+    CLIPApp.forward / compute_loss      easynlp/appzoo/clip/model.py:106-164
+    CHINESE_CLIP.forward                easynlp/modelzoo/models/clip/modeling_chineseclip.py:343-365
+    VisualTransformer / ResidualAttentionBlock   .../modeling_chineseclip.py:170-253   (pre-LN, QuickGELU)
+    BertModel (embeddings + post-LN encoder)     easynlp/modelzoo/models/bert/modeling_bert.py:72-541
+    clip_grad_norm_ + AdamW.step        easynlp/core/trainer.py:315-337, easynlp/core/optimizers.py:405-464
+
+Numerics: bf16 GEMM/attention operands with fp32 accumulation, fp32 residual stream / LayerNorm statistics /
+embeddings / logits / loss, fp32 master weights and gradients.  Layout: token-major [B*L, d] activations.
+Dropout probabilities are taken as 0 by this engine ("dropout").
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .params import ParamStore
+
+SM_TARGET = 148 * 2
+
+
+def _splits_for(m, n, k):
+    tiles = ((m + 127) // 128) * ((n + 255) // 256 if (n % 256 == 0 or n > 512) else (n + 127) // 128)
+    s = max(1, SM_TARGET // max(1, tiles))
+    return max(1, min(s, max(1, k // 256)))
+
+
+class ClipEngine:
+    def __init__(self, cfg: dict, device="cuda", with_optimizer_state: bool = True):
+        if isinstance(cfg.get("vision_layers"), (tuple, list)):
+            raise NotImplementedError("ModifiedResNet visual towers are outside the hot path (ViT only)")
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.W = cfg["vision_width"]; self.P = cfg["vision_patch_size"]; self.R = cfg["image_resolution"]
+        self.E = cfg["embed_dim"]; self.g = self.R // self.P; self.Lv = self.g * self.g + 1
+        self.Hv = self.W // 64                                   # modeling_chineseclip.py:289
+        self.H = cfg["text_hidden_size"]; self.I = cfg["text_intermediate_size"]; self.Ht = cfg["text_num_attention_heads"]
+        self.nv = cfg["vision_layers"]; self.nt = cfg["text_num_hidden_layers"]
+        if self.H != self.Ht * 64 or self.W % 128 or self.H % 128 or self.E % 128:
+            raise NotImplementedError("clipk kernels need head_dim 64 and widths that are multiples of 128")
+        if (3 * self.P * self.P) % 8:
+            raise NotImplementedError("patch dim 3*P*P must be a multiple of 8 (pad the patch matrix for ViT-*/14)")
+        if cfg.get("text_hidden_act", "gelu") != "gelu":
+            raise NotImplementedError("text tower activation must be erf-GELU")
+        self.params = ParamStore(cfg, device, with_optimizer_state)
+        self._buf: Dict[tuple, torch.Tensor] = {}
+        self._saved = None
+        self.norm_and_coef = torch.zeros(2, device=self.dev)
+        self._norm_ws = torch.zeros(1024, dtype=torch.float64, device=self.dev)
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        t = self._buf.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.dev)
+            self._buf[key] = t
+        return t
+
+    def bf(self, name, *shape):
+        return self.buf(name, shape, torch.bfloat16)
+
+    def f32(self, name, *shape):
+        return self.buf(name, shape, torch.float32)
+
+    # ------------------------------------------------------------------ ViT
+    def vit_forward(self, pixels: torch.Tensor, save: bool):
+        P_ = self.params; W = self.W; B = pixels.shape[0]; Lv = self.Lv; M = B * Lv; Hh = self.Hv
+        assert pixels.dtype == torch.float32 and pixels.is_contiguous() and pixels.shape[1:] == (3, self.R, self.R)
+        npatch = B * self.g * self.g
+        kdim = 3 * self.P * self.P
+        patches = self.bf("v.patches", npatch, kdim)
+        ops.im2col_patches(pixels, patches, B, self.R, self.P)
+        patch_out = self.f32("v.patch_out", npatch, W)
+        ops.gemm(patches, P_.w("visual.conv1.weight", (W, kdim)), patch_out)
+        x0 = self.f32("v.x0", M, W)
+        ops.vit_assemble(patch_out, P_.p("visual.class_embedding"), P_.p("visual.positional_embedding"), x0, B, Lv, W)
+        x = self.f32("v.x.0", M, W)
+        st = {"B": B, "mean0": self.f32("v.mean0", M), "rstd0": self.f32("v.rstd0", M), "layers": []}
+        ops.layernorm_fwd(x0, P_.p("visual.ln_pre.weight"), P_.p("visual.ln_pre.bias"), 1e-5, None, x, st["mean0"], st["rstd0"])
+        for i in range(self.nv):
+            p = f"visual.transformer.resblocks.{i}."
+            tag = f"v.{i}." if save else "v.t."
+            ly = {"x_in": x}
+            ly["h"] = self.bf(tag + "h", M, W); ly["m1"] = self.f32(tag + "m1", M); ly["r1"] = self.f32(tag + "r1", M)
+            ops.layernorm_fwd(x, P_.p(p + "ln_1.weight"), P_.p(p + "ln_1.bias"), 1e-5, ly["h"], None, ly["m1"], ly["r1"])
+            ly["qkv"] = self.bf(tag + "qkv", M, 3 * W)
+            ops.gemm(ly["h"], P_.w(p + "attn.in_proj_weight"), ly["qkv"], bias=P_.p(p + "attn.in_proj_bias"))
+            ly["ctx"] = self.bf(tag + "ctx", M, W); ly["lse"] = self.f32(tag + "lse", B * Hh * Lv)
+            ops.attention_fwd(ly["qkv"], None, ly["ctx"], ly["lse"], B, Lv, Hh)
+            ly["x1"] = self.f32(tag + "x1", M, W)
+            ops.gemm(ly["ctx"], P_.w(p + "attn.out_proj.weight"), ly["x1"], bias=P_.p(p + "attn.out_proj.bias"), residual=x)
+            ly["h2"] = self.bf(tag + "h2", M, W); ly["m2"] = self.f32(tag + "m2", M); ly["r2"] = self.f32(tag + "r2", M)
+            ops.layernorm_fwd(ly["x1"], P_.p(p + "ln_2.weight"), P_.p(p + "ln_2.bias"), 1e-5, ly["h2"], None, ly["m2"], ly["r2"])
+            ly["z"] = self.bf(tag + "z", M, 4 * W); ly["a"] = self.bf(tag + "a", M, 4 * W)
+            ops.gemm(ly["h2"], P_.w(p + "mlp.c_fc.weight"), ly["z"], bias=P_.p(p + "mlp.c_fc.bias"), mode=L.EPI_QUICK_GELU, out2=ly["a"])
+            x_next = self.f32(f"v.x.{i + 1}" if save else f"v.x.t{i % 2}", M, W)
+            ops.gemm(ly["a"], P_.w(p + "mlp.c_proj.weight"), x_next, bias=P_.p(p + "mlp.c_proj.bias"), residual=ly["x1"])
+            x = x_next
+            st["layers"].append(ly)
+        st["x_final"] = x
+        st["pooled"] = self.bf("v.pooled", B, W); st["mp"] = self.f32("v.mp", B); st["rp"] = self.f32("v.rp", B)
+        ops.layernorm_fwd(x, P_.p("visual.ln_post.weight"), P_.p("visual.ln_post.bias"), 1e-5, st["pooled"], None, st["mp"], st["rp"],
+                          rows=B, ldx=Lv * W)
+        st["feat"] = self.f32("v.feat", B, self.E)
+        ops.gemm(st["pooled"], P_.w("visual.proj"), st["feat"], b_mn_major=1)
+        st["embeds"] = self.f32("v.embeds", B, self.E); st["norm"] = self.f32("v.norm", B)
+        ops.l2norm_fwd(st["feat"], st["embeds"], st["norm"], B, self.E)
+        return st
+
+    def vit_backward(self, st, d_embeds: torch.Tensor):
+        P_ = self.params; W = self.W; B = st["B"]; Lv = self.Lv; M = B * Lv; Hh = self.Hv; E = self.E
+        dfeat_b = self.bf("v.dfeat_b", B, E)
+        ops.l2norm_bwd(d_embeds, st["embeds"], st["norm"], None, dfeat_b, B, E)
+        # d proj[W,E] += pooled^T dfeat ; dpooled = dfeat proj^T
+        ops.gemm(st["pooled"], dfeat_b, P_.g("visual.proj"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
+        dpooled = self.f32("v.dpooled", B, W)
+        ops.gemm(dfeat_b, P_.w("visual.proj"), dpooled)
+        dX = self.f32("v.dX.a", M, W); dXb = self.bf("v.dXb.a", M, W)
+        dX.zero_()
+        last = st["layers"][-1] if self.nv else None
+        bias_prev = P_.g(f"visual.transformer.resblocks.{self.nv - 1}.mlp.c_proj.bias") if self.nv else None
+        ops.layernorm_bwd(dpooled, st["x_final"], P_.p("visual.ln_post.weight"), st["mp"], st["rp"], dx_f32=dX,
+                          dgamma=P_.g("visual.ln_post.weight"), dbeta=P_.g("visual.ln_post.bias"), dbias=bias_prev,
+                          rows=B, ldx=Lv * W, lddx=Lv * W)
+        ops.cast_bf16(dX, dXb)
+        dz = self.bf("v.dz", M, 4 * W); dh = self.bf("v.dh", M, W); dctx = self.bf("v.dctx", M, W); dqkv = self.bf("v.dqkv", M, 3 * W)
+        for i in reversed(range(self.nv)):
+            p = f"visual.transformer.resblocks.{i}."
+            ly = st["layers"][i]
+            # MLP
+            ops.gemm(dXb, ly["a"], P_.g(p + "mlp.c_proj.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+                     splits=_splits_for(W, 4 * W, M))
+            ops.gemm(dXb, P_.w(p + "mlp.c_proj.weight"), dz, b_mn_major=1, mode=L.EPI_DQUICK_GELU, aux=ly["z"])
+            ops.colsum(dz, P_.g(p + "mlp.c_fc.bias"), M, 4 * W)
+            ops.gemm(dz, ly["h2"], P_.g(p + "mlp.c_fc.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+                     splits=_splits_for(4 * W, W, M))
+            ops.gemm(dz, P_.w(p + "mlp.c_fc.weight"), dh, b_mn_major=1)
+            dX1 = self.f32("v.dX.b", M, W); dX1b = self.bf("v.dXb.b", M, W)
+            ops.layernorm_bwd(dh, ly["x1"], P_.p(p + "ln_2.weight"), ly["m2"], ly["r2"], dx_add=dX, dx_f32=dX1, dx_bf16=dX1b,
+                              dgamma=P_.g(p + "ln_2.weight"), dbeta=P_.g(p + "ln_2.bias"), dbias=P_.g(p + "attn.out_proj.bias"))
+            # attention
+            ops.gemm(dX1b, ly["ctx"], P_.g(p + "attn.out_proj.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+                     splits=_splits_for(W, W, M))
+            ops.gemm(dX1b, P_.w(p + "attn.out_proj.weight"), dctx, b_mn_major=1)
+            ops.attention_bwd(ly["qkv"], None, ly["ctx"], ly["lse"], dctx, dqkv, B, Lv, Hh)
+            ops.colsum(dqkv, P_.g(p + "attn.in_proj_bias"), M, 3 * W)
+            ops.gemm(dqkv, ly["h"], P_.g(p + "attn.in_proj_weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+                     splits=_splits_for(3 * W, W, M))
+            ops.gemm(dqkv, P_.w(p + "attn.in_proj_weight"), dh, b_mn_major=1)
+            bias_prev = P_.g(f"visual.transformer.resblocks.{i - 1}.mlp.c_proj.bias") if i > 0 else None
+            ops.layernorm_bwd(dh, ly["x_in"], P_.p(p + "ln_1.weight"), ly["m1"], ly["r1"], dx_add=dX1, dx_f32=dX, dx_bf16=dXb,
+                              dgamma=P_.g(p + "ln_1.weight"), dbeta=P_.g(p + "ln_1.bias"), dbias=bias_prev)
+        # ln_pre, token assembly, patch embedding
+        dx0 = self.f32("v.dx0", M, W)
+        ops.layernorm_bwd(dX, self.f32("v.x0", M, W), P_.p("visual.ln_pre.weight"), st["mean0"], st["rstd0"], dx_f32=dx0,
+                          dgamma=P_.g("visual.ln_pre.weight"), dbeta=P_.g("visual.ln_pre.bias"))
+        ops.colsum(dx0, P_.g("visual.positional_embedding").view(-1), B, Lv * W)
+        ops.colsum(dx0, P_.g("visual.class_embedding"), B, W, ldx=Lv * W)
+        npatch = B * self.g * self.g; kdim = 3 * self.P * self.P
+        dpatch = self.bf("v.dpatch", npatch, W)
+        ops.vit_assemble_bwd(dx0, dpatch, B, Lv, W)
+        ops.gemm(dpatch, self.bf("v.patches", npatch, kdim), P_.g("visual.conv1.weight", (W, kdim)), a_mn_major=1, b_mn_major=1,
+                 mode=L.EPI_ATOMIC_ADD, splits=_splits_for(W, kdim, npatch))
+
+    # ------------------------------------------------------------------ BERT
+    def bert_forward(self, ids: torch.Tensor, save: bool):
+        P_ = self.params; H = self.H; I = self.I; B, Lt = ids.shape; M = B * Lt; Hh = self.Ht
+        assert ids.dtype == torch.int64 and ids.is_contiguous()
+        if Lt > self.cfg["text_max_position_embeddings"]:
+            raise ValueError("sequence longer than the position table")
+        eps = 1e-12                                                   # modeling_chineseclip.py:311
+        st = {"B": B, "Lt": Lt, "ids": ids, "layers": []}
+        st["e"] = self.f32("t.e", M, H); st["mask"] = self.f32("t.mask", M)
+        ops.bert_embed(ids.view(-1), P_.p("bert.embeddings.word_embeddings.weight"), P_.p("bert.embeddings.position_embeddings.weight"),
+                       P_.p("bert.embeddings.token_type_embeddings.weight"), st["e"], M, Lt, H, self.cfg["vocab_size"], key_mask=st["mask"])
+        x = self.f32("t.x.0", M, H); xb = self.bf("t.xb.0", M, H)
+        st["me"] = self.f32("t.me", M); st["re"] = self.f32("t.re", M)
+        ops.layernorm_fwd(st["e"], P_.p("bert.embeddings.LayerNorm.weight"), P_.p("bert.embeddings.LayerNorm.bias"), eps, xb, x,
+                          st["me"], st["re"])
+        for i in range(self.nt):
+            p = f"bert.encoder.layer.{i}."
+            tag = f"t.{i}." if save else "t.t."
+            ly = {"x_in": x, "xb_in": xb}
+            ly["qkv"] = self.bf(tag + "qkv", M, 3 * H)
+            ops.gemm(xb, P_.w(p + "attention.self.query.weight", (3 * H, H)), ly["qkv"], bias=P_.p(p + "attention.self.query.bias", (3 * H,)))
+            ly["ctx"] = self.bf(tag + "ctx", M, H); ly["lse"] = self.f32(tag + "lse", B * Hh * Lt)
+            ops.attention_fwd(ly["qkv"], st["mask"], ly["ctx"], ly["lse"], B, Lt, Hh)
+            ly["s1"] = self.f32(tag + "s1", M, H)
+            ops.gemm(ly["ctx"], P_.w(p + "attention.output.dense.weight"), ly["s1"], bias=P_.p(p + "attention.output.dense.bias"), residual=x)
+            ly["y1"] = self.f32(tag + "y1", M, H); ly["y1b"] = self.bf(tag + "y1b", M, H)
+            ly["m1"] = self.f32(tag + "m1", M); ly["r1"] = self.f32(tag + "r1", M)
+            ops.layernorm_fwd(ly["s1"], P_.p(p + "attention.output.LayerNorm.weight"), P_.p(p + "attention.output.LayerNorm.bias"), eps,
+                              ly["y1b"], ly["y1"], ly["m1"], ly["r1"])
+            ly["z"] = self.bf(tag + "z", M, I); ly["a"] = self.bf(tag + "a", M, I)
+            ops.gemm(ly["y1b"], P_.w(p + "intermediate.dense.weight"), ly["z"], bias=P_.p(p + "intermediate.dense.bias"),
+                     mode=L.EPI_ERF_GELU, out2=ly["a"])
+            ly["s2"] = self.f32(tag + "s2", M, H)
+            ops.gemm(ly["a"], P_.w(p + "output.dense.weight"), ly["s2"], bias=P_.p(p + "output.dense.bias"), residual=ly["y1"])
+            x = self.f32(f"t.x.{i + 1}" if save else f"t.x.t{i % 2}", M, H)
+            xb = self.bf(f"t.xb.{i + 1}" if save else f"t.xb.t{i % 2}", M, H)
+            ly["m2"] = self.f32(tag + "m2", M); ly["r2"] = self.f32(tag + "r2", M)
+            ops.layernorm_fwd(ly["s2"], P_.p(p + "output.LayerNorm.weight"), P_.p(p + "output.LayerNorm.bias"), eps, xb, x, ly["m2"], ly["r2"])
+            st["layers"].append(ly)
+        st["xb_final"] = xb
+        st["feat"] = self.f32("t.feat", B, self.E)
+        cls_rows = xb.view(B, Lt * H)[:, :H]                           # x[:, 0, :]  (modeling_chineseclip.py:350)
+        ops.gemm(cls_rows, P_.w("text_projection"), st["feat"], b_mn_major=1)
+        st["embeds"] = self.f32("t.embeds", B, self.E); st["norm"] = self.f32("t.norm", B)
+        ops.l2norm_fwd(st["feat"], st["embeds"], st["norm"], B, self.E)
+        return st
+
+    def bert_backward(self, st, d_embeds: torch.Tensor):
+        P_ = self.params; H = self.H; I = self.I; B = st["B"]; Lt = st["Lt"]; M = B * Lt; Hh = self.Ht; E = self.E
+        dfeat_b = self.bf("t.dfeat_b", B, E)
+        ops.l2norm_bwd(d_embeds, st["embeds"], st["norm"], None, dfeat_b, B, E)
+        cls_rows = st["xb_final"].view(B, Lt * H)[:, :H]
+        ops.gemm(cls_rows, dfeat_b, P_.g("text_projection"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
+        dOut = self.f32("t.dOut", M, H)
+        dOut.zero_()
+        ops.gemm(dfeat_b, P_.w("text_projection"), dOut.view(B, Lt * H)[:, :H])
+        dy, dy_add = dOut, None
+        ds2 = self.f32("t.ds2", M, H); ds2b = self.bf("t.ds2b", M, H); ds1 = self.f32("t.ds1", M, H); ds1b = self.bf("t.ds1b", M, H)
+        dz = self.bf("t.dz", M, I); dpart = self.bf("t.dpart", M, H); dctx = self.bf("t.dctx", M, H); dqkv = self.bf("t.dqkv", M, 3 * H)
+        dxp = self.bf("t.dxp", M, H)
+        for i in reversed(range(self.nt)):
+            p = f"bert.encoder.layer.{i}."
+            ly = st["layers"][i]
+            ops.layernorm_bwd(dy, ly["s2"], P_.p(p + "output.LayerNorm.weight"), ly["m2"], ly["r2"], dy_add=dy_add, dx_f32=ds2, dx_bf16=ds2b,
+                              dgamma=P_.g(p + "output.LayerNorm.weight"), dbeta=P_.g(p + "output.LayerNorm.bias"), dbias=P_.g(p + "output.dense.bias"))
+            ops.gemm(ds2b, ly["a"], P_.g(p + "output.dense.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD, splits=_splits_for(H, I, M))
+            ops.gemm(ds2b, P_.w(p + "output.dense.weight"), dz, b_mn_major=1, mode=L.EPI_DERF_GELU, aux=ly["z"])
+            ops.colsum(dz, P_.g(p + "intermediate.dense.bias"), M, I)
+            ops.gemm(dz, ly["y1b"], P_.g(p + "intermediate.dense.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD, splits=_splits_for(I, H, M))
+            ops.gemm(dz, P_.w(p + "intermediate.dense.weight"), dpart, b_mn_major=1)
+            ops.layernorm_bwd(dpart, ly["s1"], P_.p(p + "attention.output.LayerNorm.weight"), ly["m1"], ly["r1"], dy_add=ds2, dx_f32=ds1,
+                              dx_bf16=ds1b, dgamma=P_.g(p + "attention.output.LayerNorm.weight"),
+                              dbeta=P_.g(p + "attention.output.LayerNorm.bias"), dbias=P_.g(p + "attention.output.dense.bias"))
+            ops.gemm(ds1b, ly["ctx"], P_.g(p + "attention.output.dense.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+                     splits=_splits_for(H, H, M))
+            ops.gemm(ds1b, P_.w(p + "attention.output.dense.weight"), dctx, b_mn_major=1)
+            ops.attention_bwd(ly["qkv"], st["mask"], ly["ctx"], ly["lse"], dctx, dqkv, B, Lt, Hh)
+            ops.colsum(dqkv, P_.g(p + "attention.self.query.bias", (3 * H,)), M, 3 * H)
+            ops.gemm(dqkv, ly["xb_in"], P_.g(p + "attention.self.query.weight", (3 * H, H)), a_mn_major=1, b_mn_major=1,
+                     mode=L.EPI_ATOMIC_ADD, splits=_splits_for(3 * H, H, M))
+            ops.gemm(dqkv, P_.w(p + "attention.self.query.weight", (3 * H, H)), dxp, b_mn_major=1)
+            # d(layer input) = dxp (bf16) + ds1 (f32): consumed by the LayerNorm backward of the layer below, which writes ds2
+            # (a different buffer) before ds1 is overwritten again
+            dy, dy_add = dxp, ds1
+        de = self.f32("t.de", M, H)
+        ops.layernorm_bwd(dy, st["e"], P_.p("bert.embeddings.LayerNorm.weight"), st["me"], st["re"], dy_add=dy_add, dx_f32=de,
+                          dgamma=P_.g("bert.embeddings.LayerNorm.weight"), dbeta=P_.g("bert.embeddings.LayerNorm.bias"))
+        ops.bert_embed_bwd(st["ids"].view(-1), de, P_.g("bert.embeddings.word_embeddings.weight"), M, H, self.cfg["vocab_size"])
+        ops.colsum(de, P_.g("bert.embeddings.position_embeddings.weight").view(-1)[:Lt * H], B, Lt * H)
+        ops.colsum(de, P_.g("bert.embeddings.token_type_embeddings.weight")[0], M, H)
+
+    # ------------------------------------------------------------------ contrastive head
+    def loss_forward(self, text_embeds, image_embeds, gallery_image=None, gallery_text=None, label_offset=0, want_logits=True):
+        """Two CE strips: local texts vs the image gallery, local images vs the text gallery.  With no gallery given the
+        local batch is the gallery (world size 1: identical to the reference's [B,B] loss)."""
+        gi = image_embeds if gallery_image is None else gallery_image
+        gt = text_embeds if gallery_text is None else gallery_text
+        B = text_embeds.shape[0]; G = gi.shape[0]
+        ls = self.params.p("logit_scale")
+        st = {"T": text_embeds, "I": image_embeds, "GI": gi, "GT": gt, "off": label_offset, "G": G}
+        st["lse_t"] = self.f32("l.lse_t", B); st["lse_i"] = self.f32("l.lse_i", B)
+        rows_t = self.f32("l.rows_t", B); rows_i = self.f32("l.rows_i", B)
+        logits = self.f32("l.logits", B, G) if want_logits else None
+        ops.ce_strip_fwd(text_embeds, gi, ls, label_offset, st["lse_t"], rows_t, S_out=logits, lds=G)
+        ops.ce_strip_fwd(image_embeds, gt, ls, label_offset, st["lse_i"], rows_i)
+        st["loss_sum"] = self.f32("l.loss", 1)       # sum over LOCAL rows of both directions / (2 G)
+        ops.reduce_sum(rows_t, B, 1.0 / (2 * G), st["loss_sum"], False)
+        ops.reduce_sum(rows_i, B, 1.0 / (2 * G), st["loss_sum"], True)
+        st["logits"] = logits
+        return st
+
+    def loss_backward(self, st, grad_scale: float = 1.0, local_gallery: bool = True):
+        """d(grad_scale * loss) w.r.t. the local embeddings.  With local_gallery (world size 1) the gallery IS the local batch and
+        its gradient accumulates straight onto dI / dT; otherwise the gallery gradients (all G rows) are returned separately so
+        the distributed wrapper can reduce-scatter them to their owners."""
+        B = st["T"].shape[0]; G = st["G"]; E = self.E
+        coef = grad_scale / (2.0 * G)
+        ls = self.params.p("logit_scale"); dls = self.params.g("logit_scale").view(1)
+        dT = self.f32("l.dT", B, E); dI = self.f32("l.dI", B, E)
+        ops.ce_strip_bwd(st["T"], st["GI"], ls, st["lse_t"], st["off"], coef, True, dT, False, dls)
+        ops.ce_strip_bwd(st["I"], st["GT"], ls, st["lse_i"], st["off"], coef, True, dI, False, dls)
+        if local_gallery:
+            ops.ce_strip_bwd(st["GI"], st["T"], ls, st["lse_t"], st["off"], coef, False, dI, True)
+            ops.ce_strip_bwd(st["GT"], st["I"], ls, st["lse_i"], st["off"], coef, False, dT, True)
+            return dT, dI, None, None
+        dGI = self.f32("l.dGI", G, E); dGT = self.f32("l.dGT", G, E)
+        ops.ce_strip_bwd(st["GI"], st["T"], ls, st["lse_t"], st["off"], coef, False, dGI, False)
+        ops.ce_strip_bwd(st["GT"], st["I"], ls, st["lse_i"], st["off"], coef, False, dGT, False)
+        return dT, dI, dGI, dGT
+
+    # ------------------------------------------------------------------ public steps
+    def encode(self, pixels: Optional[torch.Tensor], ids: Optional[torch.Tensor]):
+        """feat=True path of CLIPApp.forward (model.py:145-146): embeddings only, no activations kept."""
+        out = {"image_embeds": None, "text_embeds": None}
+        if pixels is not None:
+            out["image_embeds"] = self.vit_forward(pixels, save=False)["embeds"]
+        if ids is not None:
+            out["text_embeds"] = self.bert_forward(ids, save=False)["embeds"]
+        return out
+
+    def forward(self, pixels, ids, save=True, want_logits=True):
+        v = self.vit_forward(pixels, save)
+        t = self.bert_forward(ids, save)
+        l = self.loss_forward(t["embeds"], v["embeds"], want_logits=want_logits)
+        self._saved = (v, t, l) if save else None
+        return {"image_embeds": v["embeds"], "text_embeds": t["embeds"], "logits_per_text": l["logits"], "loss": l["loss_sum"]}
+
+    def zero_grad(self):
+        self.params.grad.zero_()
+
+    def backward(self, grad_scale: float = 1.0):
+        """Gradient of grad_scale * loss into params.grad (accumulating)."""
+        if self._saved is None:
+            raise RuntimeError("backward() needs a forward(save=True) first")
+        v, t, l = self._saved
+        dT, dI, _, _ = self.loss_backward(l, grad_scale, local_gallery=True)
+        self.bert_backward(t, dT)
+        self.vit_backward(v, dI)
+        self._saved = None
+
+    def optimizer_step(self, lr: float, weight_decay: float = 1e-4, max_grad_norm: float = 1.0):
+        """clip_grad_norm_(max_grad_norm) + AdamW(betas 0.9/0.999, eps 1e-6) with the reference's decay grouping."""
+        P_ = self.params
+        P_.step += 1
+        n_tr, n_dec = P_.n_trainable, P_.n_decay
+        coef = None
+        if max_grad_norm and max_grad_norm > 0:
+            ops.grad_norm(P_.grad, n_tr, float(max_grad_norm), self._norm_ws, self.norm_and_coef)
+            coef = self.norm_and_coef[1:]
+        ops.adamw_step(P_.master[:n_dec], P_.grad[:n_dec], P_.exp_avg[:n_dec], P_.exp_avg_sq[:n_dec], P_.shadow[:n_dec], n_dec,
+                       lr, weight_decay, P_.step, coef)
+        ops.adamw_step(P_.master[n_dec:n_tr], P_.grad[n_dec:n_tr], P_.exp_avg[n_dec:n_tr], P_.exp_avg_sq[n_dec:n_tr],
+                       P_.shadow[n_dec:n_tr], n_tr - n_dec, lr, 0.0, P_.step, coef)

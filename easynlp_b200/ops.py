@@ -119,10 +119,10 @@ def vit_assemble_bwd(dx0, dpatch, B, L, W):
     L_.check(L_.lib().clipk_vit_assemble_bwd(_f32(dx0), _b16(dpatch), B, L, W, _stream()), "vit_assemble_bwd")
 
 
-def bert_embed(ids, word, pos, type0, e, rows, L, H, vocab):
+def bert_embed(ids, word, pos, type0, e, rows, L, H, vocab, key_mask=None):
     assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous()
-    L_.check(L_.lib().clipk_bert_embed(_ptr(ids), _f32(word), _f32(pos), _f32(type0), _f32(e), rows, L, H, vocab, _stream()),
-             "bert_embed")
+    L_.check(L_.lib().clipk_bert_embed(_ptr(ids), _f32(word), _f32(pos), _f32(type0), _f32(e), _f32(key_mask), rows, L, H, vocab,
+                                       _stream()), "bert_embed")
 
 
 def bert_embed_bwd(ids, de, dword, rows, H, vocab):

@@ -1,0 +1,158 @@
+"""Flat parameter storage for the chinese_clip model: ONE fp32 master buffer (+ grads, Adam moments, bf16 shadow)
+with named views, laid out as  [ weight-decay group | no-decay group | tensors that never receive a gradient ].
+
+The names and shapes are the reference's checkpoint schema (modeling_chineseclip.py:219-233,316;
+modeling_bert.py:72-129,145-147,264-346,535-541); the decay grouping is the substring rule of
+easynlp/core/optimizers.py:490,519-523.  The layout lets clip+AdamW run as one multi-tensor kernel per group and
+keeps BERT's separate query/key/value matrices adjacent so the QKV projection is one [3H, H] GEMM operand.
+"""
+from collections import OrderedDict
+from typing import Dict, List, Tuple
+
+import torch
+
+NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight")
+ALIGN = 8  # elements: 16 B for the bf16 shadow (TMA base alignment), 32 B for fp32
+
+
+def uses_weight_decay(name: str) -> bool:
+    return not any(nd in name for nd in NO_DECAY)
+
+
+def param_schema(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
+    """(name -> shape) in checkpoint order for model_type == chinese_clip with a ViT visual tower."""
+    W = cfg["vision_width"]; P = cfg["vision_patch_size"]; E = cfg["embed_dim"]
+    n_tok = (cfg["image_resolution"] // P) ** 2 + 1
+    H = cfg["text_hidden_size"]; I = cfg["text_intermediate_size"]
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    s["text_projection"] = (H, E)
+    s["logit_scale"] = ()
+    s["visual.class_embedding"] = (W,)
+    s["visual.positional_embedding"] = (n_tok, W)
+    s["visual.proj"] = (W, E)
+    s["visual.conv1.weight"] = (W, 3, P, P)
+    s["visual.ln_pre.weight"] = (W,); s["visual.ln_pre.bias"] = (W,)
+    for i in range(cfg["vision_layers"]):
+        p = f"visual.transformer.resblocks.{i}."
+        s[p + "attn.in_proj_weight"] = (3 * W, W); s[p + "attn.in_proj_bias"] = (3 * W,)
+        s[p + "attn.out_proj.weight"] = (W, W); s[p + "attn.out_proj.bias"] = (W,)
+        s[p + "ln_1.weight"] = (W,); s[p + "ln_1.bias"] = (W,)
+        s[p + "mlp.c_fc.weight"] = (4 * W, W); s[p + "mlp.c_fc.bias"] = (4 * W,)
+        s[p + "mlp.c_proj.weight"] = (W, 4 * W); s[p + "mlp.c_proj.bias"] = (W,)
+        s[p + "ln_2.weight"] = (W,); s[p + "ln_2.bias"] = (W,)
+    s["visual.ln_post.weight"] = (W,); s["visual.ln_post.bias"] = (W,)
+    s["bert.embeddings.word_embeddings.weight"] = (cfg["vocab_size"], H)
+    s["bert.embeddings.position_embeddings.weight"] = (cfg["text_max_position_embeddings"], H)
+    s["bert.embeddings.token_type_embeddings.weight"] = (cfg["text_type_vocab_size"], H)
+    s["bert.embeddings.LayerNorm.weight"] = (H,); s["bert.embeddings.LayerNorm.bias"] = (H,)
+    for i in range(cfg["text_num_hidden_layers"]):
+        p = f"bert.encoder.layer.{i}."
+        for nm in ("query", "key", "value"):
+            s[p + f"attention.self.{nm}.weight"] = (H, H)
+        for nm in ("query", "key", "value"):
+            s[p + f"attention.self.{nm}.bias"] = (H,)
+        s[p + "attention.output.dense.weight"] = (H, H); s[p + "attention.output.dense.bias"] = (H,)
+        s[p + "attention.output.LayerNorm.weight"] = (H,); s[p + "attention.output.LayerNorm.bias"] = (H,)
+        s[p + "intermediate.dense.weight"] = (I, H); s[p + "intermediate.dense.bias"] = (I,)
+        s[p + "output.dense.weight"] = (H, I); s[p + "output.dense.bias"] = (H,)
+        s[p + "output.LayerNorm.weight"] = (H,); s[p + "output.LayerNorm.bias"] = (H,)
+    s["bert.pooler.dense.weight"] = (H, H); s["bert.pooler.dense.bias"] = (H,)
+    return s
+
+
+# the pooler is computed-but-unused by chinese_clip (modeling_chineseclip.py:349 takes [0]); its parameters never get a
+# gradient, so the reference optimizer skips them (optimizers.py:420-421) -- they sit outside the updated range.
+NO_GRAD = ("bert.pooler.dense.weight", "bert.pooler.dense.bias")
+
+
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
+def _pad(n):
+    return (n + ALIGN - 1) // ALIGN * ALIGN
+
+
+class ParamStore:
+    def __init__(self, cfg: dict, device="cuda", with_optimizer_state: bool = True):
+        self.cfg = cfg
+        self.schema = param_schema(cfg)
+        decay = [n for n in self.schema if n not in NO_GRAD and uses_weight_decay(n)]
+        nodecay = [n for n in self.schema if n not in NO_GRAD and not uses_weight_decay(n)]
+        frozen = [n for n in self.schema if n in NO_GRAD]
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        for group in (decay, nodecay, frozen):
+            for n in group:
+                self.offsets[n] = off
+                off += _pad(max(1, _numel(self.schema[n])))
+            if group is decay:
+                self.n_decay = off
+            elif group is nodecay:
+                self.n_trainable = off
+        self.n_total = off
+        self.device = torch.device(device)
+        self.master = torch.zeros(self.n_total, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
+        self.shadow = torch.zeros(self.n_total, dtype=torch.bfloat16, device=self.device)
+        self.exp_avg = self.exp_avg_sq = None
+        if with_optimizer_state:
+            self.exp_avg = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
+            self.exp_avg_sq = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
+        self.step = 0
+
+    # ---- views
+    def _view(self, buf, name, shape=None, numel=None):
+        shape = self.schema[name] if shape is None else shape
+        n = _numel(shape) if numel is None else numel
+        o = self.offsets[name]
+        return buf[o:o + n].view(shape)
+
+    def p(self, name, shape=None):
+        return self._view(self.master, name, shape)
+
+    def w(self, name, shape=None):
+        """bf16 shadow copy (GEMM operand)."""
+        return self._view(self.shadow, name, shape)
+
+    def g(self, name, shape=None):
+        return self._view(self.grad, name, shape)
+
+    def names(self) -> List[str]:
+        return list(self.schema.keys())
+
+    def trainable_names(self) -> List[str]:
+        return [n for n in self.schema if n not in NO_GRAD]
+
+    # ---- checkpoint I/O (reference key names; `chinese_clip.` prefix handled by the caller)
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = False):
+        missing = []
+        for n, shape in self.schema.items():
+            if n not in sd:
+                missing.append(n)
+                continue
+            t = sd[n]
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError(f"shape mismatch for {n}: checkpoint {tuple(t.shape)} vs model {tuple(shape)}")
+            self.p(n).copy_(t.to(device=self.device, dtype=torch.float32))
+        if strict and missing:
+            raise KeyError(f"missing keys: {missing[:5]}...")
+        self.refresh_shadow()
+        return missing
+
+    def state_dict(self) -> "OrderedDict[str, torch.Tensor]":
+        out = OrderedDict()
+        for n in self.schema:
+            out[n] = self.p(n).detach().clone()
+            if n == "bert.embeddings.word_embeddings.weight":
+                pass
+        # buffer exported by the reference BertEmbeddings (modeling_bert.py:87)
+        out["bert.embeddings.position_ids"] = torch.arange(self.cfg["text_max_position_embeddings"], device=self.device).unsqueeze(0)
+        return out
+
+    def refresh_shadow(self):
+        from . import ops
+        ops.cast_bf16(self.master, self.shadow)

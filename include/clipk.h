@@ -108,8 +108,9 @@ int clipk_vit_assemble(const float* patch_f32, const float* cls, const float* po
 int clipk_vit_assemble_bwd(const float* dx0, void* dpatch_bf16, int B, int L, int W, cudaStream_t stream);
 /* BERT embeddings (modeling_bert.py:95-129): e = word[ids] + type[0] + pos[l]; backward scatters into dword
  * (row 0 = padding_idx receives no gradient).  ids: int64 [rows] on device.                                     */
-int clipk_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0, float* e, int rows,
-                     int L, int H, int vocab, cudaStream_t stream);
+int clipk_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0, float* e,
+                     float* key_mask /* optional [rows]: (ids==0) * -10000 */, int rows, int L, int H, int vocab,
+                     cudaStream_t stream);
 int clipk_bert_embed_bwd(const long long* ids, const float* de, float* dword, int rows, int H, int vocab,
                          cudaStream_t stream);
 
