@@ -53,6 +53,7 @@ def _declare(L):
     L.clipk_l2norm_fwd.argtypes = [vp, vp, vp, i, i, vp]
     L.clipk_l2norm_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, vp]
     L.clipk_cast_bf16.argtypes = [vp, vp, ll, vp]
+    L.clipk_axpy.argtypes = [vp, vp, f, ll, vp]
     L.clipk_ce_strip_fwd.argtypes = [vp, vp, vp, i, vp, ll, i, vp, vp, i, i, i, vp]
     L.clipk_ce_strip_bwd.argtypes = [vp, vp, vp, vp, i, f, i, vp, i, vp, i, i, i, vp]
     L.clipk_reduce_sum.argtypes = [vp, i, f, vp, i, vp]

@@ -1,0 +1,43 @@
+"""AppZoo registry for the one application on the hot path -- same call signatures as easynlp/appzoo/api.py:281-468
+(prefix match on app_name, NotImplementedError for unknown apps, extra kwargs tolerated)."""
+
+
+def _clip_classes():
+    from .clip.model import CLIPApp
+    from .clip.evaluator import CLIPEvaluator
+    from .clip.predictor import CLIPPredictor
+    from .clip.data import CLIPDataset
+    return CLIPApp, CLIPEvaluator, CLIPPredictor, CLIPDataset
+
+
+def _match(app_name):
+    if app_name is not None and app_name.startswith("clip"):
+        return True
+    raise NotImplementedError(f"application {app_name!r} is outside the B200 hot path (only 'clip' is registered)")
+
+
+def get_application_model(app_name, pretrained_model_name_or_path, user_defined_parameters=None, **kwargs):
+    _match(app_name)
+    return _clip_classes()[0](pretrained_model_name_or_path, user_defined_parameters=user_defined_parameters, **kwargs)
+
+
+def get_application_model_for_evaluation(app_name, pretrained_model_name_or_path, user_defined_parameters=None, **kwargs):
+    _match(app_name)
+    return _clip_classes()[0].from_pretrained(pretrained_model_name_or_path, user_defined_parameters=user_defined_parameters or {}, **kwargs)
+
+
+def get_application_evaluator(app_name, valid_dataset, user_defined_parameters=None, **kwargs):
+    _match(app_name)
+    return _clip_classes()[1](valid_dataset=valid_dataset, user_defined_parameters=user_defined_parameters, **kwargs)
+
+
+def get_application_predictor(app_name, model_dir, user_defined_parameters=None, **kwargs):
+    _match(app_name)
+    cls = _clip_classes()
+    return cls[2](model_dir=model_dir, model_cls=cls[0], user_defined_parameters=user_defined_parameters, **kwargs)
+
+
+def get_application_dataset(app_name, pretrained_model_name_or_path, data_file, max_seq_length, user_defined_parameters=None, **kwargs):
+    _match(app_name)
+    return _clip_classes()[3](pretrained_model_name_or_path=pretrained_model_name_or_path, data_file=data_file,
+                              max_seq_length=max_seq_length, user_defined_parameters=user_defined_parameters, **kwargs)

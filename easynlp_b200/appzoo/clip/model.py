@@ -1,0 +1,134 @@
+"""CLIPApp -- drop-in for easynlp/appzoo/clip/model.py:40-164 (model_type == chinese_clip) whose math runs in the clipk
+sm_100a kernels.  Same constructor / from_pretrained / forward(inputs, feat) / compute_loss contract, same `.config`
+wrapper, same state_dict key names (`chinese_clip.` prefix), so Trainer / CLIPEvaluator / CLIPPredictor
+written against the reference keep working.  There is no CPU or PyTorch fallback."""
+import json
+import os
+from collections import OrderedDict
+
+import torch
+
+from ..application import Application
+from ...engine import ClipEngine
+
+PREFIX = "chinese_clip."
+
+
+class Config_Wrapper:
+    """model.py:32-38 of the reference: the Trainer needs `.to_json_string()` and a `__dict__`."""
+
+    def __init__(self, json_data):
+        self.json_data = json_data
+
+    def to_json_string(self):
+        return json.dumps(self.json_data, ensure_ascii=False)
+
+
+class _ClipLossFn(torch.autograd.Function):
+    """Bridges torch.autograd (`loss.backward()` in a Trainer) to the engine's hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, app, anchor, loss_value):
+        ctx.app = app
+        return loss_value.detach().clone().view(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        app = ctx.app
+        app.engine.backward(grad_scale=float(grad_out))
+        app._publish_grads()
+        return None, None, None
+
+
+class CLIPApp(Application):
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, user_defined_parameters={}, **kwargs):
+        return cls(pretrained_model_name_or_path, user_defined_parameters)
+
+    def __init__(self, pretrained_model_name_or_path=None, user_defined_parameters=None, **kwargs):
+        super().__init__()
+        self.engine = None
+        if pretrained_model_name_or_path is None:
+            return
+        if not torch.cuda.is_available():
+            raise RuntimeError("easynlp_b200.CLIPApp needs a CUDA device (B200): there is no CPU fallback")
+        path = pretrained_model_name_or_path
+        with open(os.path.join(path, "config.json"), "r") as f:
+            self.raw_config = json.load(f)
+        mt = self.raw_config.get("model_type")
+        if mt != "chinese_clip":
+            raise NotImplementedError(f"model_type={mt!r}: only the chinese_clip branch (ViT + BertModel, model.py:64-72 of the "
+                                      "reference) is implemented by the B200 path")
+        self.model_type = "chinese_clip"
+        self.config = Config_Wrapper(self.raw_config)
+        cfg = {k: v for k, v in self.raw_config.items()}
+        self.engine = ClipEngine(cfg, device=kwargs.get("device", "cuda"))
+        ckpt = os.path.join(path, "pytorch_model.bin")
+        checkpoint = torch.load(ckpt, map_location="cpu")
+        self.engine.params.load_state_dict({k.replace(PREFIX, ""): v for k, v in checkpoint.items()}, strict=False)
+        self._wrap_params()
+        self.distributed_loss = bool((user_defined_parameters or {}).get("app_parameters", {}).get("global_contrastive", False)) \
+            if isinstance(user_defined_parameters, dict) else False
+
+    # ------------------------------------------------------------------ parameters (reference names, shared storage)
+    def _wrap_params(self):
+        P = self.engine.params
+        self._plist = OrderedDict()
+        for n in P.names():
+            self._plist[PREFIX + n] = torch.nn.Parameter(P.p(n), requires_grad=True)
+
+    def _publish_grads(self):
+        P = self.engine.params
+        for n in P.trainable_names():
+            self._plist[PREFIX + n].grad = P.g(n)
+
+    def named_parameters(self, prefix="", recurse=True, remove_duplicate=True):
+        for n, p in self._plist.items():
+            yield (prefix + ("." if prefix else "") + n, p)
+
+    def parameters(self, recurse=True):
+        for _, p in self.named_parameters():
+            yield p
+
+    def state_dict(self, *args, **kwargs):
+        sd = self.engine.params.state_dict()
+        return OrderedDict((PREFIX + k, v) for k, v in sd.items())
+
+    def load_state_dict(self, state_dict, strict=True):
+        self.engine.params.load_state_dict({k.replace(PREFIX, ""): v for k, v in state_dict.items()}, strict=False)
+
+    def zero_grad(self, set_to_none=False):
+        self.engine.zero_grad()
+
+    def to(self, *args, **kwargs):      # parameters live on the GPU from construction
+        return self
+
+    def cuda(self, device=None):
+        return self
+
+    # ------------------------------------------------------------------ forward / loss
+    def forward(self, inputs, feat=None):
+        dev = self.engine.dev
+        # like the reference (model.py:116-123) the batch dict is updated in place with device tensors
+        inputs["pixel_values"] = inputs["pixel_values"].to(dev, non_blocking=True) if inputs.get("pixel_values") is not None else None
+        inputs["input_ids"] = inputs["input_ids"].to(dev, non_blocking=True) if inputs.get("input_ids") is not None else None
+        pix = inputs["pixel_values"]; ids = inputs["input_ids"]
+        if pix is not None:
+            pix = pix.float().contiguous()
+        if ids is not None:
+            ids = ids.long().contiguous()
+        if feat is True:
+            return self.engine.encode(pix, ids)
+        assert pix is not None and ids is not None, "text and image cannot both be None!"
+        out = self.engine.forward(pix, ids, save=self.training and torch.is_grad_enabled(), distributed=self.distributed_loss)
+        lpt = out["logits_per_text"]
+        self._last_loss = out["loss"]
+        return {"logits_per_text": lpt, "logits_per_image": lpt.T, "image_embeds": out["image_embeds"], "text_embeds": out["text_embeds"]}
+
+    def compute_loss(self, forward_outputs, label_ids, **kwargs):
+        """(CE(S) + CE(S^T)) / 2 -- already evaluated by the fused CE-strip kernels during forward()."""
+        anchor = next(iter(self._plist.values()))
+        if self.training and torch.is_grad_enabled():
+            return {"loss": _ClipLossFn.apply(self, anchor, self._last_loss)}
+        return {"loss": self._last_loss.detach().clone().view(())}

@@ -280,6 +280,14 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     st_bf4(y + t * 4, ld_f4(x + t * 4));
 }
 
+// y += alpha * x   (n % 4 == 0)
+__global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float alpha, long long n4) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+    float4 a = ld_f4(x + t * 4), b = ld_f4(y + t * 4);
+    st_f4(y + t * 4, make_float4(b.x + alpha * a.x, b.y + alpha * a.y, b.z + alpha * a.z, b.w + alpha * a.w));
+  }
+}
+
 static inline int grid_for(long long work_items, int per_cta) {
   long long g = (work_items + per_cta - 1) / per_cta;
   long long cap = (long long)sm_count() * 8;
@@ -408,6 +416,15 @@ extern "C" int clipk_cast_bf16(const float* x, void* y, long long n, cudaStream_
   if (n % 4) { set_error("cast_bf16: n %% 4 != 0"); return CLIPK_ERR_ARG; }
   if (n == 0) return 0;
   cast_bf16_kernel<<<grid_for(n / 4, 256 * 4), 256, 0, stream>>>(x, (bf16*)y, n / 4);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_axpy(const float* x, float* y, float alpha, long long n, cudaStream_t stream) {
+  if (n % 4) { set_error("axpy: n %% 4 != 0"); return CLIPK_ERR_ARG; }
+  if (n == 0) return 0;
+  axpy_kernel<<<grid_for(n / 4, 256 * 4), 256, 0, stream>>>(x, y, alpha, n / 4);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

@@ -310,10 +310,22 @@ class ClipEngine:
             out["text_embeds"] = self.bert_forward(ids, save=False)["embeds"]
         return out
 
-    def forward(self, pixels, ids, save=True, want_logits=True):
+    def forward(self, pixels, ids, save=True, want_logits=True, distributed=False):
+        """Both towers + the contrastive head.  distributed=True: all-gather the embedding shards over the default process
+        group and take the loss over the GLOBAL batch (labels offset by rank * local_B); 'loss' is then this rank's share
+        (sum over ranks = global loss) and 'logits_per_text' the local [b, G] strip."""
+        from . import distributed as D
         v = self.vit_forward(pixels, save)
         t = self.bert_forward(ids, save)
-        l = self.loss_forward(t["embeds"], v["embeds"], want_logits=want_logits)
+        if distributed and D.world_size() > 1:
+            B = pixels.shape[0]; Wd = D.world_size()
+            gi = D.gather_rows(v["embeds"], self.f32("l.gi", Wd * B, self.E))
+            gt = D.gather_rows(t["embeds"], self.f32("l.gt", Wd * B, self.E))
+            l = self.loss_forward(t["embeds"], v["embeds"], gi, gt, label_offset=D.get_rank() * B, want_logits=want_logits)
+            l["dist"] = True
+        else:
+            l = self.loss_forward(t["embeds"], v["embeds"], want_logits=want_logits)
+            l["dist"] = False
         self._saved = (v, t, l) if save else None
         return {"image_embeds": v["embeds"], "text_embeds": t["embeds"], "logits_per_text": l["logits"], "loss": l["loss_sum"]}
 
@@ -325,10 +337,22 @@ class ClipEngine:
         if self._saved is None:
             raise RuntimeError("backward() needs a forward(save=True) first")
         v, t, l = self._saved
-        dT, dI, _, _ = self.loss_backward(l, grad_scale, local_gallery=True)
+        if l["dist"]:
+            from . import distributed as D
+            dT, dI, dGI, dGT = self.loss_backward(l, grad_scale, local_gallery=False)
+            B = dT.shape[0]
+            ops.axpy(D.reduce_scatter_rows(dGI, self.f32("l.rsI", B, self.E)), dI)
+            ops.axpy(D.reduce_scatter_rows(dGT, self.f32("l.rsT", B, self.E)), dT)
+        else:
+            dT, dI, _, _ = self.loss_backward(l, grad_scale, local_gallery=True)
         self.bert_backward(t, dT)
         self.vit_backward(v, dI)
         self._saved = None
+
+    def allreduce_grads(self):
+        """SUM over ranks of the flat fp32 gradient (the loss is already normalised by the global batch)."""
+        from . import distributed as D
+        D.allreduce_sum_(self.params.grad)
 
     def optimizer_step(self, lr: float, weight_decay: float = 1e-4, max_grad_norm: float = 1.0):
         """clip_grad_norm_(max_grad_norm) + AdamW(betas 0.9/0.999, eps 1e-6) with the reference's decay grouping."""

@@ -8,6 +8,26 @@ from . import _lib as L
 L_ = L
 
 
+# optional launch trace: bench.py sets TRACE = [] to time every launch with CUDA events on the launching stream
+TRACE = None
+
+
+def _traced(label, flops=0.0, bytes_=0.0):
+    class _Ctx:
+        def __enter__(self_):
+            if TRACE is not None:
+                self_.s = torch.cuda.Event(enable_timing=True); self_.e = torch.cuda.Event(enable_timing=True)
+                self_.s.record()
+            return self_
+
+        def __exit__(self_, *a):
+            if TRACE is not None:
+                self_.e.record()
+                TRACE.append((label, flops, bytes_, self_.s, self_.e))
+            return False
+    return _Ctx()
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -49,8 +69,9 @@ def gemm(a, b, out, *, a_mn_major=0, b_mn_major=0, mode=L.EPI_LINEAR, bias=None,
         assert aux.dtype == torch.bfloat16 and aux.shape == (M, N) and aux.stride(1) == 1
         e.aux = aux.data_ptr(); e.ldaux = aux.stride(0)
     e.alpha = alpha
-    L.check(L.lib().clipk_gemm_bf16(_ptr(a), a.stride(0), int(a_mn_major), _ptr(b), b.stride(0), int(b_mn_major),
-                                    M, N, K, C.byref(e), int(splits), _stream()), "clipk_gemm_bf16")
+    with _traced("gemm", 2.0 * M * N * K):
+        L.check(L.lib().clipk_gemm_bf16(_ptr(a), a.stride(0), int(a_mn_major), _ptr(b), b.stride(0), int(b_mn_major),
+                                        M, N, K, C.byref(e), int(splits), _stream()), "clipk_gemm_bf16")
     return out
 
 
@@ -68,14 +89,16 @@ def attention_fwd(qkv, key_mask, ctx, lse, B, L, H):
     d = H * 64
     assert qkv.shape == (B * L, 3 * d) and qkv.is_contiguous() and ctx.shape == (B * L, d) and ctx.is_contiguous()
     assert lse.numel() == B * H * L
-    L_.check(L_.lib().clipk_attention_fwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), B, L, H, d, _stream()), "attention_fwd")
+    with _traced("attention_fwd", 4.0 * B * H * L * L * 64):
+        L_.check(L_.lib().clipk_attention_fwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), B, L, H, d, _stream()), "attention_fwd")
 
 
 def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H):
     d = H * 64
     assert dqkv.shape == (B * L, 3 * d) and dqkv.is_contiguous() and dctx.shape == (B * L, d) and dctx.is_contiguous()
-    L_.check(L_.lib().clipk_attention_bwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), _b16(dctx), _b16(dqkv), B, L, H, d,
-                                          _stream()), "attention_bwd")
+    with _traced("attention_bwd", 10.0 * B * H * L * L * 64):
+        L_.check(L_.lib().clipk_attention_bwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), _b16(dctx), _b16(dqkv), B, L, H, d,
+                                              _stream()), "attention_bwd")
 
 
 def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None, rows=None, ldx=None):
@@ -169,3 +192,8 @@ def grad_norm(g, n, max_norm, workspace, norm_and_coef):
 def adamw_step(p, g, m, v, w_bf16, n, lr, weight_decay, step, clip_coef=None, beta1=0.9, beta2=0.999, eps=1e-6):
     L_.check(L_.lib().clipk_adamw_step(_f32(p), _f32(g), _f32(m), _f32(v), _b16(w_bf16), n, lr, beta1, beta2, eps, weight_decay,
                                        step, _f32(clip_coef), _stream()), "adamw_step")
+
+
+def axpy(x, y, alpha=1.0):
+    assert x.numel() == y.numel() and x.is_contiguous() and y.is_contiguous()
+    L_.check(L_.lib().clipk_axpy(_f32(x), _f32(y), float(alpha), x.numel(), _stream()), "axpy")

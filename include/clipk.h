@@ -120,6 +120,8 @@ int clipk_l2norm_fwd(const float* x, float* y, float* norm, int rows, int d, cud
 int clipk_l2norm_bwd(const float* dy, const float* y, const float* norm, float* dx_f32, void* dx_bf16, int rows, int d,
                      cudaStream_t stream);
 int clipk_cast_bf16(const float* x, void* y_bf16, long long n, cudaStream_t stream);
+/* y += alpha * x (f32, n % 4 == 0): adds reduce-scattered gallery gradients onto the local embedding gradients */
+int clipk_axpy(const float* x, float* y, float alpha, long long n, cudaStream_t stream);
 
 /* -------------------------------------------------------------------------------------------- contrastive loss
  * One strip of the symmetric InfoNCE (appzoo/clip/model.py:148-164): logits = exp(logit_scale_log) * Q K^T for

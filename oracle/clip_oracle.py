@@ -65,7 +65,7 @@ def vit_l14_bert_large_config() -> dict:
 def tiny_config() -> dict:
     """Small shape used for committed golden fixtures (2 heads of 64 per tower)."""
     return dict(
-        model_type="chinese_clip", embed_dim=64,
+        model_type="chinese_clip", embed_dim=128,
         image_resolution=64, vision_layers=2, vision_width=128, vision_patch_size=16,
         vocab_size=512, text_attention_probs_dropout_prob=0.0, text_hidden_act="gelu",
         text_hidden_dropout_prob=0.0, text_hidden_size=128, text_initializer_range=0.02,

@@ -118,7 +118,7 @@ def tiny_case(CLIPApp, AdamW, outdir):
     opt.step()
     after = {n.replace("chinese_clip.", ""): p.detach().clone() for n, p in named}
     for k, v in after.items():
-        check_close("post-step " + k, sd_o[k], v, rtol=1e-5, atol=1e-7)
+        check_close("post-step " + k, sd_o[k], v, rtol=1e-5, atol=5e-6)  # Adam: every update is ~lr = 1e-3; fp32 grad rounding moves it by < 0.5 %
 
     blob = {"cfg_json": np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8),
             "pixels": pixels.numpy(), "ids": ids.numpy(),
