@@ -1,0 +1,75 @@
+"""CPU: host-side logic of the product package (parameter schema / flat layout / registry), no kernels."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from easynlp_b200.params import ParamStore, param_schema, uses_weight_decay, NO_GRAD
+from oracle import clip_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_schema_equals_reference_checkpoint_keys():
+    z = np.load(os.path.join(GOLD, "tiny_fwd_bwd.npz"))
+    cfg = json.loads(bytes(z["cfg_json"]).decode())
+    ref = {k[2:]: z[k].shape for k in z.files if k.startswith("w.")}
+    ref.pop("bert.embeddings.position_ids")
+    sch = param_schema(cfg)
+    assert set(sch) == set(ref)
+    for k, shp in sch.items():
+        assert tuple(shp) == tuple(ref[k]), k
+    b16 = param_schema(O.vit_b16_bert_base_config())
+    assert len(b16) == 353                              # + position_ids buffer = the 354 entries of SURVEY.md A.3
+    n = sum(int(np.prod(s)) if len(s) else 1 for s in b16.values())
+    assert n == 188_847_361 or abs(n - 188.85e6) < 0.01e6, n
+
+
+def test_flat_layout_groups_and_alignment():
+    cfg = O.tiny_config()
+    st = ParamStore(cfg, device="cpu")
+    offs = st.offsets
+    for n, o in offs.items():
+        assert o % 8 == 0, n
+    for n in st.schema:
+        if n in NO_GRAD:
+            assert offs[n] >= st.n_trainable
+        elif uses_weight_decay(n):
+            assert offs[n] < st.n_decay
+        else:
+            assert st.n_decay <= offs[n] < st.n_trainable
+    # BERT q/k/v are adjacent so that [3H, H] views exist
+    H = cfg["text_hidden_size"]
+    p = "bert.encoder.layer.1.attention.self."
+    assert offs[p + "key.weight"] - offs[p + "query.weight"] == H * H
+    assert offs[p + "value.weight"] - offs[p + "key.weight"] == H * H
+    assert offs[p + "key.bias"] - offs[p + "query.bias"] == H
+    fused = st.p(p + "query.weight", (3 * H, H))
+    st.p(p + "value.weight").fill_(3.0)
+    assert float(fused[2 * H:].min()) == 3.0 and float(fused[:2 * H].abs().max()) == 0.0
+    # decay rule mirrors the oracle's restatement of optimizers.py:519-523
+    for n in st.schema:
+        assert uses_weight_decay("chinese_clip." + n) == O.uses_weight_decay("chinese_clip." + n)
+
+
+def test_registry_prefix_match_and_unknown_app():
+    from easynlp_b200.appzoo import api
+    with pytest.raises(NotImplementedError):
+        api.get_application_model("sequence_classification", "/tmp/x")
+    assert api._match("clip") and api._match("clip_finetune")
+
+
+def test_synthetic_batch_layout():
+    from easynlp_b200.synthetic import synthetic_batch, random_state_dict
+    cfg = O.tiny_config()
+    px, ids = synthetic_batch(cfg, 5, 16, seed=3)
+    assert px.shape == (5, 3, 64, 64) and ids.shape == (5, 16) and ids.dtype == torch.int64
+    assert (ids[:, 0] == 101).all()
+    for r in ids:
+        nz = (r != 0).nonzero().flatten()
+        assert nz[-1].item() == len(nz) - 1           # contiguous tokens then 0-padding
+    sd = random_state_dict(cfg, seed=1)
+    assert set(sd) == set(param_schema(cfg))
+    assert float(sd["bert.embeddings.word_embeddings.weight"][0].abs().max()) == 0.0

@@ -1,0 +1,94 @@
+"""CPU: the oracle (oracle/clip_oracle.py) against the fixtures written by the UNMODIFIED reference (oracle/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import clip_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _tiny():
+    z = np.load(os.path.join(GOLD, "tiny_fwd_bwd.npz"))
+    cfg = json.loads(bytes(z["cfg_json"]).decode())
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w.")}
+    return z, cfg, sd
+
+
+def test_tiny_forward_loss_grads_and_step_match_reference():
+    z, cfg, sd = _tiny()
+    assert cfg == O.tiny_config()
+    pixels = torch.from_numpy(z["pixels"]); ids = torch.from_numpy(z["ids"])
+    st = {}
+    before = {k: v.clone() for k, v in sd.items()}
+    res = O.train_step(sd, cfg, pixels, ids, st, lr=1e-3, weight_decay=1e-4, max_grad_norm=1.0)
+    assert torch.allclose(res["logits_per_text"], torch.from_numpy(z["out.logits_per_text"]), rtol=1e-4, atol=1e-4)
+    assert abs(res["loss"].item() - float(z["out.loss"])) < 1e-5
+    assert abs(res["grad_norm"].item() - float(z["out.grad_norm"])) < 1e-4 * float(z["out.grad_norm"])
+    coef = min(1.0, 1.0 / (float(z["out.grad_norm"]) + 1e-6))
+    n_g = 0
+    for k in z.files:
+        if k.startswith("g."):
+            ref = torch.from_numpy(z[k]) * coef          # fixtures hold UNclipped grads; train_step clips in place
+            assert torch.allclose(res["grads"][k[2:]], ref, rtol=2e-3, atol=2e-6 + 2e-4 * ref.abs().max().item()), k
+            n_g += 1
+    assert n_g == len(res["grads"])
+    assert "bert.pooler.dense.weight" not in res["grads"]           # unused pooler: no gradient, no update
+    for k in z.files:
+        if k.startswith("a."):
+            assert torch.allclose(sd[k[2:]], torch.from_numpy(z[k]), rtol=1e-5, atol=5e-6), k
+    assert torch.equal(sd["bert.pooler.dense.weight"], before["bert.pooler.dense.weight"])
+
+
+def test_tiny_init_is_seed_deterministic():
+    z, cfg, sd = _tiny()
+    again = O.init_state_dict(cfg, seed=7, scale_boost=3.0)
+    for k, v in sd.items():
+        assert torch.equal(again[k], v), k
+
+
+def test_b16_forward_matches_reference():
+    z = np.load(os.path.join(GOLD, "b16_fwd.npz"))
+    cfg = dict(O.vit_b16_bert_base_config(), text_attention_probs_dropout_prob=0.0, text_hidden_dropout_prob=0.0)
+    sd = O.init_state_dict(cfg, seed=1234, scale_boost=2.0)
+    pixels, ids = O.synthetic_batch(cfg, 8, seq_len=77, seed=1234)
+    assert np.array_equal(ids.numpy(), z["ids"])
+    assert abs(pixels.double().sum().item() - float(z["pixels_checksum"])) < 1e-6
+    taps = {}
+    with torch.no_grad():
+        out = O.clip_forward(sd, cfg, pixels, ids, taps)
+    assert torch.allclose(out["image_embeds"], torch.from_numpy(z["out.image_embeds"]), atol=5e-6)
+    assert torch.allclose(out["text_embeds"], torch.from_numpy(z["out.text_embeds"]), atol=5e-6)
+    assert torch.allclose(out["logits_per_text"], torch.from_numpy(z["out.logits_per_text"]), atol=5e-5)
+    assert abs(O.clip_loss(out["logits_per_text"]).item() - float(z["out.loss"])) < 1e-5
+    for k, v in taps.items():
+        ref = z["tap." + k]
+        assert abs(v.double().abs().sum().item() - ref[1]) < 1e-4 * abs(ref[1]), k
+
+
+def test_recall_matches_reference_evaluator_loop():
+    z = np.load(os.path.join(GOLD, "recall.npz"))
+    img = torch.from_numpy(z["image_embeds"]); txt = torch.from_numpy(z["text_embeds"])
+    hits = O.recall_at_k(txt, img)
+    assert [hits[1], hits[5], hits[10]] == z["hits"].tolist()
+    ranks = O.rank_of_match(txt, img)
+    assert [int((ranks < k).sum()) for k in (1, 5, 10)] == z["hits"].tolist()
+
+
+def test_decay_grouping_and_schedule():
+    # easynlp/core/optimizers.py:490,519-523 substring rule
+    assert O.uses_weight_decay("chinese_clip.logit_scale")
+    assert O.uses_weight_decay("chinese_clip.visual.ln_pre.weight")
+    assert O.uses_weight_decay("chinese_clip.visual.class_embedding")
+    assert not O.uses_weight_decay("chinese_clip.visual.ln_pre.bias")
+    assert not O.uses_weight_decay("chinese_clip.visual.transformer.resblocks.0.attn.in_proj_bias")
+    assert not O.uses_weight_decay("chinese_clip.bert.encoder.layer.0.output.LayerNorm.weight")
+    assert O.uses_weight_decay("chinese_clip.bert.embeddings.word_embeddings.weight")
+    # easynlp/core/optimizers.py:191-204
+    assert O.warmup_linear_lambda(0, 10, 100) == 0.0
+    assert O.warmup_linear_lambda(5, 10, 100) == 0.5
+    assert O.warmup_linear_lambda(10, 10, 100) == 1.0
+    assert abs(O.warmup_linear_lambda(55, 10, 100) - 0.5) < 1e-12
+    assert O.warmup_linear_lambda(100, 10, 100) == 0.0
