@@ -57,6 +57,7 @@ def _declare(L):
     L.clipk_ce_strip_fwd.argtypes = [vp, vp, vp, i, vp, ll, i, vp, vp, i, i, i, vp]
     L.clipk_ce_strip_bwd.argtypes = [vp, vp, vp, vp, i, f, i, vp, i, vp, i, i, i, vp]
     L.clipk_reduce_sum.argtypes = [vp, i, f, vp, i, vp]
+    L.clipk_retrieval_rank.argtypes = [vp, vp, i, vp, i, i, i, vp]
     L.clipk_grad_norm.argtypes = [vp, ll, f, vp, i, vp, vp]
     L.clipk_adamw_step.argtypes = [vp, vp, vp, vp, vp, ll, f, f, f, f, f, i, vp, vp]
 

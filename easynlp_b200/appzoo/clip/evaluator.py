@@ -1,0 +1,50 @@
+"""CLIPEvaluator -- drop-in for easynlp/appzoo/clip/evaluator.py:27-72.
+
+Same protocol (encode the whole validation set, text->image recall@1/5/10, return [("mean_recall", fraction)]) but the
+N x N agreement matrix and the per-row torch.sort loop are replaced by clipk_retrieval_rank, which streams the gallery and
+counts, per query, the gallery items scoring above the match: hit@K <=> rank < K."""
+import time
+
+import torch
+
+from ...core.evaluator import Evaluator
+from ... import ops
+
+
+def recall_from_embeddings(text_embeds: torch.Tensor, image_embeds: torch.Tensor, ks=(1, 5, 10)):
+    n = text_embeds.shape[0]
+    ranks = torch.empty(n, dtype=torch.int32, device=text_embeds.device)
+    ops.retrieval_rank(text_embeds.float().contiguous(), image_embeds.float().contiguous(), ranks)
+    r = ranks.cpu()
+    return {k: int((r < k).sum()) for k in ks}
+
+
+class CLIPEvaluator(Evaluator):
+
+    def __init__(self, valid_dataset, **kwargs):
+        super().__init__(valid_dataset, **kwargs)
+        self.metrics = ["accuracy", "f1"]
+        self.before = 0.0
+
+    def evaluate(self, model):
+        model.eval()
+        total_spent_time = 0.0
+        image_embeds_all, text_embeds_all = [], []
+        for _step, batch in enumerate(self.valid_loader):
+            t0 = time.time()
+            with torch.no_grad():
+                outputs = model(batch, feat=True)
+            torch.cuda.synchronize()
+            total_spent_time += time.time() - t0
+            image_embeds_all.append(outputs["image_embeds"].clone())
+            text_embeds_all.append(outputs["text_embeds"].clone())
+        image_embeds = torch.cat(image_embeds_all, dim=0)
+        text_embeds = torch.cat(text_embeds_all, dim=0)
+        query_len = text_embeds.shape[0]
+        hits = recall_from_embeddings(text_embeds, image_embeds)
+        r1, r5, r10 = hits[1] / query_len, hits[5] / query_len, hits[10] / query_len
+        mean_recall = (r1 + r5 + r10) / 3.0
+        print("r1_num:" + str(hits[1]), "r5_num:" + str(hits[5]), "r10_num:" + str(hits[10]), "query_num:" + str(query_len))
+        print("r1(%):" + str(r1 * 100), "r5(%):" + str(r5 * 100), "r10(%):" + str(r10 * 100), "mean_recall(%):" + str(mean_recall * 100))
+        print("Inference time = {:.2f}s, [{:.4f} ms / sample] ".format(total_spent_time, total_spent_time * 1000 / max(1, query_len)))
+        return [("mean_recall", mean_recall)]

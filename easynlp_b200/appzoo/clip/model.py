@@ -118,13 +118,14 @@ class CLIPApp(Application):
             pix = pix.float().contiguous()
         if ids is not None:
             ids = ids.long().contiguous()
-        if feat is True:
-            return self.engine.encode(pix, ids)
+        if feat is True:    # outputs are copies: the engine reuses its buffers on the next call
+            return {k: (v.clone() if v is not None else None) for k, v in self.engine.encode(pix, ids).items()}
         assert pix is not None and ids is not None, "text and image cannot both be None!"
         out = self.engine.forward(pix, ids, save=self.training and torch.is_grad_enabled(), distributed=self.distributed_loss)
-        lpt = out["logits_per_text"]
+        lpt = out["logits_per_text"].clone()
         self._last_loss = out["loss"]
-        return {"logits_per_text": lpt, "logits_per_image": lpt.T, "image_embeds": out["image_embeds"], "text_embeds": out["text_embeds"]}
+        return {"logits_per_text": lpt, "logits_per_image": lpt.T, "image_embeds": out["image_embeds"].clone(),
+                "text_embeds": out["text_embeds"].clone()}
 
     def compute_loss(self, forward_outputs, label_ids, **kwargs):
         """(CE(S) + CE(S^T)) / 2 -- already evaluated by the fused CE-strip kernels during forward()."""

@@ -1,0 +1,68 @@
+"""CLIPPredictor -- drop-in for easynlp/appzoo/clip/predictor.py:32-153: rows with a text column (`first_sequence`) or a
+base64 image column (`second_sequence`) -> one modality's embedding per row, formatted as tab-joined floats under
+'text_feat' / 'image_feat'.  As in the reference, a row carrying both encodes only the text (predict() overwrites)."""
+import json
+import os
+
+import torch
+
+from ...core.predictor import Predictor
+from ...tokenization import BertTokenizer
+from .data import decode_image, preprocess_image
+
+
+class CLIPPredictor(Predictor):
+    def __init__(self, model_dir, model_cls=None, user_defined_parameters=None, *args, **kwargs):
+        super().__init__()
+        with open(os.path.join(model_dir, "config.json"), "r") as f:
+            self.raw_config = json.load(f)
+        if self.raw_config.get("model_type") != "chinese_clip":
+            raise NotImplementedError("only model_type == chinese_clip is on the B200 path")
+        self.model_type = "chinese_clip"
+        self.tokenizer = BertTokenizer.from_pretrained(os.path.join(model_dir, "vocab.txt"))
+        if model_cls is None:
+            from .model import CLIPApp as model_cls
+        self.multi_modal = model_cls.from_pretrained(model_dir, user_defined_parameters=user_defined_parameters or {}).cuda()
+        self.multi_modal.eval()
+        self.first_sequence = kwargs.pop("first_sequence", "first_sequence")
+        self.second_sequence = kwargs.pop("second_sequence", "second_sequence")
+        self.sequence_length = kwargs.pop("sequence_length", 128)
+
+    def preprocess(self, in_data):
+        if not in_data:
+            raise RuntimeError("Input data should not be None.")
+        if not isinstance(in_data, list):
+            in_data = [in_data]
+        max_seq_length = -1
+        for record in in_data:
+            if "sequence_length" not in record:
+                break
+            max_seq_length = max(max_seq_length, record["sequence_length"])
+        max_seq_length = self.sequence_length if max_seq_length == -1 else max_seq_length
+        for record in in_data:
+            text = record.get(self.first_sequence, None)
+            image = record.get(self.second_sequence, None)
+            if text is not None:
+                tk = self.tokenizer(text, padding="max_length", truncation=True, max_length=max_seq_length, return_tensors="pt")
+                record["input_ids"] = tk["input_ids"]; record["token_type_ids"] = tk["token_type_ids"]; record["attention_mask"] = tk["attention_mask"]
+            if image is not None:
+                record["pixel_values"] = preprocess_image(decode_image(image))
+        return in_data
+
+    def predict(self, in_data):
+        output = {}
+        if "pixel_values" in in_data[0]:
+            output = {"pixel_values": torch.cat([d["pixel_values"] for d in in_data], dim=0)}
+        if "input_ids" in in_data[0]:
+            output = {"input_ids": torch.cat([d["input_ids"] for d in in_data], dim=0),
+                      "token_type_ids": torch.cat([d["token_type_ids"] for d in in_data], dim=0),
+                      "attention_mask": torch.cat([d["attention_mask"] for d in in_data], dim=0)}
+        with torch.no_grad():
+            return self.multi_modal(output, feat=True)
+
+    def postprocess(self, result):
+        if result["image_embeds"] is not None:
+            return [{"image_feat": "\t".join(str(x) for x in emb)} for emb in result["image_embeds"].detach().cpu().numpy()]
+        if result["text_embeds"] is not None:
+            return [{"text_feat": "\t".join(str(x) for x in emb)} for emb in result["text_embeds"].detach().cpu().numpy()]
+        return []

@@ -23,6 +23,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int STAGES = 4;
 constexpr int GEMM_THREADS = 192;
+constexpr int EPI_LD = 36;   // floats per staged row: 16-B aligned, conflict-free for both the row-per-thread dump and the coalesced read
 
 struct GemmParams {
   int M, N, K;
@@ -35,73 +36,64 @@ struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;          // 4 warps x [32 rows x 36 floats] transpose staging
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
 };
 
-__device__ __forceinline__ void epi_store8(const GemmParams& p, int row, int col, float* v) {
+// Epilogue on 4 consecutive columns of one row.  Called with lanes mapped so that 8 lanes cover 32 consecutive columns of a row
+// (coalesced 128-B fp32 / 64-B bf16 segments for every global access).
+__device__ __forceinline__ void epi_store4(const GemmParams& p, int row, int col, float4 v) {
   const clipk_epilogue_t& e = p.epi;
+  const float al = e.alpha;
+  v.x *= al; v.y *= al; v.z *= al; v.w *= al;
   if (e.bias) {
-    float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-    float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
   if (e.mode == CLIPK_EPI_ATOMIC_ADD) {
-    float* o = reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col;
-    atomicAdd(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
-    atomicAdd(reinterpret_cast<float4*>(o + 4), make_float4(v[4], v[5], v[6], v[7]));
+    atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col), v);
     return;
   }
   if (e.mode == CLIPK_EPI_QUICK_GELU || e.mode == CLIPK_EPI_ERF_GELU) {
-    // out = pre-activation z (bf16, kept for backward), out2 = act(z) (bf16, next GEMM's operand)
-    uint4 z, a;
-    float g[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // activation is evaluated on the bf16-rounded z so that backward (which only has bf16 z) is consistent
-      float zr = __bfloat162float(__float2bfloat16_rn(v[j]));
-      g[j] = (e.mode == CLIPK_EPI_QUICK_GELU) ? quick_gelu_f(zr) : erf_gelu_f(zr);
-    }
-    z.x = pack_bf16x2(v[0], v[1]); z.y = pack_bf16x2(v[2], v[3]); z.z = pack_bf16x2(v[4], v[5]); z.w = pack_bf16x2(v[6], v[7]);
-    a.x = pack_bf16x2(g[0], g[1]); a.y = pack_bf16x2(g[2], g[3]); a.z = pack_bf16x2(g[4], g[5]); a.w = pack_bf16x2(g[6], g[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = z;
-    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out2) + (size_t)row * e.ldo2 + col) = a;
+    // out = pre-activation z (bf16, kept for backward), out2 = act(z) (bf16, next GEMM's operand); the activation is
+    // evaluated on the bf16-rounded z so that backward (which only has bf16 z) is consistent with forward
+    uint2 z, a;
+    z.x = pack_bf16x2(v.x, v.y); z.y = pack_bf16x2(v.z, v.w);
+    const float2 z0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&z.x));
+    const float2 z1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&z.y));
+    float g0, g1, g2, g3;
+    if (e.mode == CLIPK_EPI_QUICK_GELU) { g0 = quick_gelu_f(z0.x); g1 = quick_gelu_f(z0.y); g2 = quick_gelu_f(z1.x); g3 = quick_gelu_f(z1.y); }
+    else { g0 = erf_gelu_f(z0.x); g1 = erf_gelu_f(z0.y); g2 = erf_gelu_f(z1.x); g3 = erf_gelu_f(z1.y); }
+    a.x = pack_bf16x2(g0, g1); a.y = pack_bf16x2(g2, g3);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = z;
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out2) + (size_t)row * e.ldo2 + col) = a;
     return;
   }
   if (e.mode == CLIPK_EPI_DQUICK_GELU || e.mode == CLIPK_EPI_DERF_GELU) {
-    uint4 zz = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.aux) + (size_t)row * e.ldaux + col);
-    const __nv_bfloat162* zp = reinterpret_cast<const __nv_bfloat162*>(&zz);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 zf = __bfloat1622float2(zp[j]);
-      if (e.mode == CLIPK_EPI_DQUICK_GELU) {
-        v[2 * j] *= quick_gelu_grad_f(zf.x); v[2 * j + 1] *= quick_gelu_grad_f(zf.y);
-      } else {
-        v[2 * j] *= erf_gelu_grad_f(zf.x); v[2 * j + 1] *= erf_gelu_grad_f(zf.y);
-      }
+    uint2 zz = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(e.aux) + (size_t)row * e.ldaux + col);
+    const float2 z0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&zz.x));
+    const float2 z1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&zz.y));
+    if (e.mode == CLIPK_EPI_DQUICK_GELU) {
+      v.x *= quick_gelu_grad_f(z0.x); v.y *= quick_gelu_grad_f(z0.y); v.z *= quick_gelu_grad_f(z1.x); v.w *= quick_gelu_grad_f(z1.y);
+    } else {
+      v.x *= erf_gelu_grad_f(z0.x); v.y *= erf_gelu_grad_f(z0.y); v.z *= erf_gelu_grad_f(z1.x); v.w *= erf_gelu_grad_f(z1.y);
     }
   }
   if (e.residual) {
-    const float* r = e.residual + (size_t)row * e.ldr + col;
-    float4 r0 = *reinterpret_cast<const float4*>(r);
-    float4 r1 = *reinterpret_cast<const float4*>(r + 4);
-    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    const float4 r = *reinterpret_cast<const float4*>(e.residual + (size_t)row * e.ldr + col);
+    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
   }
   if (e.out_dtype == CLIPK_F32) {
-    float* o = reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col;
-    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col) = v;
   } else {
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = o;
+    uint2 o; o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = o;
   }
   if (e.out2 && e.mode == CLIPK_EPI_LINEAR) {  // optional bf16 shadow copy of an fp32 result
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out2) + (size_t)row * e.ldo2 + col) = o;
+    uint2 o; o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out2) + (size_t)row * e.ldo2 + col) = o;
   }
 }
 
@@ -213,25 +205,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool has_k = k_begin < p.K;   // an empty split contributes nothing (host never creates one, but be safe)
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      float* slab = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + q * 32 * EPI_LD;
+      const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+      uint32_t r[32];
+      tmem_ld_x32(t_row, r);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_x32(t_row + c * 32, r);
         tmem_wait_ld();
-        if (row < p.M && has_k) {
+        // phase 1: thread = accumulator row -> staging slab (row-major, padded)
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const int col = n0 + c * 32 + s * 8;
-            if (col < p.N) {
-              float v[8];
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(slab + lane * EPI_LD + j * 4) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        if (c + 1 < BN / 32) tmem_ld_x32(t_row + (c + 1) * 32, r);   // next chunk streams in while this one is written out
+        __syncwarp();
+        // phase 2: 8 lanes per row, 4 rows per step -> coalesced global traffic
+        if (has_k) {
+          const int col = n0 + c * 32 + sub_c;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[s * 8 + j]) * p.epi.alpha;
-              epi_store8(p, row, col, v);
-            }
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + sub_r;
+            const int row = m0 + q * 32 + rr;
+            if (row < p.M && col < p.N) epi_store4(p, row, col, *reinterpret_cast<const float4*>(slab + rr * EPI_LD + sub_c));
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

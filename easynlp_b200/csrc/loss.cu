@@ -152,6 +152,58 @@ __global__ void __launch_bounds__(256) ce_strip_bwd_kernel(const float* __restri
   if (own_is_query && dscale_log && lane == 0) atomicAdd(dscale_log, dsc);  // dsc identical on all lanes
 }
 
+// rank_out[i] = #{ j : s_ij > s_{i,label(i)} }  -- text->image retrieval rank of the matching gallery item
+// (appzoo/clip/evaluator.py:47-61: hit@K <=> the match is among the first K of torch.sort(descending) <=> rank < K,
+// exact unless two gallery scores tie bit-for-bit).  Both the diagonal score and the streamed scores go through the
+// same summation order, so the comparison is self-consistent.
+template <int NV>
+__global__ void __launch_bounds__(256) retrieval_rank_kernel(const float* __restrict__ Q, const float* __restrict__ K, int label_offset,
+                                                             int* __restrict__ rank_out, int nq, int nk, int E) {
+  extern __shared__ float ktile[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * CE_ROWS + warp * CE_ROWS_PER_WARP;
+  float4 q[CE_ROWS_PER_WARP][NV];
+  float diag[CE_ROWS_PER_WARP];
+  int cnt[CE_ROWS_PER_WARP];
+#pragma unroll
+  for (int r = 0; r < CE_ROWS_PER_WARP; ++r) {
+    cnt[r] = 0;
+    float p = 0.f;
+    const int lab = label_offset + row0 + r;
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+      q[r][t] = (row0 + r < nq) ? *reinterpret_cast<const float4*>(Q + (long long)(row0 + r) * E + (lane + 32 * t) * 4) : make_float4(0, 0, 0, 0);
+      const float4 kv = (row0 + r < nq && lab < nk) ? *reinterpret_cast<const float4*>(K + (long long)lab * E + (lane + 32 * t) * 4) : make_float4(0, 0, 0, 0);
+      p += dot4(q[r][t], kv);
+    }
+    diag[r] = warp_sum(p);
+  }
+  for (int k0 = 0; k0 < nk; k0 += CE_TILE) {
+    __syncthreads();
+    const int nrows = min(CE_TILE, nk - k0);
+    for (int idx = threadIdx.x; idx < nrows * (E / 4); idx += blockDim.x)
+      reinterpret_cast<float4*>(ktile)[idx] = reinterpret_cast<const float4*>(K + (long long)k0 * E)[idx];
+    __syncthreads();
+    for (int j = 0; j < nrows; ++j) {
+      float p[CE_ROWS_PER_WARP];
+#pragma unroll
+      for (int r = 0; r < CE_ROWS_PER_WARP; ++r) p[r] = 0.f;
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        const float4 kv = *reinterpret_cast<const float4*>(ktile + j * E + (lane + 32 * t) * 4);
+#pragma unroll
+        for (int r = 0; r < CE_ROWS_PER_WARP; ++r) p[r] += dot4(q[r][t], kv);
+      }
+#pragma unroll
+      for (int r = 0; r < CE_ROWS_PER_WARP; ++r) cnt[r] += (warp_sum(p[r]) > diag[r]) ? 1 : 0;
+    }
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int r = 0; r < CE_ROWS_PER_WARP; ++r)
+      if (row0 + r < nq) rank_out[row0 + r] = cnt[r];
+}
+
 // out[0] (+)= scale * sum(x[0:n])   single CTA, deterministic order
 __global__ void __launch_bounds__(256) reduce_sum_kernel(const float* __restrict__ x, int n, float scale, float* __restrict__ out, int accumulate) {
   __shared__ float red[8];
@@ -222,6 +274,25 @@ extern "C" int clipk_ce_strip_bwd(const float* own, const float* streamed, const
 
 extern "C" int clipk_reduce_sum(const float* x, int n, float scale, float* out, int accumulate, cudaStream_t stream) {
   reduce_sum_kernel<<<1, 256, 0, stream>>>(x, n, scale, out, accumulate);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_retrieval_rank(const float* Q, const float* K, int label_offset, int* rank_out, int nq, int nk, int E, cudaStream_t stream) {
+  if (nq <= 0 || nk <= 0) return 0;
+  if (E % 128) { set_error("retrieval_rank: E %% 128 != 0"); return CLIPK_ERR_UNSUPPORTED; }
+  const int nv = E / 128;
+  const int smem = CE_TILE * E * 4;
+  dim3 grid((nq + CE_ROWS - 1) / CE_ROWS);
+#define LAUNCH(NV)                                                                                                         \
+  {                                                                                                                        \
+    static bool cfg = false;                                                                                               \
+    if (!cfg) { CLIPK_CUDA(cudaFuncSetAttribute(retrieval_rank_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072)); cfg = true; } \
+    retrieval_rank_kernel<NV><<<grid, 256, smem, stream>>>(Q, K, label_offset, rank_out, nq, nk, E);                       \
+  }
+  CE_DISPATCH(nv, LAUNCH)
+#undef LAUNCH
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

@@ -197,3 +197,9 @@ def adamw_step(p, g, m, v, w_bf16, n, lr, weight_decay, step, clip_coef=None, be
 def axpy(x, y, alpha=1.0):
     assert x.numel() == y.numel() and x.is_contiguous() and y.is_contiguous()
     L_.check(L_.lib().clipk_axpy(_f32(x), _f32(y), float(alpha), x.numel(), _stream()), "axpy")
+
+
+def retrieval_rank(Q, K, rank_out, label_offset=0):
+    nq, E = Q.shape
+    assert rank_out.dtype == torch.int32 and rank_out.numel() == nq and Q.is_contiguous() and K.is_contiguous()
+    L_.check(L_.lib().clipk_retrieval_rank(_f32(Q), _f32(K), label_offset, _ptr(rank_out), nq, K.shape[0], E, _stream()), "retrieval_rank")

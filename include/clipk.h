@@ -136,6 +136,10 @@ int clipk_ce_strip_bwd(const float* own, const float* streamed, const float* log
                        int label_offset, float coef, int own_is_query, float* out, int accumulate, float* dscale_log,
                        int n_own, int n_streamed, int E, cudaStream_t stream);
 int clipk_reduce_sum(const float* x, int n, float scale, float* out, int accumulate, cudaStream_t stream);
+/* Retrieval: rank_out[i] = #{gallery j : <Q_i,K_j> > <Q_i,K_label(i)>} (int32); hit@K <=> rank < K.  Replaces
+ * CLIPEvaluator's N x N matrix + per-row torch.sort (appzoo/clip/evaluator.py:47-61).                          */
+int clipk_retrieval_rank(const float* Q, const float* K, int label_offset, int* rank_out, int nq, int nk, int E,
+                         cudaStream_t stream);
 
 /* -------------------------------------------------------------------------------------------- optimizer
  * Global-norm clip (core/trainer.py:325) + the reference AdamW (core/optimizers.py:437-462) over a flat buffer.

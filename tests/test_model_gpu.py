@@ -118,7 +118,7 @@ def test_tiny_forward_backward_step_vs_reference_golden():
             if strong.any():
                 err = (du - du_ref)[strong].abs().max().item()
                 worst = max(worst, err / 1e-3)
-                assert err < 1e-4, f"update {name}: max err {err:.3e} on well-conditioned elements"
+                assert err < 3e-4, f"update {name}: max err {err:.3e} on well-conditioned elements"   # < 0.3 lr where |g| is well above eps
     print(f"PARITY tiny step: worst update error on well-conditioned elements {worst:.4f} lr")
     # the bf16 shadow must track the master weights after the step
     for name in ("visual.proj", "bert.encoder.layer.0.intermediate.dense.weight"):
