@@ -22,8 +22,8 @@ namespace clipk {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 192;
-constexpr int EPI_LD = 36;   // floats per staged row: 16-B aligned, conflict-free for both the row-per-thread dump and the coalesced read
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning half of the tile's columns
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 
 struct GemmParams {
   int M, N, K;
@@ -36,64 +36,97 @@ struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;          // 4 warps x [32 rows x 36 floats] transpose staging
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;          // per epilogue warp: [32 rows x 32 floats] XOR-swizzled transpose staging
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;
   static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
 };
 
-// Epilogue on 4 consecutive columns of one row.  Called with lanes mapped so that 8 lanes cover 32 consecutive columns of a row
-// (coalesced 128-B fp32 / 64-B bf16 segments for every global access).
-__device__ __forceinline__ void epi_store4(const GemmParams& p, int row, int col, float4 v) {
+// Epilogue of one staged [32 rows x 32 cols] chunk.  8 lanes cover 32 consecutive columns of a row and a warp covers 4 rows per
+// step, so every global access is a coalesced 128-B (fp32) / 64-B (bf16) segment.  All global LOADS of the chunk (residual, GELU
+// pre-activation) are issued before any store: `out` may alias `residual`, so the compiler cannot hoist them itself and a
+// load -> store -> load chain would expose one DRAM latency per row group.
+__device__ __forceinline__ void epi_chunk(const GemmParams& p, const float* slab, int row0, int col, int sub_r, int sub_c) {
   const clipk_epilogue_t& e = p.epi;
-  const float al = e.alpha;
-  v.x *= al; v.y *= al; v.z *= al; v.w *= al;
-  if (e.bias) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  const bool col_ok = col < p.N;
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + sub_r;
+    v[i] = *reinterpret_cast<const float4*>(slab + rr * 32 + (((sub_c >> 2) ^ (rr & 7)) << 2));
   }
+  if (!col_ok) return;
+  const float al = e.alpha;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { v[i].x = v[i].x * al + b.x; v[i].y = v[i].y * al + b.y; v[i].z = v[i].z * al + b.z; v[i].w = v[i].w * al + b.w; }
+
   if (e.mode == CLIPK_EPI_ATOMIC_ADD) {
-    atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + 4 * i + sub_r;
+      if (row < p.M) atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col), v[i]);
+    }
     return;
   }
   if (e.mode == CLIPK_EPI_QUICK_GELU || e.mode == CLIPK_EPI_ERF_GELU) {
-    // out = pre-activation z (bf16, kept for backward), out2 = act(z) (bf16, next GEMM's operand); the activation is
-    // evaluated on the bf16-rounded z so that backward (which only has bf16 z) is consistent with forward
-    uint2 z, a;
-    z.x = pack_bf16x2(v.x, v.y); z.y = pack_bf16x2(v.z, v.w);
-    const float2 z0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&z.x));
-    const float2 z1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&z.y));
-    float g0, g1, g2, g3;
-    if (e.mode == CLIPK_EPI_QUICK_GELU) { g0 = quick_gelu_f(z0.x); g1 = quick_gelu_f(z0.y); g2 = quick_gelu_f(z1.x); g3 = quick_gelu_f(z1.y); }
-    else { g0 = erf_gelu_f(z0.x); g1 = erf_gelu_f(z0.y); g2 = erf_gelu_f(z1.x); g3 = erf_gelu_f(z1.y); }
-    a.x = pack_bf16x2(g0, g1); a.y = pack_bf16x2(g2, g3);
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = z;
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out2) + (size_t)row * e.ldo2 + col) = a;
+    // out = pre-activation z (bf16, kept for backward), out2 = act(z) (bf16, next GEMM's operand); the activation is evaluated on
+    // the bf16-rounded z so that backward (which only has bf16 z) is consistent with forward
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + 4 * i + sub_r;
+      uint2 z, a;
+      z.x = pack_bf16x2(v[i].x, v[i].y); z.y = pack_bf16x2(v[i].z, v[i].w);
+      const float2 z0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&z.x));
+      const float2 z1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&z.y));
+      float g0, g1, g2, g3;
+      if (e.mode == CLIPK_EPI_QUICK_GELU) { g0 = quick_gelu_f(z0.x); g1 = quick_gelu_f(z0.y); g2 = quick_gelu_f(z1.x); g3 = quick_gelu_f(z1.y); }
+      else { g0 = erf_gelu_f(z0.x); g1 = erf_gelu_f(z0.y); g2 = erf_gelu_f(z1.x); g3 = erf_gelu_f(z1.y); }
+      a.x = pack_bf16x2(g0, g1); a.y = pack_bf16x2(g2, g3);
+      if (row < p.M) {
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = z;
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out2) + (size_t)row * e.ldo2 + col) = a;
+      }
+    }
     return;
   }
   if (e.mode == CLIPK_EPI_DQUICK_GELU || e.mode == CLIPK_EPI_DERF_GELU) {
-    uint2 zz = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(e.aux) + (size_t)row * e.ldaux + col);
-    const float2 z0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&zz.x));
-    const float2 z1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&zz.y));
-    if (e.mode == CLIPK_EPI_DQUICK_GELU) {
-      v.x *= quick_gelu_grad_f(z0.x); v.y *= quick_gelu_grad_f(z0.y); v.z *= quick_gelu_grad_f(z1.x); v.w *= quick_gelu_grad_f(z1.y);
-    } else {
-      v.x *= erf_gelu_grad_f(z0.x); v.y *= erf_gelu_grad_f(z0.y); v.z *= erf_gelu_grad_f(z1.x); v.w *= erf_gelu_grad_f(z1.y);
+    uint2 zz[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + 4 * i + sub_r;
+      zz[i] = (row < p.M) ? *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(e.aux) + (size_t)row * e.ldaux + col) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 z0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&zz[i].x));
+      const float2 z1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&zz[i].y));
+      if (e.mode == CLIPK_EPI_DQUICK_GELU) {
+        v[i].x *= quick_gelu_grad_f(z0.x); v[i].y *= quick_gelu_grad_f(z0.y); v[i].z *= quick_gelu_grad_f(z1.x); v[i].w *= quick_gelu_grad_f(z1.y);
+      } else {
+        v[i].x *= erf_gelu_grad_f(z0.x); v[i].y *= erf_gelu_grad_f(z0.y); v[i].z *= erf_gelu_grad_f(z1.x); v[i].w *= erf_gelu_grad_f(z1.y);
+      }
     }
   }
   if (e.residual) {
-    const float4 r = *reinterpret_cast<const float4*>(e.residual + (size_t)row * e.ldr + col);
-    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    float4 r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + 4 * i + sub_r;
+      r[i] = (row < p.M) ? *reinterpret_cast<const float4*>(e.residual + (size_t)row * e.ldr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i].x += r[i].x; v[i].y += r[i].y; v[i].z += r[i].z; v[i].w += r[i].w; }
   }
-  if (e.out_dtype == CLIPK_F32) {
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col) = v;
-  } else {
-    uint2 o; o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = o;
-  }
-  if (e.out2 && e.mode == CLIPK_EPI_LINEAR) {  // optional bf16 shadow copy of an fp32 result
-    uint2 o; o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out2) + (size_t)row * e.ldo2 + col) = o;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row0 + 4 * i + sub_r;
+    if (row >= p.M) continue;
+    uint2 o; o.x = pack_bf16x2(v[i].x, v[i].y); o.y = pack_bf16x2(v[i].z, v[i].w);
+    if (e.out_dtype == CLIPK_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col) = v[i];
+    else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = o;
+    if (e.out2) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out2) + (size_t)row * e.ldo2 + col) = o;   // bf16 shadow of an fp32 result
   }
 }
 
@@ -118,7 +151,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, 2 * BN);
@@ -193,43 +226,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ================================================================ epilogue warps (TMEM lane quarter = warp % 4)
+    // ================================================================ epilogue warps: TMEM lane quarter = warp % 4, column half = (warp-2)/4
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int CHUNKS = BN / 32 / 2;        // 32-column chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
+    float* slab = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + (warp - 2) * 32 * 32;
+    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int ks = tile / tiles_mn;
       const int mn = tile - ks * tiles_mn;
       const int m0 = (mn / p.n_tiles) * BM;
-      const int n0 = (mn % p.n_tiles) * BN;
+      const int n0 = (mn % p.n_tiles) * BN + half * (BN / 2);
       const int k_begin = ks * p.k_per_split;
       const bool has_k = k_begin < p.K;   // an empty split contributes nothing (host never creates one, but be safe)
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      float* slab = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + q * 32 * EPI_LD;
-      const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
       uint32_t r[32];
       tmem_ld_x32(t_row, r);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < CHUNKS; ++c) {
         tmem_wait_ld();
-        // phase 1: thread = accumulator row -> staging slab (row-major, padded)
+        // phase 1: thread = accumulator row -> staging slab (row-major, 16-B units XOR-swizzled by row)
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(slab + lane * EPI_LD + j * 4) =
+          *reinterpret_cast<float4*>(slab + lane * 32 + ((j ^ (lane & 7)) << 2)) =
               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        if (c + 1 < BN / 32) tmem_ld_x32(t_row + (c + 1) * 32, r);   // next chunk streams in while this one is written out
+        if (c + 1 < CHUNKS) tmem_ld_x32(t_row + (c + 1) * 32, r);   // next chunk streams in while this one is written out
         __syncwarp();
         // phase 2: 8 lanes per row, 4 rows per step -> coalesced global traffic
-        if (has_k) {
-          const int col = n0 + c * 32 + sub_c;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + sub_r;
-            const int row = m0 + q * 32 + rr;
-            if (row < p.M && col < p.N) epi_store4(p, row, col, *reinterpret_cast<const float4*>(slab + rr * EPI_LD + sub_c));
-          }
-        }
+        if (has_k) epi_chunk(p, slab, m0 + q * 32, n0 + c * 32 + sub_c, sub_r, sub_c);
         __syncwarp();
       }
       tc_fence_before();
