@@ -149,23 +149,21 @@ def run_native(args):
     d_pixels = pixels.to(dev); d_ids = ids.to(dev)
     lr = 1e-5
 
-    def step(px, tk):
-        eng.zero_grad()
-        out = eng.forward(px, tk, save=True, want_logits=False, distributed=dist_on)
-        eng.backward()
-        if dist_on:
-            eng.allreduce_grads()
-        eng.optimizer_step(lr=lr, weight_decay=1e-4, max_grad_norm=1.0)
-        return out["loss"]
+    use_graph = not args.no_graph
 
-    for _ in range(args.warmup):
+    def step(px, tk):
+        return eng.train_step(px, tk, lr=lr, weight_decay=1e-4, max_grad_norm=1.0, distributed=dist_on, use_graph=use_graph)["loss"]
+
+    l0 = L.launch_count()
+    step(d_pixels, d_ids)                      # first call is always eager: counts the kernels one step launches
+    launches_per_step = L.launch_count() - l0
+    for _ in range(max(2, args.warmup - 1)):   # >= 3 untimed steps in total; the 3rd captures the CUDA graph
         step(d_pixels, d_ids)
     torch.cuda.synchronize(); D.barrier()
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    launches0 = L.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     D.barrier(); torch.cuda.synchronize()
     e0.record()
@@ -174,7 +172,7 @@ def run_native(args):
     e1.record()
     torch.cuda.synchronize(); D.barrier()
     ms = e0.elapsed_time(e1)
-    launches = L.launch_count() - launches0
+    launches = launches_per_step * args.steps   # kernels inside the replayed graph (the host counter only sees eager launches)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if dist_on:
@@ -183,50 +181,60 @@ def run_native(args):
     value = world * B / (ms_per_step * 1e-3)
     loss_val = float(loss.item())
 
-    # ---- e2e through the plugin surface with host inputs (H2D + loss read-back inside the timed region)
+    # ---- e2e through the plugin surface (Trainer.train_step on a collated HOST batch: H2D copy + step + loss.item() per step)
     e2e = None
     try:
         from easynlp_b200.appzoo.clip.model import CLIPApp
+        from easynlp_b200.core.trainer import Trainer
+        from easynlp_b200.utils.arguments import parse_args
+
+        class _Synth(torch.utils.data.Dataset):
+            label_enumerate_values = None
+
+            def __len__(self):
+                return B * 1000
+
+            def __getitem__(self, i):
+                raise RuntimeError("bench feeds collated batches directly")
+
+            def batch_fn(self, f):
+                return f
         app = CLIPApp()
         app.engine = eng; app.model_type = "chinese_clip"; app._wrap_params(); app.distributed_loss = dist_on
         app.train()
+        targs = parse_args(["--micro_batch_size", str(B), "--learning_rate", str(lr), "--epoch_num", "1", "--warmup_proportion", "0.0",
+                            "--data_threads", "0", "--logging_steps", "1000000"])
+        trainer = Trainer(model=app, train_dataset=_Synth(), evaluator=None, args=targs, use_cuda_graph=use_graph)
         h2d = pixels.numel() * 4 + ids.numel() * 8
 
         def e2e_step():
-            batch = {"pixel_values": pixels, "input_ids": ids, "label_ids": []}
-            label_ids = batch.pop("label_ids")
-            app.zero_grad()
-            fo = app(batch)
-            l = app.compute_loss(fo, label_ids)["loss"]
-            l.backward()
-            if dist_on:
-                eng.allreduce_grads()
-            eng.optimizer_step(lr=lr, weight_decay=1e-4, max_grad_norm=1.0)
-            return l.item()
-        for _ in range(2):
+            return trainer.train_step({"pixel_values": pixels, "input_ids": ids, "label_ids": []})
+        for _ in range(3):
             e2e_step()
         torch.cuda.synchronize(); D.barrier()
         n_e2e = max(3, min(args.steps, 10))
         s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
         s0.record()
         for _ in range(n_e2e):
-            e2e_step()
+            e2e_loss = e2e_step()
         s1.record(); torch.cuda.synchronize(); D.barrier()
         t2 = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
         if dist_on:
             torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = t2.item() / n_e2e
         e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": e2e_ms, "api": "CLIPApp.forward/compute_loss + loss.backward() + fused clip/AdamW"}
+               "ms_per_step": e2e_ms, "loss": e2e_loss,
+               "api": "easynlp_b200.core.Trainer.train_step(collated host batch): pinned H2D + fwd/loss/bwd/clip/AdamW + loss.item()"}
     except Exception as ex:  # the headline must not die because of the wrapper
-        e2e = {"value": None, "unit": "pairs/s", "error": repr(ex)}
+        import traceback
+        e2e = {"value": None, "unit": "pairs/s", "error": repr(ex), "trace": traceback.format_exc()[-600:]}
 
     # ---- roofline of the dominant kernel: every GEMM launch of one step timed with events on the launching stream
     peaks, peak_kind = measured_peaks()
     roofline = None
     if rank == 0:
         ops.TRACE = []
-        step(d_pixels, d_ids)
+        eng.train_step(d_pixels, d_ids, lr=lr, weight_decay=1e-4, max_grad_norm=1.0, distributed=dist_on, use_graph=False)
         torch.cuda.synchronize()
         tr = ops.TRACE; ops.TRACE = None
         agg = {}
@@ -258,7 +266,8 @@ def run_native(args):
                            "per_gpu_batch": B, "global_batch": world * B, "seq_len": Lt, "image": "224x224x3 fp32", "parallelism": f"dp{world}",
                            "loss": "global-batch InfoNCE via embedding all-gather" if dist_on else "local == global batch",
                            "dropout": 0.0, "l2": "per-step working set (~15 GB of activations) >> 126 MB L2; no explicit flush needed",
-                           "init": "random-init weights of the named architecture (no checkpoints reachable)"},
+                           "init": "random-init weights of the named architecture (no checkpoints reachable)",
+                           "launch": "one CUDA graph per step" if use_graph else "eager launches"},
                 "loss": loss_val, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if dist_on:
@@ -274,6 +283,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--seq-len", type=int, default=77)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3

@@ -59,7 +59,8 @@ def _declare(L):
     L.clipk_reduce_sum.argtypes = [vp, i, f, vp, i, vp]
     L.clipk_retrieval_rank.argtypes = [vp, vp, i, vp, i, i, i, vp]
     L.clipk_grad_norm.argtypes = [vp, ll, f, vp, i, vp, vp]
-    L.clipk_adamw_step.argtypes = [vp, vp, vp, vp, vp, ll, f, f, f, f, f, i, vp, vp]
+    L.clipk_adamw_step.argtypes = [vp, vp, vp, vp, vp, ll, f, f, f, f, f, i, vp, vp, vp]
+    L.clipk_adam_schedule.argtypes = [vp, vp, f, i, i, f, f, vp]
 
 
 def check(rc: int, what: str = ""):

@@ -36,6 +36,7 @@ class Trainer(object):
         if not hasattr(model, "engine") or model.engine is None:
             raise TypeError("easynlp_b200.Trainer drives models backed by the clipk engine (easynlp_b200 CLIPApp)")
         self.engine = model.engine
+        self.use_graph = bool(kwargs.get("use_cuda_graph", True))
         self.set_train_loader(train_dataset, self.args)
         self.set_model_and_optimizer(model, self.args)
         self.resume_from_ckpt(self.args)
@@ -95,16 +96,34 @@ class Trainer(object):
             for _step, batch in enumerate(self._train_loader):
                 if _step < skip:
                     continue
-                label_ids = batch.pop("label_ids", None)
-                forward_outputs = self._model(batch)
-                loss_dict = self.model_module.compute_loss(forward_outputs, label_ids)
-                _loss = loss_dict["loss"]
-                if args.gradient_accumulation_steps > 1:
-                    _loss = _loss / args.gradient_accumulation_steps
-                _loss.backward()
-                self.after_iter(_step, epoch, loss_dict)
+                loss_val = self.train_step(batch)
+                self.after_iter(_step, epoch, loss_val)
         self.after_train()
         print("Training Time: {}".format(time.time() - t_start))
+
+    def train_step(self, batch):
+        """One micro-step on a collated batch (host or device tensors): forward, loss, backward and -- every
+        gradient_accumulation_steps -- clip + AdamW + schedule + zero_grad; returns the loss as a Python float (the reference
+        reads loss.item() every micro-step too, trainer.py:342).  Without gradient accumulation the whole step runs as one
+        captured CUDA graph (ClipEngine.train_step); otherwise through model(batch) / compute_loss / loss.backward()."""
+        args = self.args
+        label_ids = batch.pop("label_ids", None)
+        if args.gradient_accumulation_steps == 1 and self.use_graph:
+            out = self.engine.train_step(batch["pixel_values"], batch["input_ids"], lr=args.learning_rate, weight_decay=args.weight_decay,
+                                         max_grad_norm=args.max_grad_norm, warmup_steps=self._warmup_steps, t_total=self._t_total,
+                                         distributed=getattr(self.model_module, "distributed_loss", False), use_graph=True)
+            self._sched_step += 1
+            return out["loss"].item()
+        forward_outputs = self._model(batch)
+        loss_dict = self.model_module.compute_loss(forward_outputs, label_ids)
+        _loss = loss_dict["loss"]
+        if args.gradient_accumulation_steps > 1:
+            _loss = _loss / args.gradient_accumulation_steps
+        _loss.backward()
+        loss_val = loss_dict["loss"].item()
+        if (self._global_step + 1) % args.gradient_accumulation_steps == 0:
+            self.optimizer_step()
+        return loss_val
 
     def optimizer_step(self):
         if D.world_size() > 1:
@@ -113,11 +132,8 @@ class Trainer(object):
         self._sched_step += 1
         self.engine.zero_grad()
 
-    def after_iter(self, _step, _epoch, loss_dict):
+    def after_iter(self, _step, _epoch, loss_val):
         args = self.args
-        loss_val = loss_dict["loss"].item()                                   # D2H sync per micro-step, as trainer.py:342
-        if (self._global_step + 1) % args.gradient_accumulation_steps == 0:
-            self.optimizer_step()
         if args.is_master_node and (self._global_step + 1) % args.logging_steps == 0:
             rec = {"epoch": _epoch, "global_step": self._global_step + 1, "loss": loss_val, "lr": self.learning_rate}
             self._log.append(rec)

@@ -44,12 +44,16 @@ __device__ __forceinline__ void store_row8_sw128(uint8_t* tile_base, int row, in
 }
 
 // ====================================================================================================== forward
-__global__ void __launch_bounds__(128, 2)
+// 256 threads: warp w owns TMEM lane quarter (w & 3) -- one thread per query row -- and column half (w >> 2).
+constexpr int ATT_THREADS = 256;
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, half = warp >> 2;
   const int k_bytes = p.lk_pad * 128;
   const int p_bytes = ((p.lk_pad + 63) >> 6) * 16384;
   const int v_off = max(p_bytes, 16384 + k_bytes);
@@ -58,7 +62,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sP = smem;             // overlays Q and K once S = Q K^T has completed
   uint8_t* sV = smem + v_off;
   float* smask = reinterpret_cast<float*>(sV + k_bytes);          // [256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smask + 256);      // load, s, o
+  float* sred = smask + 256;                                      // [2][128] row max per column half
+  float* ssum = sred + 256;                                       // [2][128] row sum per column half
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ssum + 256);       // load, s, o
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
 
   const uint32_t ncols = p.lk_pad > 128 ? 256 : (p.lk_pad > 64 ? 128 : 64);
@@ -68,7 +74,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_holder, ncols);
-  for (int j = tid; j < 256; j += 128)
+  for (int j = tid; j < 256; j += ATT_THREADS)
     smask[j] = (j < p.L) ? (p.mask ? p.mask[(long long)b * p.L + j] * LOG2E : 0.f) : -INFINITY;
   tc_fence_before();
   __syncthreads();
@@ -91,20 +97,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   mbar_wait(&bars[1], 0);
   tc_fence_after();
 
-  const int row = tid;
+  const int row = q4 * 32 + lane;
   const int q = qt * 128 + row;
-  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16);
   const float sc = p.scale * LOG2E;
+  const int split = ((p.lk_pad >> 1) + 15) & ~15;
+  const int c_begin = half ? split : 0, c_end = half ? p.lk_pad : split;
   float mx = -INFINITY;
-  for (int c0 = 0; c0 < p.lk_pad; c0 += 16) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
     uint32_t r[16];
     tmem_ld_x16(t_row + c0, r);
     tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]) * sc + smask[c0 + j]);
   }
+  sred[half * 128 + row] = mx;
+  __syncthreads();
+  mx = fmaxf(sred[row], sred[128 + row]);
   float sum = 0.f;
-  for (int c0 = 0; c0 < p.lk_pad; c0 += 16) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
     uint32_t r[16];
     tmem_ld_x16(t_row + c0, r);
     tmem_wait_ld();
@@ -117,6 +128,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     store_row8_sw128(sP, row, c0, pv);
     store_row8_sw128(sP, row, c0 + 8, pv + 8);
   }
+  ssum[half * 128 + row] = sum;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -129,29 +141,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       umma_bf16(tmem, desc_k(aP + (t >> 2) * 16384 + (t & 3) * 32), desc_mn(aV + t * 2048, 16384), idesc, t > 0);
     umma_commit(&bars[2]);
   }
+  sum = ssum[row] + ssum[128 + row];
   mbar_wait(&bars[2], 0);
   tc_fence_after();
   {
     const float inv = 1.0f / sum;
-    bf16* dst = p.ctx + (long long)(b * p.L + q) * p.d + h * 64;
+    bf16* dst = p.ctx + (long long)(b * p.L + q) * p.d + h * 64 + half * 32;
+    uint32_t r[32];
+    tmem_ld_x32(t_row + half * 32, r);
+    tmem_wait_ld();
+    if (q < p.L) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(t_row + c * 32, r);
-      tmem_wait_ld();
-      if (q < p.L) {
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(r[s * 8 + 0]) * inv, __uint_as_float(r[s * 8 + 1]) * inv);
-          o.y = pack_bf16x2(__uint_as_float(r[s * 8 + 2]) * inv, __uint_as_float(r[s * 8 + 3]) * inv);
-          o.z = pack_bf16x2(__uint_as_float(r[s * 8 + 4]) * inv, __uint_as_float(r[s * 8 + 5]) * inv);
-          o.w = pack_bf16x2(__uint_as_float(r[s * 8 + 6]) * inv, __uint_as_float(r[s * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + c * 32 + s * 8) = o;
-        }
+      for (int s4 = 0; s4 < 4; ++s4) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(r[s4 * 8 + 0]) * inv, __uint_as_float(r[s4 * 8 + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(r[s4 * 8 + 2]) * inv, __uint_as_float(r[s4 * 8 + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(r[s4 * 8 + 4]) * inv, __uint_as_float(r[s4 * 8 + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(r[s4 * 8 + 6]) * inv, __uint_as_float(r[s4 * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + s4 * 8) = o;
       }
+      if (half == 0 && p.lse) p.lse[((long long)b * p.H + h) * p.L + q] = (mx + log2f(sum)) * LN2;
     }
-    if (q < p.L && p.lse) p.lse[((long long)b * p.H + h) * p.L + q] = (mx + log2f(sum)) * LN2;
   }
   tc_fence_before();
   __syncthreads();
@@ -160,13 +170,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 // ====================================================================================================== backward
 // TMEM map (512 columns): [0,256) S -> dP -> dQ(64) ; [256,384) dV key-tiles 0,1 ; [384,512) dK key-tiles 0,1
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmDO,
                 const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int h = blockIdx.x, b = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, half = warp >> 2;     // TMEM lane quarter (one thread per row) / column half
   const int k_bytes = p.lk_pad * 128;
   const int n_kt = p.lk_pad > 128 ? 2 : 1;       // 128-key tiles of dK / dV
   const int kt_pad = n_kt * 128;
@@ -187,13 +198,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_holder, 512);
-  for (int j = tid; j < 256; j += 128)
+  for (int j = tid; j < 256; j += ATT_THREADS)
     smask[j] = (j < p.L) ? (p.mask ? p.mask[(long long)b * p.L + j] * LOG2E : 0.f) : -INFINITY;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
-  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16);
+  const int split = ((p.lk_pad >> 1) + 15) & ~15;   // balance the VALID key columns between the two halves
+  const int c_begin = half ? split : 0, c_end = half ? kt_pad : split;
   const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sDS);
   const float sc = p.scale * LOG2E;
   const int ksteps = p.lk_pad >> 4;
@@ -206,7 +219,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   for (int qt = 0; qt < p.q_tiles; ++qt) {
     const uint32_t ph = qt & 1;
-    const int row = tid;
+    const int row = q4 * 32 + lane;
     const int q = qt * 128 + row;
     const bool qvalid = q < p.L;
     // ---- loads + S = Q K^T
@@ -243,7 +256,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(&bars[2], ph);
     tc_fence_after();
     // ---- pass 1: P = exp(S - lse)  (rows beyond L and keys beyond L are exactly zero)
-    for (int c0 = 0; c0 < kt_pad; c0 += 16) {
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
       float pv[16];
       if (c0 < p.lk_pad) {
         uint32_t r[16];
@@ -278,7 +291,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(&bars[3], ph);
     tc_fence_after();
     // ---- pass 2: dS = scale * P o (dP - D)
-    for (int c0 = 0; c0 < kt_pad; c0 += 16) {
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
       float dv[16];
       if (c0 < p.lk_pad) {
         uint32_t r[16];
@@ -323,22 +336,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(&bars[4], ph);
     tc_fence_after();
     {
-      bf16* dst = p.dqkv + (long long)(b * p.L + q) * (3 * p.d) + h * 64;
+      bf16* dst = p.dqkv + (long long)(b * p.L + q) * (3 * p.d) + h * 64 + half * 32;
+      uint32_t r[32];
+      tmem_ld_x32(t_row + half * 32, r);
+      tmem_wait_ld();
+      if (qvalid) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_x32(t_row + c * 32, r);
-        tmem_wait_ld();
-        if (qvalid) {
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(r[s * 8 + 0]), __uint_as_float(r[s * 8 + 1]));
-            o.y = pack_bf16x2(__uint_as_float(r[s * 8 + 2]), __uint_as_float(r[s * 8 + 3]));
-            o.z = pack_bf16x2(__uint_as_float(r[s * 8 + 4]), __uint_as_float(r[s * 8 + 5]));
-            o.w = pack_bf16x2(__uint_as_float(r[s * 8 + 6]), __uint_as_float(r[s * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + c * 32 + s * 8) = o;
-          }
+        for (int s4 = 0; s4 < 4; ++s4) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(r[s4 * 8 + 0]), __uint_as_float(r[s4 * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(r[s4 * 8 + 2]), __uint_as_float(r[s4 * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(r[s4 * 8 + 4]), __uint_as_float(r[s4 * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(r[s4 * 8 + 6]), __uint_as_float(r[s4 * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + s4 * 8) = o;
         }
       }
     }
@@ -347,29 +357,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
   }
 
-  // ---- epilogue: dK, dV rows (one thread per key)
+  // ---- epilogue: dK, dV rows (one thread per key; column half 0 writes dV, half 1 writes dK)
   for (int mt = 0; mt < n_kt; ++mt) {
-    const int key = mt * 128 + tid;
+    const int key = mt * 128 + q4 * 32 + lane;
     const bool kvalid = key < p.L;
+    bf16* dst = p.dqkv + (long long)(b * p.L + key) * (3 * p.d) + (half == 0 ? 2 : 1) * p.d + h * 64;
+    const uint32_t tcol = (half == 0 ? 256 : 384) + mt * 64;
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {   // 0: dV -> V block, 1: dK -> K block
-      bf16* dst = p.dqkv + (long long)(b * p.L + key) * (3 * p.d) + (which == 0 ? 2 : 1) * p.d + h * 64;
-      const uint32_t tcol = (which == 0 ? 256 : 384) + mt * 64;
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(t_row + tcol + c * 32, r);
+      tmem_wait_ld();
+      if (kvalid) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_x32(t_row + tcol + c * 32, r);
-        tmem_wait_ld();
-        if (kvalid) {
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(r[s * 8 + 0]), __uint_as_float(r[s * 8 + 1]));
-            o.y = pack_bf16x2(__uint_as_float(r[s * 8 + 2]), __uint_as_float(r[s * 8 + 3]));
-            o.z = pack_bf16x2(__uint_as_float(r[s * 8 + 4]), __uint_as_float(r[s * 8 + 5]));
-            o.w = pack_bf16x2(__uint_as_float(r[s * 8 + 6]), __uint_as_float(r[s * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + c * 32 + s * 8) = o;
-          }
+        for (int s4 = 0; s4 < 4; ++s4) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(r[s4 * 8 + 0]), __uint_as_float(r[s4 * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(r[s4 * 8 + 2]), __uint_as_float(r[s4 * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(r[s4 * 8 + 4]), __uint_as_float(r[s4 * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(r[s4 * 8 + 6]), __uint_as_float(r[s4 * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + c * 32 + s4 * 8) = o;
         }
       }
     }
@@ -405,13 +412,13 @@ extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void*
   const int k_bytes = p.lk_pad * 128;
   const int p_bytes = ((p.lk_pad + 63) >> 6) * 16384;
   const int v_off = p_bytes > 16384 + k_bytes ? p_bytes : 16384 + k_bytes;
-  const int smem = v_off + k_bytes + 1024 + 64 + 1024;
+  const int smem = v_off + k_bytes + 1024 + 2048 + 64 + 1024;
   static int configured = 0;
   if (configured < smem) {
     CLIPK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  attn_fwd_kernel<<<dim3(p.q_tiles, H, B), 128, smem, stream>>>(tQ, tKV, p);
+  attn_fwd_kernel<<<dim3(p.q_tiles, H, B), ATT_THREADS, smem, stream>>>(tQ, tKV, p);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;
@@ -440,7 +447,7 @@ extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const
     CLIPK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  attn_bwd_kernel<<<dim3(H, B), 128, smem, stream>>>(tQ, tKV, tDO, p);
+  attn_bwd_kernel<<<dim3(H, B), ATT_THREADS, smem, stream>>>(tQ, tKV, tDO, p);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

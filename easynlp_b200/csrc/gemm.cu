@@ -130,6 +130,28 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, const float* slab
   }
 }
 
+// L2 prefetch of the epilogue's global INPUTS (fp32 residual / bf16 GELU pre-activation) for one warp's [32 rows x BN/2 cols]
+// slice, issued one tile ahead so the epilogue's loads hit L2 instead of exposing a DRAM latency per chunk.
+template <int BN>
+__device__ __forceinline__ void epi_prefetch(const GemmParams& p, int tile, int tiles_mn, int q, int half, int lane) {
+  const clipk_epilogue_t& e = p.epi;
+  if (!e.residual && !e.aux) return;
+  const int mn = tile % tiles_mn;
+  const int row = (mn / p.n_tiles) * BM + q * 32 + lane;
+  const int col = (mn % p.n_tiles) * BN + half * (BN / 2);
+  if (row >= p.M || col >= p.N) return;
+  if (e.residual) {
+    const char* ptr = reinterpret_cast<const char*>(e.residual + (size_t)row * e.ldr + col);
+#pragma unroll
+    for (int i = 0; i < (BN / 2) * 4 / 128; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + i * 128));
+  }
+  if (e.aux) {
+    const char* ptr = reinterpret_cast<const char*>(reinterpret_cast<const bf16*>(e.aux) + (size_t)row * e.ldaux + col);
+#pragma unroll
+    for (int i = 0; i < (BN / 2) * 2 / 128; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + i * 128));
+  }
+}
+
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -233,7 +255,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0; uint32_t acc_phase = 0;
     float* slab = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + (warp - 2) * 32 * 32;
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+    if ((int)blockIdx.x < num_tiles) epi_prefetch<BN>(p, blockIdx.x, tiles_mn, q, half, lane);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (tile + (int)gridDim.x < num_tiles) epi_prefetch<BN>(p, tile + gridDim.x, tiles_mn, q, half, lane);
       const int ks = tile / tiles_mn;
       const int mn = tile - ks * tiles_mn;
       const int m0 = (mn / p.n_tiles) * BM;

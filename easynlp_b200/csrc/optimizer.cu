@@ -26,6 +26,25 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
   }
 }
 
+// One thread: step += 1; hyper = {lr_k, lr_k * sqrt(1 - b2^k) / (1 - b1^k)} with lr_k = base_lr * lambda(k - 1), lambda = the
+// reference's EasyNLPWarmupLinearSchedule (core/optimizers.py:191-204; scheduler.step() runs AFTER optimizer.step(), so step k uses
+// lambda(k-1)).  t_total <= 0 means a constant learning rate.
+__global__ void adam_schedule_kernel(int* __restrict__ step, float* __restrict__ hyper, float base_lr, int warmup_steps, int t_total,
+                                     float beta1, float beta2) {
+  const int k = step[0] + 1;
+  step[0] = k;
+  float lam = 1.f;
+  if (t_total > 0) {
+    const int s = k - 1;
+    if (s < warmup_steps) lam = (float)s / (float)max(1, warmup_steps);
+    else lam = fmaxf(0.f, (float)(t_total - s) / fmaxf(1.f, (float)(t_total - warmup_steps)));
+  }
+  const float lr = base_lr * lam;
+  const double bc1 = 1.0 - pow((double)beta1, (double)k), bc2 = 1.0 - pow((double)beta2, (double)k);
+  hyper[0] = lr;
+  hyper[1] = (float)((double)lr * sqrt(bc2) / bc1);
+}
+
 // norm_out[0] = sqrt(sum partials) ; norm_out[1] = clip coefficient min(1, max_norm / (norm + 1e-6))
 __global__ void __launch_bounds__(256) gradnorm_final_kernel(const double* __restrict__ partials, int n, float max_norm, float* __restrict__ norm_out) {
   __shared__ double red[8];
@@ -48,8 +67,9 @@ __global__ void __launch_bounds__(256) gradnorm_final_kernel(const double* __res
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, bf16* __restrict__ w_bf16, long long n4, float lr, float beta1,
                                                     float beta2, float eps, float weight_decay, float step_size,
-                                                    const float* __restrict__ clip_coef) {
+                                                    const float* __restrict__ clip_coef, const float* __restrict__ dev_hyper) {
   const float cc = clip_coef ? clip_coef[0] : 1.f;
+  if (dev_hyper) { lr = dev_hyper[0]; step_size = dev_hyper[1]; }   // device-resident schedule: lets a CUDA graph replay the step
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
     float4 pv = reinterpret_cast<float4*>(p)[t];
     float4 gv = reinterpret_cast<const float4*>(g)[t];
@@ -93,9 +113,11 @@ extern "C" int clipk_grad_norm(const float* g, long long n, float max_norm, doub
 }
 
 extern "C" int clipk_adamw_step(float* p, const float* g, float* m, float* v, void* w_bf16, long long n, float lr, float beta1, float beta2,
-                                float eps, float weight_decay, int step, const float* clip_coef, cudaStream_t stream) {
+                                float eps, float weight_decay, int step, const float* clip_coef, const float* dev_hyper,
+                                cudaStream_t stream) {
   if (n == 0) return 0;
-  if (n % 4 || step < 1) { set_error("adamw: n %% 4 != 0 or step < 1"); return CLIPK_ERR_ARG; }
+  if (n % 4 || (step < 1 && !dev_hyper)) { set_error("adamw: n %% 4 != 0 or step < 1"); return CLIPK_ERR_ARG; }
+  if (step < 1) step = 1;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
@@ -103,7 +125,15 @@ extern "C" int clipk_adamw_step(float* p, const float* g, float* m, float* v, vo
   long long nb = (n4 + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (nb > cap) nb = cap;
-  adamw_kernel<<<(int)nb, 256, 0, stream>>>(p, g, m, v, (bf16*)w_bf16, n4, lr, beta1, beta2, eps, weight_decay, step_size, clip_coef);
+  adamw_kernel<<<(int)nb, 256, 0, stream>>>(p, g, m, v, (bf16*)w_bf16, n4, lr, beta1, beta2, eps, weight_decay, step_size, clip_coef, dev_hyper);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_adam_schedule(int* step_dev, float* hyper_dev, float base_lr, int warmup_steps, int t_total, float beta1, float beta2,
+                                   cudaStream_t stream) {
+  adam_schedule_kernel<<<1, 1, 0, stream>>>(step_dev, hyper_dev, base_lr, warmup_steps, t_total, beta1, beta2);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

@@ -354,16 +354,72 @@ class ClipEngine:
         from . import distributed as D
         D.allreduce_sum_(self.params.grad)
 
-    def optimizer_step(self, lr: float, weight_decay: float = 1e-4, max_grad_norm: float = 1.0):
-        """clip_grad_norm_(max_grad_norm) + AdamW(betas 0.9/0.999, eps 1e-6) with the reference's decay grouping."""
+    def optimizer_step(self, lr: float, weight_decay: float = 1e-4, max_grad_norm: float = 1.0, warmup_steps: int = 0, t_total: int = 0):
+        """clip_grad_norm_(max_grad_norm) + AdamW(betas 0.9/0.999, eps 1e-6) with the reference's decay grouping.
+        The step counter and {lr, bias-corrected step size} live on the device (clipk_adam_schedule), so the same launches can be
+        replayed from a CUDA graph.  t_total == 0: `lr` is the learning rate of THIS step (host-side scheduler, Trainer);
+        t_total > 0: `lr` is the base rate and the reference's warmup-linear schedule is evaluated on the device."""
         P_ = self.params
         P_.step += 1
         n_tr, n_dec = P_.n_trainable, P_.n_decay
+        if not hasattr(self, "_dev_step"):
+            self._dev_step = torch.full((1,), P_.step - 1, dtype=torch.int32, device=self.dev)
+            self._dev_hyper = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        ops.adam_schedule(self._dev_step, self._dev_hyper, float(lr), int(warmup_steps), int(t_total))
         coef = None
         if max_grad_norm and max_grad_norm > 0:
             ops.grad_norm(P_.grad, n_tr, float(max_grad_norm), self._norm_ws, self.norm_and_coef)
             coef = self.norm_and_coef[1:]
         ops.adamw_step(P_.master[:n_dec], P_.grad[:n_dec], P_.exp_avg[:n_dec], P_.exp_avg_sq[:n_dec], P_.shadow[:n_dec], n_dec,
-                       lr, weight_decay, P_.step, coef)
+                       lr, weight_decay, 0, coef, dev_hyper=self._dev_hyper)
         ops.adamw_step(P_.master[n_dec:n_tr], P_.grad[n_dec:n_tr], P_.exp_avg[n_dec:n_tr], P_.exp_avg_sq[n_dec:n_tr],
-                       P_.shadow[n_dec:n_tr], n_tr - n_dec, lr, 0.0, P_.step, coef)
+                       P_.shadow[n_dec:n_tr], n_tr - n_dec, lr, 0.0, 0, coef, dev_hyper=self._dev_hyper)
+
+    # ------------------------------------------------------------------ whole training step, optionally as ONE CUDA graph
+    def _step_body(self, pixels, ids, hp):
+        self.zero_grad()
+        out = self.forward(pixels, ids, save=True, want_logits=hp["want_logits"], distributed=hp["distributed"])
+        self.backward(hp["grad_scale"])
+        if hp["allreduce"]:
+            self.allreduce_grads()
+        self.optimizer_step(hp["lr"], hp["weight_decay"], hp["max_grad_norm"], hp["warmup_steps"], hp["t_total"])
+        return out
+
+    def train_step(self, pixels, ids, lr, weight_decay=1e-4, max_grad_norm=1.0, warmup_steps=0, t_total=0, distributed=False,
+                   want_logits=False, use_graph=True, grad_scale=None, allreduce=None):
+        """zero_grad -> forward -> backward -> (grad all-reduce) -> clip + AdamW.  `pixels` / `ids` may live on the host (pinned):
+        they are copied into static device buffers.  After two eager calls (which size every buffer and set kernel attributes) the
+        whole step is captured once into a CUDA graph and replayed: ~2.6 k kernel launches collapse into one cudaGraphLaunch.
+        With use_graph, `lr` must be the BASE rate and the schedule (warmup_steps, t_total) is evaluated on the device.
+        Returns the dict of forward(); tensors are engine-owned buffers, valid until the next call."""
+        from . import distributed as D
+        if allreduce is None:
+            allreduce = D.world_size() > 1
+        if grad_scale is None:      # local-loss data parallelism averages gradients like DDP; the global loss is already normalised
+            grad_scale = 1.0 if (distributed or D.world_size() == 1) else 1.0 / D.world_size()
+        B, Lt = ids.shape
+        key = (B, Lt, bool(allreduce), float(lr), float(weight_decay), float(max_grad_norm), int(warmup_steps), int(t_total), bool(distributed), bool(want_logits), float(grad_scale))
+        st = getattr(self, "_gs", None)
+        if st is None or st["key"] != key:
+            st = {"key": key, "calls": 0, "graph": None, "out": None,
+                  "pixels": torch.empty((B, 3, self.R, self.R), dtype=torch.float32, device=self.dev),
+                  "ids": torch.empty((B, Lt), dtype=torch.int64, device=self.dev)}
+            self._gs = st
+        st["pixels"].copy_(pixels, non_blocking=True)
+        st["ids"].copy_(ids, non_blocking=True)
+        hp = {"lr": lr, "weight_decay": weight_decay, "max_grad_norm": max_grad_norm, "warmup_steps": warmup_steps, "t_total": t_total,
+              "distributed": distributed, "want_logits": want_logits, "grad_scale": grad_scale, "allreduce": allreduce}
+        if not use_graph or st["calls"] < 2:
+            st["calls"] += 1
+            return self._step_body(st["pixels"], st["ids"], hp)
+        if st["graph"] is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            host_step = self.params.step
+            with torch.cuda.graph(g):
+                st["out"] = self._step_body(st["pixels"], st["ids"], hp)
+            self.params.step = host_step      # capture does not execute
+            st["graph"] = g
+        self.params.step += 1
+        st["graph"].replay()
+        return st["out"]

@@ -189,9 +189,15 @@ def grad_norm(g, n, max_norm, workspace, norm_and_coef):
              "grad_norm")
 
 
-def adamw_step(p, g, m, v, w_bf16, n, lr, weight_decay, step, clip_coef=None, beta1=0.9, beta2=0.999, eps=1e-6):
+def adamw_step(p, g, m, v, w_bf16, n, lr, weight_decay, step, clip_coef=None, beta1=0.9, beta2=0.999, eps=1e-6, dev_hyper=None):
     L_.check(L_.lib().clipk_adamw_step(_f32(p), _f32(g), _f32(m), _f32(v), _b16(w_bf16), n, lr, beta1, beta2, eps, weight_decay,
-                                       step, _f32(clip_coef), _stream()), "adamw_step")
+                                       step, _f32(clip_coef), _f32(dev_hyper), _stream()), "adamw_step")
+
+
+def adam_schedule(step_dev, hyper_dev, base_lr, warmup_steps, t_total, beta1=0.9, beta2=0.999):
+    assert step_dev.dtype == torch.int32 and hyper_dev.dtype == torch.float32 and hyper_dev.numel() >= 2
+    L_.check(L_.lib().clipk_adam_schedule(_ptr(step_dev), _ptr(hyper_dev), base_lr, warmup_steps, t_total, beta1, beta2, _stream()),
+             "adam_schedule")
 
 
 def axpy(x, y, alpha=1.0):

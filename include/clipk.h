@@ -146,9 +146,16 @@ int clipk_retrieval_rank(const float* Q, const float* K, int label_offset, int* 
  * norm_and_coef[0] = ||g||_2, [1] = min(1, max_norm / (norm + 1e-6)).  workspace: doubles, len >= 4*#SM.        */
 int clipk_grad_norm(const float* g, long long n, float max_norm, double* workspace, int workspace_len,
                     float* norm_and_coef, cudaStream_t stream);
-/* p, m, v updated in place; w_bf16 (optional) = bf16(p) refreshed for the GEMMs; clip_coef optional device scalar */
+/* p, m, v updated in place; w_bf16 (optional) = bf16(p) refreshed for the GEMMs; clip_coef optional device scalar.
+ * dev_hyper (optional, device float[2] = {lr, lr*sqrt(1-b2^k)/(1-b1^k)}) overrides lr/step so that a captured CUDA
+ * graph can be replayed while the schedule advances on the device (clipk_adam_schedule).                          */
 int clipk_adamw_step(float* p, const float* g, float* m, float* v, void* w_bf16, long long n, float lr, float beta1,
-                     float beta2, float eps, float weight_decay, int step, const float* clip_coef, cudaStream_t stream);
+                     float beta2, float eps, float weight_decay, int step, const float* clip_coef, const float* dev_hyper,
+                     cudaStream_t stream);
+/* step_dev[0] += 1 and hyper_dev = {lr_k, step_size_k} for the reference's warmup-linear schedule
+ * (core/optimizers.py:191-204); t_total <= 0 -> constant lr.                                                      */
+int clipk_adam_schedule(int* step_dev, float* hyper_dev, float base_lr, int warmup_steps, int t_total, float beta1,
+                        float beta2, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

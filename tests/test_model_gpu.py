@@ -114,11 +114,12 @@ def test_tiny_forward_backward_step_vs_reference_golden():
         # clearly non-zero (|g| > 1e-3 after clipping scale)
         g = torch.from_numpy(z["g." + name]) if ("g." + name) in z.files else None
         if g is not None:
-            strong = g.abs() > 0.05 * g.abs().max()
+            coef = min(1.0, 1.0 / (gn_ref + 1e-6))
+            strong = (g * coef).abs() > 1e-4                # |clipped g| >= 100 eps: the update is -lr*sign(g) to within 1 %
             if strong.any():
                 err = (du - du_ref)[strong].abs().max().item()
                 worst = max(worst, err / 1e-3)
-                assert err < 3e-4, f"update {name}: max err {err:.3e} on well-conditioned elements"   # < 0.3 lr where |g| is well above eps
+                assert err < 1e-4, f"update {name}: max err {err:.3e} on well-conditioned elements"   # < 0.1 lr
     print(f"PARITY tiny step: worst update error on well-conditioned elements {worst:.4f} lr")
     # the bf16 shadow must track the master weights after the step
     for name in ("visual.proj", "bert.encoder.layer.0.intermediate.dense.weight"):
