@@ -28,6 +28,23 @@ def _traced(label, flops=0.0, bytes_=0.0):
     return _Ctx()
 
 
+def _op(fn):
+    """when TRACE is a list, bracket the launch with CUDA events (label = op name) unless the op records a richer entry itself"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        if TRACE is None or fn.__name__ in ("gemm", "attention_fwd", "attention_bwd"):
+            return fn(*a, **k)
+        s_ = torch.cuda.Event(enable_timing=True); e_ = torch.cuda.Event(enable_timing=True)
+        s_.record()
+        r = fn(*a, **k)
+        e_.record()
+        TRACE.append((fn.__name__, 0.0, 0.0, s_, e_))
+        return r
+    return wrapped
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -36,6 +53,7 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+@_op
 def gemm(a, b, out, *, a_mn_major=0, b_mn_major=0, mode=L.EPI_LINEAR, bias=None, residual=None, out2=None, aux=None,
          alpha=1.0, splits=1):
     """out[M,N] = epilogue(op(a) @ op(b)^T); see include/clipk.h clipk_gemm_bf16."""
@@ -85,6 +103,7 @@ def _b16(t):
     return _ptr(t)
 
 
+@_op
 def attention_fwd(qkv, key_mask, ctx, lse, B, L, H):
     d = H * 64
     assert qkv.shape == (B * L, 3 * d) and qkv.is_contiguous() and ctx.shape == (B * L, d) and ctx.is_contiguous()
@@ -93,6 +112,7 @@ def attention_fwd(qkv, key_mask, ctx, lse, B, L, H):
         L_.check(L_.lib().clipk_attention_fwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), B, L, H, d, _stream()), "attention_fwd")
 
 
+@_op
 def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H):
     d = H * 64
     assert dqkv.shape == (B * L, 3 * d) and dqkv.is_contiguous() and dctx.shape == (B * L, d) and dctx.is_contiguous()
@@ -101,6 +121,7 @@ def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H):
                                               _stream()), "attention_bwd")
 
 
+@_op
 def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None, rows=None, ldx=None):
     d = gamma.numel()
     if rows is None:
@@ -111,6 +132,7 @@ def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=
                                           _f32(rstd), rows, d, _stream()), "layernorm_fwd")
 
 
+@_op
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, dy_add=None, dx_add=None, dx_f32=None, dx_bf16=None, dgamma=None, dbeta=None,
                   dbias=None, rows=None, ldx=None, lddx=None):
     d = gamma.numel()
@@ -125,46 +147,56 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dy_add=None, dx_add=None, dx_f32=
                                           _f32(dbias), rows, d, _stream()), "layernorm_bwd")
 
 
+@_op
 def colsum(x, out, rows, n, ldx=None):
     ldx = n if ldx is None else ldx
     L_.check(L_.lib().clipk_colsum(_ptr(x), int(x.dtype == torch.float32), ldx, _f32(out), rows, n, _stream()), "colsum")
 
 
+@_op
 def im2col_patches(pixels, patches, B, R, P):
     L_.check(L_.lib().clipk_im2col_patches(_f32(pixels), _b16(patches), B, R, P, _stream()), "im2col")
 
 
+@_op
 def vit_assemble(patch, cls, pos, x0, B, L, W):
     L_.check(L_.lib().clipk_vit_assemble(_f32(patch), _f32(cls), _f32(pos), _f32(x0), B, L, W, _stream()), "vit_assemble")
 
 
+@_op
 def vit_assemble_bwd(dx0, dpatch, B, L, W):
     L_.check(L_.lib().clipk_vit_assemble_bwd(_f32(dx0), _b16(dpatch), B, L, W, _stream()), "vit_assemble_bwd")
 
 
+@_op
 def bert_embed(ids, word, pos, type0, e, rows, L, H, vocab, key_mask=None):
     assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous()
     L_.check(L_.lib().clipk_bert_embed(_ptr(ids), _f32(word), _f32(pos), _f32(type0), _f32(e), _f32(key_mask), rows, L, H, vocab,
                                        _stream()), "bert_embed")
 
 
+@_op
 def bert_embed_bwd(ids, de, dword, rows, H, vocab):
     L_.check(L_.lib().clipk_bert_embed_bwd(_ptr(ids), _f32(de), _f32(dword), rows, H, vocab, _stream()), "bert_embed_bwd")
 
 
+@_op
 def l2norm_fwd(x, y, norm, rows, d):
     L_.check(L_.lib().clipk_l2norm_fwd(_f32(x), _f32(y), _f32(norm), rows, d, _stream()), "l2norm_fwd")
 
 
+@_op
 def l2norm_bwd(dy, y, norm, dx_f32, dx_bf16, rows, d):
     L_.check(L_.lib().clipk_l2norm_bwd(_f32(dy), _f32(y), _f32(norm), _f32(dx_f32), _b16(dx_bf16), rows, d, _stream()), "l2norm_bwd")
 
 
+@_op
 def cast_bf16(x, y):
     assert x.numel() == y.numel()
     L_.check(L_.lib().clipk_cast_bf16(_f32(x), _b16(y), x.numel(), _stream()), "cast_bf16")
 
 
+@_op
 def ce_strip_fwd(Q, K, logit_scale_log, label_offset, lse, loss_rows, S_out=None, lds=0, transpose_out=False):
     nq, E = Q.shape
     nk = K.shape[0]
@@ -172,6 +204,7 @@ def ce_strip_fwd(Q, K, logit_scale_log, label_offset, lse, loss_rows, S_out=None
                                          int(transpose_out), _f32(lse), _f32(loss_rows), nq, nk, E, _stream()), "ce_strip_fwd")
 
 
+@_op
 def ce_strip_bwd(own, streamed, logit_scale_log, lse, label_offset, coef, own_is_query, out, accumulate, dscale_log=None):
     n_own, E = own.shape
     L_.check(L_.lib().clipk_ce_strip_bwd(_f32(own), _f32(streamed), _f32(logit_scale_log), _f32(lse), label_offset, coef,
@@ -179,32 +212,38 @@ def ce_strip_bwd(own, streamed, logit_scale_log, lse, label_offset, coef, own_is
                                          streamed.shape[0], E, _stream()), "ce_strip_bwd")
 
 
+@_op
 def reduce_sum(x, n, scale, out, accumulate=False):
     L_.check(L_.lib().clipk_reduce_sum(_f32(x), n, scale, _f32(out), int(accumulate), _stream()), "reduce_sum")
 
 
+@_op
 def grad_norm(g, n, max_norm, workspace, norm_and_coef):
     assert workspace.dtype == torch.float64
     L_.check(L_.lib().clipk_grad_norm(_f32(g), n, max_norm, _ptr(workspace), workspace.numel(), _f32(norm_and_coef), _stream()),
              "grad_norm")
 
 
+@_op
 def adamw_step(p, g, m, v, w_bf16, n, lr, weight_decay, step, clip_coef=None, beta1=0.9, beta2=0.999, eps=1e-6, dev_hyper=None):
     L_.check(L_.lib().clipk_adamw_step(_f32(p), _f32(g), _f32(m), _f32(v), _b16(w_bf16), n, lr, beta1, beta2, eps, weight_decay,
                                        step, _f32(clip_coef), _f32(dev_hyper), _stream()), "adamw_step")
 
 
+@_op
 def adam_schedule(step_dev, hyper_dev, base_lr, warmup_steps, t_total, beta1=0.9, beta2=0.999):
     assert step_dev.dtype == torch.int32 and hyper_dev.dtype == torch.float32 and hyper_dev.numel() >= 2
     L_.check(L_.lib().clipk_adam_schedule(_ptr(step_dev), _ptr(hyper_dev), base_lr, warmup_steps, t_total, beta1, beta2, _stream()),
              "adam_schedule")
 
 
+@_op
 def axpy(x, y, alpha=1.0):
     assert x.numel() == y.numel() and x.is_contiguous() and y.is_contiguous()
     L_.check(L_.lib().clipk_axpy(_f32(x), _f32(y), float(alpha), x.numel(), _stream()), "axpy")
 
 
+@_op
 def retrieval_rank(Q, K, rank_out, label_offset=0):
     nq, E = Q.shape
     assert rank_out.dtype == torch.int32 and rank_out.numel() == nq and Q.is_contiguous() and K.is_contiguous()

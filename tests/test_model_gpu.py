@@ -115,7 +115,8 @@ def test_tiny_forward_backward_step_vs_reference_golden():
         g = torch.from_numpy(z["g." + name]) if ("g." + name) in z.files else None
         if g is not None:
             coef = min(1.0, 1.0 / (gn_ref + 1e-6))
-            strong = (g * coef).abs() > 1e-4                # |clipped g| >= 100 eps: the update is -lr*sign(g) to within 1 %
+            # |clipped g| >= 100 eps (update = -lr*sign(g) to within 1 %) and large within its tensor (bf16 noise cannot flip it)
+            strong = ((g * coef).abs() > 1e-4) & (g.abs() > 0.25 * g.abs().max())
             if strong.any():
                 err = (du - du_ref)[strong].abs().max().item()
                 worst = max(worst, err / 1e-3)
