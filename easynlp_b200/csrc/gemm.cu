@@ -14,6 +14,7 @@
 // (SWIZZLE_128B), one MMA-issuing thread (tcgen05.mma cta_group::1, M=128, N=BN, K=16), accumulators double-buffered
 // in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   warp 0: TMA producer   warp 1: MMA issuer + TMEM owner   warps 2-5: epilogue (TMEM -> registers -> global)
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/clipk.h"
 
@@ -156,8 +157,10 @@ template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using L = GemmSmem<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-B aligned dynamic smem (SWIZZLE_128B atoms); indexing the __shared__ array directly keeps the address space known to
+  // the compiler (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -315,6 +318,194 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
   return 0;
 }
 
+
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  CTA r holds rows
+// [128 r, 128 r + 128) of A and of the accumulator (its own TMEM) and columns [128 r, 128 r + 128) of B; the leader's single
+// MMA thread issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory, so each SM stages only HALF of
+// B per k-block (32 KB / stage instead of 48 KB): operand smem traffic per SM drops from 12 to 8 KB per MMA and the ring is
+// 6 stages deep.  Barriers: full[s] (leader; 2 producer arrivals + both CTAs' TMA bytes), empty[s] / tmem_full[a] (per CTA,
+// multicast tcgen05.commit), tmem_empty[a] (leader; all epilogue warps of both CTAs).
+constexpr int STAGES2 = 6;
+constexpr int BN2 = 256;
+
+struct Gemm2Smem {
+  static constexpr int A_BYTES = 128 * BK * 2;
+  static constexpr int B_BYTES = 128 * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_OFFSET = STAGES2 * STAGE_BYTES;
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int A_MN, int B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using L = Gemm2Smem;
+  // 1024-B aligned dynamic smem (SWIZZLE_128B atoms); indexing the __shared__ array directly keeps the address space known to
+  // the compiler (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES2;
+  uint64_t* tmem_full = empty_bar + STAGES2;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int tiles_mn = p.m_tiles * p.n_tiles;            // m_tiles counts 256-row pair tiles here
+  const int num_tiles = tiles_mn * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * EPI_WARPS); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_holder, 2 * BN2);
+  tc_fence_before();
+  cluster_sync_all();          // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer (both CTAs, each loads its halves)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int ks = tile / tiles_mn;
+        const int mn = tile - ks * tiles_mn;
+        const int m0 = (mn / p.n_tiles) * 256 + rank * 128;
+        const int n0 = (mn % p.n_tiles) * BN2 + rank * 128;
+        const int k_begin = ks * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * L::STAGE_BYTES;
+          uint8_t* sB = sA + L::A_BYTES;
+          const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sA + j * (BK * 128), &tmA, lead_bar, m0 + 64 * j, k0);
+          } else {
+            tma_load_2d_2sm(sA, &tmA, lead_bar, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sB + j * (BK * 128), &tmB, lead_bar, n0 + 64 * j, k0);
+          } else {
+            tma_load_2d_2sm(sB, &tmB, lead_bar, k0, n0);
+          }
+          if (!leader) mbar_arrive_cluster(lead_bar);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (one thread of the leader CTA)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN2, A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int ks = tile / tiles_mn;
+        const int k_begin = ks * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN2;
+        uint32_t accumulate = 0;
+        for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sB = sA + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_smem_desc(sA + k * 2048, BK * 128, 1024) : umma_smem_desc(sA + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_smem_desc(sB + k * 2048, BK * 128, 1024) : umma_smem_desc(sB + k * 32, 16, 1024);
+            umma_bf16_2sm(d_tmem, da, db, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);   // both CTAs' smem slots
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc], 3);       // both CTAs' epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================ epilogue warps (each CTA drains its own 128 accumulator rows)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int CHUNKS = BN2 / 32 / 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    float* slab = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + (warp - 2) * 32 * 32;
+    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+    for (int tile = pair; tile < num_tiles; tile += npairs) {
+      const int ks = tile / tiles_mn;
+      const int mn = tile - ks * tiles_mn;
+      const int m0 = (mn / p.n_tiles) * 256 + rank * 128;
+      const int n0 = (mn % p.n_tiles) * BN2 + half * (BN2 / 2);
+      const int k_begin = ks * p.k_per_split;
+      const bool has_k = k_begin < p.K;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN2 + half * (BN2 / 2);
+      uint32_t r[32];
+      tmem_ld_x32(t_row, r);
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(slab + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        if (c + 1 < CHUNKS) tmem_ld_x32(t_row + (c + 1) * 32, r);
+        __syncwarp();
+        if (has_k) epi_chunk(p, slab, m0 + q * 32, n0 + c * 32 + sub_c, sub_r, sub_c);
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));   // the leader's MMA thread owns the accumulator ring
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // nobody exits (or frees TMEM) while the peer may still touch this CTA's smem / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BN2);
+  }
+}
+
+template <int A_MN, int B_MN>
+static int launch_gemm2(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
+  static bool configured = false;
+  const int smem = Gemm2Smem::TOTAL;
+  if (!configured) {
+    CLIPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles * p.splits;
+  int pairs = sm_count() / 2;
+  if (tiles < pairs) pairs = tiles;
+  kern<<<2 * pairs, GEMM_THREADS, smem, stream>>>(tA, tB, p);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace clipk
 
 using namespace clipk;
@@ -331,9 +522,12 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   if ((epi->mode == CLIPK_EPI_DQUICK_GELU || epi->mode == CLIPK_EPI_DERF_GELU) && !epi->aux) { set_error("clipk_gemm_bf16: dGELU epilogue needs aux"); return CLIPK_ERR_ARG; }
 
   const int BN = (N % 256 == 0 || N > 512) ? 256 : 128;
+  static int use_pair = -1;
+  if (use_pair < 0) { const char* ev = getenv("CLIPK_GEMM_2CTA"); use_pair = (ev && ev[0] == '0') ? 0 : 1; }
+  const bool pair = use_pair && BN == 256 && M >= 256;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  p.m_tiles = (M + BM - 1) / BM;
+  p.m_tiles = pair ? (M + 255) / 256 : (M + BM - 1) / BM;
   p.n_tiles = (N + BN - 1) / BN;
   int kblocks = (K + BK - 1) / BK;
   if (splits > kblocks) splits = kblocks;
@@ -350,8 +544,16 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   else            rc = make_tmap_2d_bf16(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
   if (rc) return rc;
   if (b_mn_major) rc = make_tmap_2d_bf16(&tB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
-  else            rc = make_tmap_2d_bf16(&tB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN);
+  else            rc = make_tmap_2d_bf16(&tB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, pair ? 128 : BN);
   if (rc) return rc;
+  if (pair) {
+    if (a_mn_major) {
+      if (b_mn_major) return launch_gemm2<1, 1>(tA, tB, p, stream);
+      return launch_gemm2<1, 0>(tA, tB, p, stream);
+    }
+    if (b_mn_major) return launch_gemm2<0, 1>(tA, tB, p, stream);
+    return launch_gemm2<0, 0>(tA, tB, p, stream);
+  }
 
 #define CLIPK_DISPATCH(BN_)                                                          \
   if (a_mn_major) {                                                                  \

@@ -3,7 +3,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from easynlp_b200 import ops
-from tests.gemm_bench import timeit
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from gemm_bench import timeit
 M, N, K = 50432, 768, 768
 dev = "cuda"
 A = torch.randn(M, K, device=dev).bfloat16(); W = (torch.randn(N, K, device=dev) * 0.05).bfloat16(); bias = torch.randn(N, device=dev)
