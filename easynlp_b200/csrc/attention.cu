@@ -186,19 +186,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int n_kt = p.lk_pad > 128 ? 2 : 1;       // 128-key tiles of dK / dV
   const int kt_pad = n_kt * 128;
   const int ps_bytes = n_kt * 2 * 16384;         // P / dS tiles: 64-key blocks of [128 x 128 B]
-  uint8_t* sQ = smem;
-  uint8_t* sDO = sQ + 16384;
-  uint8_t* sK = sDO + 16384;
+  uint8_t* sQ0 = smem;                            // Q / dO tiles are double-buffered: tile qt+1 streams in while tile qt is processed
+  uint8_t* sDO0 = smem + 2 * 16384;
+  uint8_t* sK = smem + 4 * 16384;
   uint8_t* sV = sK + k_bytes;
-  uint8_t* sP = sV + k_bytes;
-  uint8_t* sDS = sP + ps_bytes;
-  float* smask = reinterpret_cast<float*>(sDS + ps_bytes);        // [256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smask + 256);      // kv, qdo, s, dp, dq
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+  uint8_t* sP = sV + k_bytes;                     // P, overwritten in place by dS once dV += P^T dO has completed
+  uint8_t* sDS = sP;
+  float* smask = reinterpret_cast<float*>(sP + ps_bytes);         // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smask + 256);      // kv, qdo[0], qdo[1], s, dp, dq
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmDO);
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_holder, 512);
@@ -211,7 +211,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16);
   const int split = ((p.lk_pad >> 1) + 15) & ~15;   // balance the VALID key columns between the two halves
   const int c_begin = half ? split : 0, c_end = half ? kt_pad : split;
-  const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sDS);
+  const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sDS);
   const float sc = p.scale * LOG2E;
   const int ksteps = p.lk_pad >> 4;
 
@@ -219,25 +219,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_expect_tx(&bars[0], 2 * k_bytes);
     tma_load_2d(sK, &tmKV, &bars[0], p.d + h * 64, b * p.L);
     tma_load_2d(sV, &tmKV, &bars[0], 2 * p.d + h * 64, b * p.L);
+    mbar_expect_tx(&bars[1], 2 * 16384);
+    tma_load_2d(sQ0, &tmQ, &bars[1], h * 64, b * p.L);
+    tma_load_2d(sDO0, &tmDO, &bars[1], h * 64, b * p.L);
   }
 
   for (int qt = 0; qt < p.q_tiles; ++qt) {
     const uint32_t ph = qt & 1;
+    const int buf = qt & 1;
+    const uint32_t aQ = smem_u32(sQ0 + buf * 16384), aDO = smem_u32(sDO0 + buf * 16384);
     const int row = q4 * 32 + lane;
     const int q = qt * 128 + row;
     const bool qvalid = q < p.L;
     // ---- loads + S = Q K^T
     if (tid == 0) {
-      mbar_expect_tx(&bars[1], 2 * 16384);
-      tma_load_2d(sQ, &tmQ, &bars[1], h * 64, b * p.L + qt * 128);
-      tma_load_2d(sDO, &tmDO, &bars[1], h * 64, b * p.L + qt * 128);
+      if (qt + 1 < p.q_tiles) {   // prefetch the next query tile into the other buffer (its last readers finished with tile qt-1)
+        mbar_expect_tx(&bars[1 + (buf ^ 1)], 2 * 16384);
+        tma_load_2d(sQ0 + (buf ^ 1) * 16384, &tmQ, &bars[1 + (buf ^ 1)], h * 64, b * p.L + (qt + 1) * 128);
+        tma_load_2d(sDO0 + (buf ^ 1) * 16384, &tmDO, &bars[1 + (buf ^ 1)], h * 64, b * p.L + (qt + 1) * 128);
+      }
       if (qt == 0) mbar_wait(&bars[0], 0);
-      mbar_wait(&bars[1], ph);
+      mbar_wait(&bars[1 + buf], (qt >> 1) & 1);
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, p.lk_pad, 0, 0);
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_k(aQ + k * 32), desc_k(aK + k * 32), idesc, k > 0);
-      umma_commit(&bars[2]);
+      umma_commit(&bars[3]);
     }
     // D = rowsum(dO o O) and the row's LSE, straight from global memory while the MMA runs
     float Dq = 0.f, lse2 = 0.f;
@@ -257,7 +264,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       lse2 = p.lse[((long long)b * p.H + h) * p.L + q] * LOG2E;
     }
-    mbar_wait(&bars[2], ph);
+    mbar_wait(&bars[3], ph);
     tc_fence_after();
     // ---- pass 1: P = exp(S - lse)  (rows beyond L and keys beyond L are exactly zero)
     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
@@ -290,9 +297,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int ks = 0; ks < 8; ++ks)
           umma_bf16(tmem + 256 + mt * 64, desc_mn(aP + mt * 32768 + ks * 2048, 16384), desc_mn(aDO + ks * 2048, 16384), idesc_t,
                     (qt > 0 || ks > 0) ? 1u : 0u);
-      umma_commit(&bars[3]);
+      umma_commit(&bars[4]);
     }
-    mbar_wait(&bars[3], ph);
+    mbar_wait(&bars[4], ph);
     tc_fence_after();
     // ---- pass 2: dS = scale * P o (dP - D)
     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
@@ -335,9 +342,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int ks = 0; ks < 8; ++ks)
           umma_bf16(tmem + 384 + mt * 64, desc_mn(aDS + mt * 32768 + ks * 2048, 16384), desc_mn(aQ + ks * 2048, 16384), idesc_t,
                     (qt > 0 || ks > 0) ? 1u : 0u);
-      umma_commit(&bars[4]);
+      umma_commit(&bars[5]);
     }
-    mbar_wait(&bars[4], ph);
+    mbar_wait(&bars[5], ph);
     tc_fence_after();
     {
       bf16* dst = p.dqkv + (long long)(b * p.L + q) * (3 * p.d) + h * 64 + half * 32;
@@ -445,7 +452,7 @@ extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const
   if ((rc = make_tmap_2d_bf16(&tDO, dctx, (uint64_t)d, (uint64_t)B * L, (uint64_t)d, 64, 128))) return rc;
   const int k_bytes = p.lk_pad * 128;
   const int n_kt = p.lk_pad > 128 ? 2 : 1;
-  const int smem = 2 * 16384 + 2 * k_bytes + 2 * (n_kt * 2 * 16384) + 1024 + 64 + 1024;
+  const int smem = 4 * 16384 + 2 * k_bytes + (n_kt * 2 * 16384) + 1024 + 64 + 1024;
   static int configured = 0;
   if (configured < smem) {
     CLIPK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

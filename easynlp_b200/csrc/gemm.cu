@@ -523,7 +523,8 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
 
   const int BN = (N % 256 == 0 || N > 512) ? 256 : 128;
   static int use_pair = -1;
-  if (use_pair < 0) { const char* ev = getenv("CLIPK_GEMM_2CTA"); use_pair = (ev && ev[0] == '0') ? 0 : 1; }
+  // experimental: correct (tests pass) but measured at half the 1-CTA rate on B200 (profiles/r01_gemm_2cta_note.md) -> opt-in only
+  if (use_pair < 0) { const char* ev = getenv("CLIPK_GEMM_2CTA"); use_pair = (ev && ev[0] == '1') ? 1 : 0; }
   const bool pair = use_pair && BN == 256 && M >= 256;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
