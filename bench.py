@@ -237,9 +237,14 @@ def run_native(args):
         eng.train_step(d_pixels, d_ids, lr=lr, weight_decay=1e-4, max_grad_norm=1.0, distributed=dist_on, use_graph=False)
         torch.cuda.synchronize()
         tr = ops.TRACE; ops.TRACE = None
-        agg = {}
+        agg = {}; shapes = {}
         for label, fl, by, s, e in tr:
+            if label.startswith("gemm|"):
+                sh = shapes.setdefault(label[5:], [0, 0.0, 0.0]); sh[0] += 1; sh[1] += fl; sh[2] += s.elapsed_time(e)
+                label = "gemm"
             a = agg.setdefault(label, [0, 0.0, 0.0]); a[0] += 1; a[1] += fl; a[2] += s.elapsed_time(e)
+        gemm_shapes = {k: {"n": v[0], "ms": round(v[2], 3), "tflops": round(v[1] / (v[2] * 1e-3) / 1e12, 1)}
+                       for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][2])[:26]}
         g = agg.get("gemm", [0, 0.0, 1e-9])
         gemm_tflops = g[1] / (g[2] * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
@@ -248,6 +253,7 @@ def run_native(args):
                     "traffic": None, "launches_per_step": g[0], "gflop_per_launch": g[1] / max(1, g[0]) / 1e9,
                     "avg_launch_ms": g[2] / max(1, g[0]),
                     "step_breakdown_ms": {k: round(v[2], 3) for k, v in agg.items()} | {"step_total": round(ms_per_step, 3)},
+                    "gemm_shapes_MxNxK|majors|mode": gemm_shapes,
                     "attention_tflops": {k: (agg[k][1] / (agg[k][2] * 1e-3) / 1e12) for k in agg if k.startswith("attention")},
                     "whole_step_frac_of_peak": (B * FLOPS_TRAIN_PER_PAIR / (ms_per_step * 1e-3) / 1e12) / peak}
 

@@ -150,7 +150,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x,
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(rows, r0 + rows_per_cta);
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = r0; r < r1; ++r) {
+  int r = r0;
+  // 8 independent row loads in flight per thread: the kernel is pure HBM streaming
+  for (; r + 8 <= r1; r += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = is_f32 ? ld_f4(reinterpret_cast<const float*>(x) + (long long)(r + u) * ldx + c4)
+                    : ld_bf4(reinterpret_cast<const bf16*>(x) + (long long)(r + u) * ldx + c4);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+  }
+  for (; r < r1; ++r) {
     float4 v = is_f32 ? ld_f4(reinterpret_cast<const float*>(x) + (long long)r * ldx + c4)
                       : ld_bf4(reinterpret_cast<const bf16*>(x) + (long long)r * ldx + c4);
     a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
@@ -342,9 +353,9 @@ extern "C" int clipk_colsum(const void* x, int is_f32, long long ldx, float* out
   if (rows <= 0 || n <= 0) return 0;
   if (n % 4 || ldx % 4) { set_error("colsum: n=%d ldx=%lld must be multiples of 4", n, ldx); return CLIPK_ERR_ARG; }
   const int bx = (n / 4 + 255) / 256;
-  int by = (sm_count() * 8 + bx - 1) / bx;
+  int by = (sm_count() * 16 + bx - 1) / bx;
   int rows_per = (rows + by - 1) / by;
-  if (rows_per < 16) rows_per = 16;
+  if (rows_per < 32) rows_per = 32;
   by = (rows + rows_per - 1) / rows_per;
   colsum_kernel<<<dim3(bx, by), 256, 0, stream>>>(x, is_f32, ldx, out, rows, n, rows_per);
   note_launch();

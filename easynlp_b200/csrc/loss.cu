@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) ce_strip_fwd_kernel(const float* __restri
   extern __shared__ float ktile[];  // [CE_TILE][E]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float scale = __expf(*logit_scale_log);
-  const int row0 = blockIdx.x * CE_ROWS + warp * CE_ROWS_PER_WARP;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + warp) * CE_ROWS_PER_WARP;
   float4 q[CE_ROWS_PER_WARP][NV];
 #pragma unroll
   for (int r = 0; r < CE_ROWS_PER_WARP; ++r)
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) ce_strip_bwd_kernel(const float* __restri
   extern __shared__ float stile[];  // [CE_TILE][E]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float scale = __expf(*logit_scale_log);
-  const int row0 = blockIdx.x * CE_ROWS + warp * CE_ROWS_PER_WARP;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + warp) * CE_ROWS_PER_WARP;
   float4 o[CE_ROWS_PER_WARP][NV], acc[CE_ROWS_PER_WARP][NV];
   float own_lse[CE_ROWS_PER_WARP];
 #pragma unroll
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) retrieval_rank_kernel(const float* __rest
                                                              int* __restrict__ rank_out, int nq, int nk, int E) {
   extern __shared__ float ktile[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row0 = blockIdx.x * CE_ROWS + warp * CE_ROWS_PER_WARP;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + warp) * CE_ROWS_PER_WARP;
   float4 q[CE_ROWS_PER_WARP][NV];
   float diag[CE_ROWS_PER_WARP];
   int cnt[CE_ROWS_PER_WARP];
@@ -219,6 +219,14 @@ __global__ void __launch_bounds__(256) reduce_sum_kernel(const float* __restrict
   }
 }
 
+// warps (x 4 rows) per CTA: small strips use small CTAs so that B = 256 still spreads over 64 SMs; big strips amortise the gallery stream
+static inline int ce_warps_for(int n_rows) {
+  const int sms = sm_count();
+  if (n_rows >= sms * 32) return 8;
+  if (n_rows >= sms * 8) return 2;
+  return 1;
+}
+
 }  // namespace clipk
 
 using namespace clipk;
@@ -237,12 +245,13 @@ extern "C" int clipk_ce_strip_fwd(const float* Q, const float* K, const float* l
   if (E % 128) { set_error("clip_ce: E %% 128 != 0"); return CLIPK_ERR_UNSUPPORTED; }
   const int nv = E / 128;
   const int smem = CE_TILE * E * 4;
-  dim3 grid((nq + CE_ROWS - 1) / CE_ROWS);
+  const int nw = ce_warps_for(nq);
+  dim3 grid((nq + nw * CE_ROWS_PER_WARP - 1) / (nw * CE_ROWS_PER_WARP));
 #define LAUNCH(NV)                                                                                                         \
   {                                                                                                                        \
     static bool cfg = false;                                                                                               \
     if (!cfg) { CLIPK_CUDA(cudaFuncSetAttribute(ce_strip_fwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072)); cfg = true; } \
-    ce_strip_fwd_kernel<NV><<<grid, 256, smem, stream>>>(Q, K, logit_scale_log, label_offset, S_out, lds, transpose_out, lse, loss_rows, nq, nk, E); \
+    ce_strip_fwd_kernel<NV><<<grid, 32 * nw, smem, stream>>>(Q, K, logit_scale_log, label_offset, S_out, lds, transpose_out, lse, loss_rows, nq, nk, E); \
   }
   CE_DISPATCH(nv, LAUNCH)
 #undef LAUNCH
@@ -258,12 +267,13 @@ extern "C" int clipk_ce_strip_bwd(const float* own, const float* streamed, const
   if (E % 128) { set_error("clip_ce: E %% 128 != 0"); return CLIPK_ERR_UNSUPPORTED; }
   const int nv = E / 128;
   const int smem = CE_TILE * E * 4;
-  dim3 grid((n_own + CE_ROWS - 1) / CE_ROWS);
+  const int nw = ce_warps_for(n_own);
+  dim3 grid((n_own + nw * CE_ROWS_PER_WARP - 1) / (nw * CE_ROWS_PER_WARP));
 #define LAUNCH(NV)                                                                                                         \
   {                                                                                                                        \
     static bool cfg = false;                                                                                               \
     if (!cfg) { CLIPK_CUDA(cudaFuncSetAttribute(ce_strip_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072)); cfg = true; } \
-    ce_strip_bwd_kernel<NV><<<grid, 256, smem, stream>>>(own, streamed, logit_scale_log, lse, label_offset, coef, own_is_query, out, accumulate, dscale_log, n_own, n_streamed, E); \
+    ce_strip_bwd_kernel<NV><<<grid, 32 * nw, smem, stream>>>(own, streamed, logit_scale_log, lse, label_offset, coef, own_is_query, out, accumulate, dscale_log, n_own, n_streamed, E); \
   }
   CE_DISPATCH(nv, LAUNCH)
 #undef LAUNCH
@@ -284,12 +294,13 @@ extern "C" int clipk_retrieval_rank(const float* Q, const float* K, int label_of
   if (E % 128) { set_error("retrieval_rank: E %% 128 != 0"); return CLIPK_ERR_UNSUPPORTED; }
   const int nv = E / 128;
   const int smem = CE_TILE * E * 4;
-  dim3 grid((nq + CE_ROWS - 1) / CE_ROWS);
+  const int nw = ce_warps_for(nq);
+  dim3 grid((nq + nw * CE_ROWS_PER_WARP - 1) / (nw * CE_ROWS_PER_WARP));
 #define LAUNCH(NV)                                                                                                         \
   {                                                                                                                        \
     static bool cfg = false;                                                                                               \
     if (!cfg) { CLIPK_CUDA(cudaFuncSetAttribute(retrieval_rank_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072)); cfg = true; } \
-    retrieval_rank_kernel<NV><<<grid, 256, smem, stream>>>(Q, K, label_offset, rank_out, nq, nk, E);                       \
+    retrieval_rank_kernel<NV><<<grid, 32 * nw, smem, stream>>>(Q, K, label_offset, rank_out, nq, nk, E);                       \
   }
   CE_DISPATCH(nv, LAUNCH)
 #undef LAUNCH

@@ -87,7 +87,7 @@ def gemm(a, b, out, *, a_mn_major=0, b_mn_major=0, mode=L.EPI_LINEAR, bias=None,
         assert aux.dtype == torch.bfloat16 and aux.shape == (M, N) and aux.stride(1) == 1
         e.aux = aux.data_ptr(); e.ldaux = aux.stride(0)
     e.alpha = alpha
-    with _traced("gemm", 2.0 * M * N * K):
+    with _traced(f"gemm|{M}x{N}x{K}|{int(a_mn_major)}{int(b_mn_major)}|m{mode}{'r' if residual is not None else ''}{'f' if out.dtype == torch.float32 else 'b'}", 2.0 * M * N * K):
         L.check(L.lib().clipk_gemm_bf16(_ptr(a), a.stride(0), int(a_mn_major), _ptr(b), b.stride(0), int(b_mn_major),
                                         M, N, K, C.byref(e), int(splits), _stream()), "clipk_gemm_bf16")
     return out
