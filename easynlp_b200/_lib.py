@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libclipk.so")
 
-EPI_LINEAR, EPI_QUICK_GELU, EPI_ERF_GELU, EPI_DQUICK_GELU, EPI_DERF_GELU, EPI_ATOMIC_ADD = range(6)
+EPI_LINEAR, EPI_QUICK_GELU, EPI_ERF_GELU, EPI_MUL_AUX, _EPI_RESERVED4, EPI_ATOMIC_ADD = range(6)
 BF16, F32 = 0, 1
 
 
@@ -42,7 +42,7 @@ def _declare(L):
     L.clipk_gemm_bf16.argtypes = [vp, i, i, vp, i, i, i, i, i, C.POINTER(Epilogue), i, vp]
     L.clipk_attention_fwd.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
     L.clipk_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
-    L.clipk_layernorm_fwd.argtypes = [vp, ll, vp, vp, f, vp, vp, vp, vp, i, i, vp]
+    L.clipk_layernorm_fwd.argtypes = [vp, ll, vp, ll, vp, vp, vp, f, vp, vp, vp, vp, i, i, vp]
     L.clipk_layernorm_bwd.argtypes = [vp, i, vp, vp, ll, vp, vp, vp, vp, vp, ll, vp, vp, vp, vp, i, i, vp]
     L.clipk_colsum.argtypes = [vp, i, ll, vp, i, i, vp]
     L.clipk_im2col_patches.argtypes = [vp, vp, i, i, i, vp]

@@ -106,29 +106,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int split = ((p.lk_pad >> 1) + 15) & ~15;
   const int c_begin = half ? split : 0, c_end = half ? p.lk_pad : split;
   float mx = -INFINITY;
-  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-    uint32_t r[16];
-    tmem_ld_x16(t_row + c0, r);
-    tmem_wait_ld();
+  {
+    uint32_t r[16], rn[16];
+    if (c_begin < c_end) tmem_ld_x16(t_row + c_begin, r);
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+      tmem_wait_ld();
+      if (c0 + 16 < c_end) tmem_ld_x16(t_row + c0 + 16, rn);     // next chunk streams in behind the math
+      float m[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]) * sc + smask[c0 + j]);
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(m + 4 * j) = *reinterpret_cast<const float4*>(smask + c0 + 4 * j);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), sc, m[j]));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = rn[j];
+    }
   }
   sred[half * 128 + row] = mx;
   __syncthreads();
   mx = fmaxf(sred[row], sred[128 + row]);
   float sum = 0.f;
-  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-    uint32_t r[16];
-    tmem_ld_x16(t_row + c0, r);
-    tmem_wait_ld();
-    float pv[16];
+  {
+    uint32_t r[16], rn[16];
+    if (c_begin < c_end) tmem_ld_x16(t_row + c_begin, r);
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+      tmem_wait_ld();
+      if (c0 + 16 < c_end) tmem_ld_x16(t_row + c0 + 16, rn);
+      float m[16], pv[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      pv[j] = exp2f(__uint_as_float(r[j]) * sc + smask[c0 + j] - mx);
-      sum += pv[j];
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(m + 4 * j) = *reinterpret_cast<const float4*>(smask + c0 + 4 * j);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        pv[j] = exp2f(fmaf(__uint_as_float(r[j]), sc, m[j] - mx));
+        sum += pv[j];
+      }
+      store_row8_sw128(sP, row, c0, pv);
+      store_row8_sw128(sP, row, c0 + 8, pv + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = rn[j];
     }
-    store_row8_sw128(sP, row, c0, pv);
-    store_row8_sw128(sP, row, c0 + 8, pv + 8);
   }
   ssum[half * 128 + row] = sum;
   fence_proxy_async_smem();
@@ -272,9 +287,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (c0 < p.lk_pad) {
         uint32_t r[16];
         tmem_ld_x16(t_row + c0, r);
+        float m[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(m + 4 * j) = *reinterpret_cast<const float4*>(smask + c0 + 4 * j);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pv[j] = qvalid ? exp2f(__uint_as_float(r[j]) * sc + smask[c0 + j] - lse2) : 0.f;
+        for (int j = 0; j < 16; ++j) pv[j] = qvalid ? exp2f(fmaf(__uint_as_float(r[j]), sc, m[j] - lse2)) : 0.f;
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) pv[j] = 0.f;
@@ -307,9 +325,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (c0 < p.lk_pad) {
         uint32_t r[16];
         tmem_ld_x16(t_row + c0, r);
-        tmem_wait_ld();
         uint4 pa = *reinterpret_cast<const uint4*>(sP + (c0 >> 6) * 16384 + sw128_offset(row, (c0 & 63) >> 3));
         uint4 pb = *reinterpret_cast<const uint4*>(sP + (c0 >> 6) * 16384 + sw128_offset(row, ((c0 + 8) & 63) >> 3));
+        tmem_wait_ld();
         const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&pa);
         const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&pb);
 #pragma unroll

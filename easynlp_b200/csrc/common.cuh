@@ -226,6 +226,17 @@ __device__ __forceinline__ float erf_gelu_grad_f(float x) {
   float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// activation and its derivative from one pass over z (the forward GEMM epilogue saves both)
+__device__ __forceinline__ void quick_gelu_both(float x, float& act, float& grad) {
+  const float s = 1.0f / (1.0f + __expf(-1.702f * x));
+  act = x * s;
+  grad = s * (1.0f + 1.702f * x * (1.0f - s));
+}
+__device__ __forceinline__ void erf_gelu_both(float x, float& act, float& grad) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  act = x * cdf;
+  grad = cdf + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

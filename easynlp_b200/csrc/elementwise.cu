@@ -23,8 +23,12 @@ __device__ __forceinline__ float4 ld_bf4(const bf16* p) {
 
 // ------------------------------------------------------------------------------------------------ LayerNorm fwd
 // reference: modeling_chineseclip.py:170-176 (fp32 LN, eps 1e-5) and nn.LayerNorm(eps=1e-12) in modeling_bert.py:84,266,344
+// optional fused residual add: xs = x + add (add = the bf16 output of the preceding projection GEMM), xs is written to x_out
+// (fp32, kept for backward / the next residual) and normalised -- the GEMM then has a plain bf16 epilogue and the fp32 residual
+// stream is only touched by this HBM-streaming kernel.
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const bf16* __restrict__ add,
+                                                            long long ldadd, float* __restrict__ x_out, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, bf16* __restrict__ y_bf16,
                                                             float* __restrict__ y_f32, float* __restrict__ mean_out,
                                                             float* __restrict__ rstd_out, int rows, int d) {
@@ -35,9 +39,19 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   float4 v[NV];
   float s = 0.f;
 #pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = ld_f4(xr + (lane + 32 * i) * 4);
+  if (add) {
+    const bf16* ar = add + (long long)row * ldadd;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = ld_bf4(ar + (lane + 32 * i) * 4);
+      v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+    }
+  }
+#pragma unroll
   for (int i = 0; i < NV; ++i) {
-    v[i] = ld_f4(xr + (lane + 32 * i) * 4);
     s += v[i].x + v[i].y + v[i].z + v[i].w;
+    if (x_out) st_f4(x_out + (long long)row * d + (lane + 32 * i) * 4, v[i]);
   }
   const float mean = warp_sum(s) / d;
   float q = 0.f;
@@ -317,13 +331,14 @@ using namespace clipk;
     case 7: __VA_ARGS__(7); break; case 8: __VA_ARGS__(8); break;  \
     default: set_error("layernorm: d=%d unsupported (d %% 128 == 0, d <= 1024)", d); return CLIPK_ERR_UNSUPPORTED; }
 
-extern "C" int clipk_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y_bf16,
-                                   float* y_f32, float* mean, float* rstd, int rows, int d, cudaStream_t stream) {
+extern "C" int clipk_layernorm_fwd(const float* x, long long ldx, const void* add_bf16, long long ldadd, float* x_out, const float* gamma,
+                                   const float* beta, float eps, void* y_bf16, float* y_f32, float* mean, float* rstd, int rows, int d,
+                                   cudaStream_t stream) {
   if (rows <= 0) return 0;
-  if (d % 128 || d > 128 * LN_MAXV || (ldx % 4)) { set_error("layernorm_fwd: d=%d ldx=%lld unsupported", d, ldx); return CLIPK_ERR_UNSUPPORTED; }
+  if (d % 128 || d > 128 * LN_MAXV || (ldx % 4) || (ldadd % 4)) { set_error("layernorm_fwd: d=%d ldx=%lld unsupported", d, ldx); return CLIPK_ERR_UNSUPPORTED; }
   const int nv = d / 128;
   dim3 grid((rows + 7) / 8), block(256);
-#define LAUNCH(NV) layernorm_fwd_kernel<NV><<<grid, block, 0, stream>>>(x, ldx, gamma, beta, eps, (bf16*)y_bf16, y_f32, mean, rstd, rows, d)
+#define LAUNCH(NV) layernorm_fwd_kernel<NV><<<grid, block, 0, stream>>>(x, ldx, (const bf16*)add_bf16, ldadd, x_out, gamma, beta, eps, (bf16*)y_bf16, y_f32, mean, rstd, rows, d)
   LN_DISPATCH(nv, LAUNCH)
 #undef LAUNCH
   note_launch();

@@ -72,27 +72,28 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, const float* slab
     return;
   }
   if (e.mode == CLIPK_EPI_QUICK_GELU || e.mode == CLIPK_EPI_ERF_GELU) {
-    // out = pre-activation z (bf16, kept for backward), out2 = act(z) (bf16, next GEMM's operand); the activation is evaluated on
-    // the bf16-rounded z so that backward (which only has bf16 z) is consistent with forward
+    // out2 = act(z) (bf16, the next GEMM's operand); out = act'(z) (bf16), saved INSTEAD of z: the backward epilogue then is a
+    // single multiply (no MUFU), which keeps the K = 768 dgrad GEMM off the epilogue roofline.  Both are evaluated on the fp32 z.
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = row0 + 4 * i + sub_r;
-      uint2 z, a;
-      z.x = pack_bf16x2(v[i].x, v[i].y); z.y = pack_bf16x2(v[i].z, v[i].w);
-      const float2 z0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&z.x));
-      const float2 z1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&z.y));
-      float g0, g1, g2, g3;
-      if (e.mode == CLIPK_EPI_QUICK_GELU) { g0 = quick_gelu_f(z0.x); g1 = quick_gelu_f(z0.y); g2 = quick_gelu_f(z1.x); g3 = quick_gelu_f(z1.y); }
-      else { g0 = erf_gelu_f(z0.x); g1 = erf_gelu_f(z0.y); g2 = erf_gelu_f(z1.x); g3 = erf_gelu_f(z1.y); }
-      a.x = pack_bf16x2(g0, g1); a.y = pack_bf16x2(g2, g3);
+      float a0, a1, a2, a3, g0, g1, g2, g3;
+      if (e.mode == CLIPK_EPI_QUICK_GELU) {
+        quick_gelu_both(v[i].x, a0, g0); quick_gelu_both(v[i].y, a1, g1); quick_gelu_both(v[i].z, a2, g2); quick_gelu_both(v[i].w, a3, g3);
+      } else {
+        erf_gelu_both(v[i].x, a0, g0); erf_gelu_both(v[i].y, a1, g1); erf_gelu_both(v[i].z, a2, g2); erf_gelu_both(v[i].w, a3, g3);
+      }
       if (row < p.M) {
-        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = z;
+        uint2 a, g;
+        a.x = pack_bf16x2(a0, a1); a.y = pack_bf16x2(a2, a3);
+        g.x = pack_bf16x2(g0, g1); g.y = pack_bf16x2(g2, g3);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out) + (size_t)row * e.ldo + col) = g;
         *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.out2) + (size_t)row * e.ldo2 + col) = a;
       }
     }
     return;
   }
-  if (e.mode == CLIPK_EPI_DQUICK_GELU || e.mode == CLIPK_EPI_DERF_GELU) {
+  if (e.mode == CLIPK_EPI_MUL_AUX) {
     uint2 zz[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -103,11 +104,7 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, const float* slab
     for (int i = 0; i < 8; ++i) {
       const float2 z0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&zz[i].x));
       const float2 z1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&zz[i].y));
-      if (e.mode == CLIPK_EPI_DQUICK_GELU) {
-        v[i].x *= quick_gelu_grad_f(z0.x); v[i].y *= quick_gelu_grad_f(z0.y); v[i].z *= quick_gelu_grad_f(z1.x); v[i].w *= quick_gelu_grad_f(z1.y);
-      } else {
-        v[i].x *= erf_gelu_grad_f(z0.x); v[i].y *= erf_gelu_grad_f(z0.y); v[i].z *= erf_gelu_grad_f(z1.x); v[i].w *= erf_gelu_grad_f(z1.y);
-      }
+      v[i].x *= z0.x; v[i].y *= z0.y; v[i].z *= z1.x; v[i].w *= z1.y;
     }
   }
   if (e.residual) {
@@ -519,7 +516,8 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   if (splits > 1 && epi->mode != CLIPK_EPI_ATOMIC_ADD) { set_error("clipk_gemm_bf16: split-K requires CLIPK_EPI_ATOMIC_ADD"); return CLIPK_ERR_ARG; }
   if (epi->mode == CLIPK_EPI_ATOMIC_ADD && epi->out_dtype != CLIPK_F32) { set_error("clipk_gemm_bf16: atomic epilogue needs fp32 output"); return CLIPK_ERR_ARG; }
   if ((epi->mode == CLIPK_EPI_QUICK_GELU || epi->mode == CLIPK_EPI_ERF_GELU) && !epi->out2) { set_error("clipk_gemm_bf16: GELU epilogue needs out2"); return CLIPK_ERR_ARG; }
-  if ((epi->mode == CLIPK_EPI_DQUICK_GELU || epi->mode == CLIPK_EPI_DERF_GELU) && !epi->aux) { set_error("clipk_gemm_bf16: dGELU epilogue needs aux"); return CLIPK_ERR_ARG; }
+  if (epi->mode == CLIPK_EPI_MUL_AUX && !epi->aux) { set_error("clipk_gemm_bf16: MUL_AUX epilogue needs aux"); return CLIPK_ERR_ARG; }
+  if (epi->mode < 0 || epi->mode > CLIPK_EPI_ATOMIC_ADD) { set_error("clipk_gemm_bf16: unknown epilogue mode %d", epi->mode); return CLIPK_ERR_ARG; }
 
   const int BN = (N % 256 == 0 || N > 512) ? 256 : 128;
   static int use_pair = -1;

@@ -138,7 +138,7 @@ class ClipEngine:
             # MLP
             ops.gemm(dXb, ly["a"], P_.g(p + "mlp.c_proj.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
                      splits=_splits_for(W, 4 * W, M))
-            ops.gemm(dXb, P_.w(p + "mlp.c_proj.weight"), dz, b_mn_major=1, mode=L.EPI_DQUICK_GELU, aux=ly["z"])
+            ops.gemm(dXb, P_.w(p + "mlp.c_proj.weight"), dz, b_mn_major=1, mode=L.EPI_MUL_AUX, aux=ly["z"])
             ops.colsum(dz, P_.g(p + "mlp.c_fc.bias"), M, 4 * W)
             ops.gemm(dz, ly["h2"], P_.g(p + "mlp.c_fc.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
                      splits=_splits_for(4 * W, W, M))
@@ -236,7 +236,7 @@ class ClipEngine:
             ops.layernorm_bwd(dy, ly["s2"], P_.p(p + "output.LayerNorm.weight"), ly["m2"], ly["r2"], dy_add=dy_add, dx_f32=ds2, dx_bf16=ds2b,
                               dgamma=P_.g(p + "output.LayerNorm.weight"), dbeta=P_.g(p + "output.LayerNorm.bias"), dbias=P_.g(p + "output.dense.bias"))
             ops.gemm(ds2b, ly["a"], P_.g(p + "output.dense.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD, splits=_splits_for(H, I, M))
-            ops.gemm(ds2b, P_.w(p + "output.dense.weight"), dz, b_mn_major=1, mode=L.EPI_DERF_GELU, aux=ly["z"])
+            ops.gemm(ds2b, P_.w(p + "output.dense.weight"), dz, b_mn_major=1, mode=L.EPI_MUL_AUX, aux=ly["z"])
             ops.colsum(dz, P_.g(p + "intermediate.dense.bias"), M, I)
             ops.gemm(dz, ly["y1b"], P_.g(p + "intermediate.dense.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD, splits=_splits_for(I, H, M))
             ops.gemm(dz, P_.w(p + "intermediate.dense.weight"), dpart, b_mn_major=1)

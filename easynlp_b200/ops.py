@@ -122,14 +122,17 @@ def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H):
 
 
 @_op
-def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None, rows=None, ldx=None):
+def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None, rows=None, ldx=None, add=None, ldadd=None,
+                  x_out=None):
     d = gamma.numel()
     if rows is None:
         rows = x.numel() // d
     if ldx is None:
         ldx = d
-    L_.check(L_.lib().clipk_layernorm_fwd(_f32(x), ldx, _f32(gamma), _f32(beta), eps, _b16(y_bf16), _f32(y_f32), _f32(mean),
-                                          _f32(rstd), rows, d, _stream()), "layernorm_fwd")
+    if add is not None and ldadd is None:
+        ldadd = d
+    L_.check(L_.lib().clipk_layernorm_fwd(_f32(x), ldx, _b16(add), ldadd or 0, _f32(x_out), _f32(gamma), _f32(beta), eps, _b16(y_bf16),
+                                          _f32(y_f32), _f32(mean), _f32(rstd), rows, d, _stream()), "layernorm_fwd")
 
 
 @_op

@@ -12,7 +12,7 @@ from typing import Dict, List, Tuple
 import torch
 
 NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight")
-ALIGN = 8  # elements: 16 B for the bf16 shadow (TMA base alignment), 32 B for fp32
+ALIGN = 64  # elements: every tensor starts on a 128-B line in the bf16 shadow (TMA rows = whole sectors) and 256 B in fp32
 
 
 def uses_weight_decay(name: str) -> bool:

@@ -43,10 +43,11 @@ int64_t clipk_launch_count(void);
  * Replaces nn.Linear / nn.Conv2d(patch) / MultiheadAttention in/out projections and their autograd
  * (reference: modeling_chineseclip.py:188-204,224-251; modeling_bert.py:145-147,264-268,329-346).   */
 #define CLIPK_EPI_LINEAR 0       /* out = alpha*acc + bias + residual                    (out bf16|f32, optional bf16 out2) */
-#define CLIPK_EPI_QUICK_GELU 1   /* out = z = acc + bias (bf16); out2 = z*sigmoid(1.702 z) (modeling_chineseclip.py:179-181) */
-#define CLIPK_EPI_ERF_GELU 2     /* out = z (bf16); out2 = gelu_erf(z)                    (modelzoo/activations.py:45-48)   */
-#define CLIPK_EPI_DQUICK_GELU 3  /* out = acc * d/dz quick_gelu(aux)                      (backward of mode 1)              */
-#define CLIPK_EPI_DERF_GELU 4    /* out = acc * d/dz gelu_erf(aux)                        (backward of mode 2)              */
+#define CLIPK_EPI_QUICK_GELU 1   /* z = acc + bias; out2 = z*sigmoid(1.702 z) (bf16); out = d/dz of it (bf16, saved for backward)
+                                    (modeling_chineseclip.py:179-181)                                                     */
+#define CLIPK_EPI_ERF_GELU 2     /* same with gelu_erf (modelzoo/activations.py:45-48): out2 = act(z), out = act'(z)              */
+#define CLIPK_EPI_MUL_AUX 3      /* out = (alpha*acc + bias) * aux (+ residual): backward of modes 1/2 with aux = act'(z)          */
+#define CLIPK_EPI_RESERVED4 4    /* unused                                                                                  */
 #define CLIPK_EPI_ATOMIC_ADD 5   /* out(f32) += acc  via red.add -- split-K weight gradients                                */
 
 typedef struct {
@@ -59,7 +60,7 @@ typedef struct {
   const float* bias;     /* optional [N] */
   const float* residual; /* optional f32 [M, ldr] */
   int ldr;
-  const void* aux;       /* bf16 [M, ldaux] (pre-activation for the dGELU modes) */
+  const void* aux;       /* bf16 [M, ldaux] multiplier for CLIPK_EPI_MUL_AUX (the saved activation derivative) */
   int ldaux;
   float alpha;           /* 0 is read as 1 */
 } clipk_epilogue_t;
@@ -86,9 +87,13 @@ int clipk_attention_bwd(const void* qkv, const float* key_mask, const void* ctx,
 /* -------------------------------------------------------------------------------------------- LayerNorm
  * y = (x - mean) * rstd * gamma + beta over the last dim d (d % 128 == 0, d <= 1024), fp32 statistics
  * (modeling_chineseclip.py:170-176 eps 1e-5; nn.LayerNorm eps 1e-12 in modeling_bert.py:84,266,344).
- * x: f32 rows with stride ldx; y_bf16 / y_f32 / mean / rstd optional outputs (contiguous).                     */
-int clipk_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y_bf16,
-                        float* y_f32, float* mean, float* rstd, int rows, int d, cudaStream_t stream);
+ * x: f32 rows with stride ldx; y_bf16 / y_f32 / mean / rstd optional outputs (contiguous).
+ * Optional fused residual add: if add_bf16 != NULL (bf16 rows, stride ldadd) the kernel normalises xs = x + add and, if
+ * x_out != NULL, stores xs (f32, contiguous) -- `x + attention(...)` / `x + mlp(...)` of modeling_chineseclip.py:203-204 and
+ * `dense(...) + input_tensor` of modeling_bert.py:266,344 without a residual read in the GEMM epilogue.               */
+int clipk_layernorm_fwd(const float* x, long long ldx, const void* add_bf16, long long ldadd, float* x_out,
+                        const float* gamma, const float* beta, float eps, void* y_bf16, float* y_f32, float* mean,
+                        float* rstd, int rows, int d, cudaStream_t stream);
 /* g = dy (+ dy_add); dx = LN'(g) (+ dx_add) -> dx_f32 (stride lddx) / dx_bf16; dgamma, dbeta, dbias(=colsum dx) are
  * ACCUMULATED with fp32 atomics (optional).                                                                     */
 int clipk_layernorm_bwd(const void* dy, int dy_is_f32, const float* dy_add, const float* x, long long ldx,

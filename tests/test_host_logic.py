@@ -32,7 +32,7 @@ def test_flat_layout_groups_and_alignment():
     st = ParamStore(cfg, device="cpu")
     offs = st.offsets
     for n, o in offs.items():
-        assert o % 8 == 0, n
+        assert o % 64 == 0, n
     for n in st.schema:
         if n in NO_GRAD:
             assert offs[n] >= st.n_trainable

@@ -64,20 +64,20 @@ def test_gemm_epilogues():
     ob = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
     ops.gemm(A, W, ob, bias=bias, alpha=0.5)
     assert_close(ob, 0.5 * acc + bias, 1e-2, 2e-2, "alpha")
-    # GELUs
+    # GELUs: out2 = act(z), out = act'(z) (saved for backward instead of z)
+    zf = (acc + bias)
     for mode, fn in ((L.EPI_QUICK_GELU, lambda z: z * torch.sigmoid(1.702 * z)), (L.EPI_ERF_GELU, torch.nn.functional.gelu)):
-        z = torch.empty(M, N, device=DEV, dtype=torch.bfloat16); a = torch.empty_like(z)
-        ops.gemm(A, W, z, bias=bias, mode=mode, out2=a)
-        assert_close(z, acc + bias, 1e-2, 2e-2, "z")
-        assert_close(a, fn(z.float()), 1e-2, 1e-2, "act")
-    # dGELUs
-    zb = (acc + bias).bfloat16()
-    for mode, fn in ((L.EPI_DQUICK_GELU, lambda z: z * torch.sigmoid(1.702 * z)), (L.EPI_DERF_GELU, torch.nn.functional.gelu)):
-        zz = zb.float().requires_grad_(True)
-        fn(zz).backward(acc)
+        g = torch.empty(M, N, device=DEV, dtype=torch.bfloat16); a = torch.empty_like(g)
+        ops.gemm(A, W, g, bias=bias, mode=mode, out2=a)
+        zz = zf.clone().requires_grad_(True)
+        y = fn(zz)
+        y.backward(torch.ones_like(y))
+        assert_close(a, y, 1e-2, 1e-2, "act")
+        assert_close(g, zz.grad, 1e-2, 1e-2, "act'")
+        # backward epilogue: out = acc * aux
         o = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-        ops.gemm(A, W, o, mode=mode, aux=zb)
-        assert_close(o, zz.grad, 2e-2, 3e-2, "dgelu")
+        ops.gemm(A, W, o, mode=L.EPI_MUL_AUX, aux=g)
+        assert_close(o, acc * g.float(), 2e-2, 3e-2, "mul_aux")
 
 
 # --------------------------------------------------------------------------------------------- attention
