@@ -85,30 +85,48 @@ class ClipEngine:
         x = self.f32("v.x.0", M, W)
         st = {"B": B, "mean0": self.f32("v.mean0", M), "rstd0": self.f32("v.rstd0", M), "layers": []}
         ops.layernorm_fwd(x0, P_.p("visual.ln_pre.weight"), P_.p("visual.ln_pre.bias"), 1e-5, None, x, st["mean0"], st["rstd0"])
+        # Residual stream: every projection GEMM writes its branch output as bf16 (plain epilogue); the fp32 residual add is fused
+        # into the LayerNorm that follows it (x_new = x + branch is stored by that kernel for backward / the next residual).
+        ybr = self.bf("v.ybr", M, W)                 # branch output (attention out-proj / MLP c_proj), reused
+        pending = None                               # (x_res, add): residual add owed to the next LayerNorm
         for i in range(self.nv):
             p = f"visual.transformer.resblocks.{i}."
             tag = f"v.{i}." if save else "v.t."
-            ly = {"x_in": x}
+            ly = {}
             ly["h"] = self.bf(tag + "h", M, W); ly["m1"] = self.f32(tag + "m1", M); ly["r1"] = self.f32(tag + "r1", M)
-            ops.layernorm_fwd(x, P_.p(p + "ln_1.weight"), P_.p(p + "ln_1.bias"), 1e-5, ly["h"], None, ly["m1"], ly["r1"])
+            if pending is None:
+                ops.layernorm_fwd(x, P_.p(p + "ln_1.weight"), P_.p(p + "ln_1.bias"), 1e-5, ly["h"], None, ly["m1"], ly["r1"])
+            else:       # x = x1_prev + c_proj(...) of the previous block
+                x_new = self.f32(f"v.x.{i}" if save else f"v.x.t{i % 2}", M, W)
+                ops.layernorm_fwd(pending, P_.p(p + "ln_1.weight"), P_.p(p + "ln_1.bias"), 1e-5, ly["h"], None, ly["m1"], ly["r1"],
+                                  add=ybr, x_out=x_new)
+                x = x_new
+            ly["x_in"] = x
             ly["qkv"] = self.bf(tag + "qkv", M, 3 * W)
             ops.gemm(ly["h"], P_.w(p + "attn.in_proj_weight"), ly["qkv"], bias=P_.p(p + "attn.in_proj_bias"))
             ly["ctx"] = self.bf(tag + "ctx", M, W); ly["lse"] = self.f32(tag + "lse", B * Hh * Lv)
             ops.attention_fwd(ly["qkv"], None, ly["ctx"], ly["lse"], B, Lv, Hh)
+            ops.gemm(ly["ctx"], P_.w(p + "attn.out_proj.weight"), ybr, bias=P_.p(p + "attn.out_proj.bias"))
             ly["x1"] = self.f32(tag + "x1", M, W)
-            ops.gemm(ly["ctx"], P_.w(p + "attn.out_proj.weight"), ly["x1"], bias=P_.p(p + "attn.out_proj.bias"), residual=x)
             ly["h2"] = self.bf(tag + "h2", M, W); ly["m2"] = self.f32(tag + "m2", M); ly["r2"] = self.f32(tag + "r2", M)
-            ops.layernorm_fwd(ly["x1"], P_.p(p + "ln_2.weight"), P_.p(p + "ln_2.bias"), 1e-5, ly["h2"], None, ly["m2"], ly["r2"])
+            ops.layernorm_fwd(x, P_.p(p + "ln_2.weight"), P_.p(p + "ln_2.bias"), 1e-5, ly["h2"], None, ly["m2"], ly["r2"],
+                              add=ybr, x_out=ly["x1"])
+            # "z" holds act'(z) (QuickGELU derivative) saved for backward, "a" the activation
             ly["z"] = self.bf(tag + "z", M, 4 * W); ly["a"] = self.bf(tag + "a", M, 4 * W)
             ops.gemm(ly["h2"], P_.w(p + "mlp.c_fc.weight"), ly["z"], bias=P_.p(p + "mlp.c_fc.bias"), mode=L.EPI_QUICK_GELU, out2=ly["a"])
-            x_next = self.f32(f"v.x.{i + 1}" if save else f"v.x.t{i % 2}", M, W)
-            ops.gemm(ly["a"], P_.w(p + "mlp.c_proj.weight"), x_next, bias=P_.p(p + "mlp.c_proj.bias"), residual=ly["x1"])
-            x = x_next
+            ops.gemm(ly["a"], P_.w(p + "mlp.c_proj.weight"), ybr, bias=P_.p(p + "mlp.c_proj.bias"))
+            pending = ly["x1"]
             st["layers"].append(ly)
-        st["x_final"] = x
+        # ln_post on the CLS rows of x_final = x1_last + c_proj(...): the add is fused here too; x_cls [B, W] is kept for backward
+        st["x_cls"] = self.f32("v.x_cls", B, W)
         st["pooled"] = self.bf("v.pooled", B, W); st["mp"] = self.f32("v.mp", B); st["rp"] = self.f32("v.rp", B)
-        ops.layernorm_fwd(x, P_.p("visual.ln_post.weight"), P_.p("visual.ln_post.bias"), 1e-5, st["pooled"], None, st["mp"], st["rp"],
-                          rows=B, ldx=Lv * W)
+        if pending is None:      # zero-layer tower (degenerate configs): no pending residual
+            ops.layernorm_fwd(x, P_.p("visual.ln_post.weight"), P_.p("visual.ln_post.bias"), 1e-5, st["pooled"], None, st["mp"], st["rp"],
+                              rows=B, ldx=Lv * W)
+            st["x_cls"] = None; st["x_final"] = x
+        else:
+            ops.layernorm_fwd(pending, P_.p("visual.ln_post.weight"), P_.p("visual.ln_post.bias"), 1e-5, st["pooled"], None, st["mp"], st["rp"],
+                              rows=B, ldx=Lv * W, add=ybr, ldadd=Lv * W, x_out=st["x_cls"])
         st["feat"] = self.f32("v.feat", B, self.E)
         ops.gemm(st["pooled"], P_.w("visual.proj"), st["feat"], b_mn_major=1)
         st["embeds"] = self.f32("v.embeds", B, self.E); st["norm"] = self.f32("v.norm", B)
@@ -127,9 +145,10 @@ class ClipEngine:
         dX.zero_()
         last = st["layers"][-1] if self.nv else None
         bias_prev = P_.g(f"visual.transformer.resblocks.{self.nv - 1}.mlp.c_proj.bias") if self.nv else None
-        ops.layernorm_bwd(dpooled, st["x_final"], P_.p("visual.ln_post.weight"), st["mp"], st["rp"], dx_f32=dX,
+        x_post, ld_post = (st["x_cls"], W) if st.get("x_cls") is not None else (st["x_final"], Lv * W)
+        ops.layernorm_bwd(dpooled, x_post, P_.p("visual.ln_post.weight"), st["mp"], st["rp"], dx_f32=dX,
                           dgamma=P_.g("visual.ln_post.weight"), dbeta=P_.g("visual.ln_post.bias"), dbias=bias_prev,
-                          rows=B, ldx=Lv * W, lddx=Lv * W)
+                          rows=B, ldx=ld_post, lddx=Lv * W)
         ops.cast_bf16(dX, dXb)
         dz = self.bf("v.dz", M, 4 * W); dh = self.bf("v.dh", M, W); dctx = self.bf("v.dctx", M, W); dqkv = self.bf("v.dqkv", M, 3 * W)
         for i in reversed(range(self.nv)):
@@ -185,6 +204,7 @@ class ClipEngine:
         st["me"] = self.f32("t.me", M); st["re"] = self.f32("t.re", M)
         ops.layernorm_fwd(st["e"], P_.p("bert.embeddings.LayerNorm.weight"), P_.p("bert.embeddings.LayerNorm.bias"), eps, xb, x,
                           st["me"], st["re"])
+        tbr = self.bf("t.tbr", M, H)                 # bf16 branch output of attention.output.dense / output.dense
         for i in range(self.nt):
             p = f"bert.encoder.layer.{i}."
             tag = f"t.{i}." if save else "t.t."
@@ -193,21 +213,22 @@ class ClipEngine:
             ops.gemm(xb, P_.w(p + "attention.self.query.weight", (3 * H, H)), ly["qkv"], bias=P_.p(p + "attention.self.query.bias", (3 * H,)))
             ly["ctx"] = self.bf(tag + "ctx", M, H); ly["lse"] = self.f32(tag + "lse", B * Hh * Lt)
             ops.attention_fwd(ly["qkv"], st["mask"], ly["ctx"], ly["lse"], B, Lt, Hh)
+            ops.gemm(ly["ctx"], P_.w(p + "attention.output.dense.weight"), tbr, bias=P_.p(p + "attention.output.dense.bias"))
             ly["s1"] = self.f32(tag + "s1", M, H)
-            ops.gemm(ly["ctx"], P_.w(p + "attention.output.dense.weight"), ly["s1"], bias=P_.p(p + "attention.output.dense.bias"), residual=x)
             ly["y1"] = self.f32(tag + "y1", M, H); ly["y1b"] = self.bf(tag + "y1b", M, H)
             ly["m1"] = self.f32(tag + "m1", M); ly["r1"] = self.f32(tag + "r1", M)
-            ops.layernorm_fwd(ly["s1"], P_.p(p + "attention.output.LayerNorm.weight"), P_.p(p + "attention.output.LayerNorm.bias"), eps,
-                              ly["y1b"], ly["y1"], ly["m1"], ly["r1"])
-            ly["z"] = self.bf(tag + "z", M, I); ly["a"] = self.bf(tag + "a", M, I)
+            ops.layernorm_fwd(x, P_.p(p + "attention.output.LayerNorm.weight"), P_.p(p + "attention.output.LayerNorm.bias"), eps,
+                              ly["y1b"], ly["y1"], ly["m1"], ly["r1"], add=tbr, x_out=ly["s1"])      # LN(dense(ctx) + input)
+            ly["z"] = self.bf(tag + "z", M, I); ly["a"] = self.bf(tag + "a", M, I)                  # z = gelu'(.) saved for backward
             ops.gemm(ly["y1b"], P_.w(p + "intermediate.dense.weight"), ly["z"], bias=P_.p(p + "intermediate.dense.bias"),
                      mode=L.EPI_ERF_GELU, out2=ly["a"])
+            ops.gemm(ly["a"], P_.w(p + "output.dense.weight"), tbr, bias=P_.p(p + "output.dense.bias"))
             ly["s2"] = self.f32(tag + "s2", M, H)
-            ops.gemm(ly["a"], P_.w(p + "output.dense.weight"), ly["s2"], bias=P_.p(p + "output.dense.bias"), residual=ly["y1"])
             x = self.f32(f"t.x.{i + 1}" if save else f"t.x.t{i % 2}", M, H)
             xb = self.bf(f"t.xb.{i + 1}" if save else f"t.xb.t{i % 2}", M, H)
             ly["m2"] = self.f32(tag + "m2", M); ly["r2"] = self.f32(tag + "r2", M)
-            ops.layernorm_fwd(ly["s2"], P_.p(p + "output.LayerNorm.weight"), P_.p(p + "output.LayerNorm.bias"), eps, xb, x, ly["m2"], ly["r2"])
+            ops.layernorm_fwd(ly["y1"], P_.p(p + "output.LayerNorm.weight"), P_.p(p + "output.LayerNorm.bias"), eps, xb, x, ly["m2"], ly["r2"],
+                              add=tbr, x_out=ly["s2"])
             st["layers"].append(ly)
         st["xb_final"] = xb
         st["feat"] = self.f32("t.feat", B, self.E)

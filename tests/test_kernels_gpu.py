@@ -138,6 +138,11 @@ def test_layernorm_fwd_bwd(rows, d, eps):
     assert_close(dg, gr.grad, 1e-3, 1e-3 * math.sqrt(rows), "ln dgamma")
     assert_close(db, br.grad, 1e-3, 1e-3 * math.sqrt(rows), "ln dbeta")
     assert_close(dbias, (xr.grad + dx_add).sum(0), 1e-3, 1e-3 * math.sqrt(rows), "ln dbias")
+    # fused residual add: LN(x + add) with the sum written out
+    add = rnd(rows, d, seed=28).bfloat16(); xo = torch.empty(rows, d, device=DEV)
+    ops.layernorm_fwd(x, g, b, eps, yb, yf, mean, rstd, add=add, x_out=xo)
+    assert_close(xo, x + add.float(), 1e-6, 1e-6, "ln add x_out")
+    assert_close(yf, torch.nn.functional.layer_norm(x + add.float(), (d,), g, b, eps), 1e-4, 1e-4, "ln add y")
     # bf16 dy, strided x rows (CLS pooling)
     L_ = 5
     xs = rnd(rows * L_, d, seed=27)
