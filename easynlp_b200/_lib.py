@@ -14,6 +14,10 @@ class ClipkError(RuntimeError):
     pass
 
 
+class Dropout(C.Structure):
+    _fields_ = [("p", C.c_float), ("seed", C.c_ulonglong), ("dev_offset", C.c_void_p), ("site", C.c_uint)]
+
+
 class Epilogue(C.Structure):
     _fields_ = [("mode", C.c_int), ("out_dtype", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int),
                 ("out2", C.c_void_p), ("ldo2", C.c_int), ("bias", C.c_void_p), ("residual", C.c_void_p),
@@ -40,10 +44,12 @@ def _declare(L):
     vp, i, f = C.c_void_p, C.c_int, C.c_float
     ll = C.c_longlong
     L.clipk_gemm_bf16.argtypes = [vp, i, i, vp, i, i, i, i, i, C.POINTER(Epilogue), i, vp]
-    L.clipk_attention_fwd.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
-    L.clipk_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
-    L.clipk_layernorm_fwd.argtypes = [vp, ll, vp, ll, vp, vp, vp, f, vp, vp, vp, vp, i, i, vp]
-    L.clipk_layernorm_bwd.argtypes = [vp, i, vp, vp, ll, vp, vp, vp, vp, vp, ll, vp, vp, vp, vp, i, i, vp]
+    dp = C.POINTER(Dropout)
+    L.clipk_attention_fwd.argtypes = [vp, vp, vp, vp, i, i, i, i, dp, vp]
+    L.clipk_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, dp, vp]
+    L.clipk_dropout_mask.argtypes = [vp, i, i, dp, vp]
+    L.clipk_layernorm_fwd.argtypes = [vp, ll, vp, ll, vp, vp, vp, f, vp, vp, vp, vp, i, i, dp, i, vp]
+    L.clipk_layernorm_bwd.argtypes = [vp, i, vp, vp, ll, vp, vp, vp, vp, vp, ll, vp, vp, vp, vp, i, i, dp, i, vp]
     L.clipk_colsum.argtypes = [vp, i, ll, vp, i, i, vp]
     L.clipk_im2col_patches.argtypes = [vp, vp, i, i, i, vp]
     L.clipk_vit_assemble.argtypes = [vp, vp, vp, vp, i, i, i, vp]

@@ -73,6 +73,20 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return 0;
 }
 
+DropArg make_drop_arg(const void* ptr) {
+  DropArg a{};
+  const clipk_dropout_t* d = reinterpret_cast<const clipk_dropout_t*>(ptr);
+  if (!d || !(d->p > 0.f)) return a;
+  float p = d->p > 0.999f ? 0.999f : d->p;
+  a.on = 1;
+  a.k0 = (uint32_t)(d->seed & 0xffffffffull); a.k1 = (uint32_t)(d->seed >> 32);
+  a.site = d->site;
+  a.thresh = (uint32_t)((double)p * 4294967296.0);
+  a.scale = 1.0f / (1.0f - p);
+  a.dev_offset = d->dev_offset;
+  return a;
+}
+
 }  // namespace clipk
 
 extern "C" const char* clipk_last_error(void) { return clipk::g_err; }

@@ -31,6 +31,7 @@ struct AttnParams {
   const bf16* ctx_in;  // bwd in
   const bf16* dctx;    // bwd in  [B*L, d]
   bf16* dqkv;          // bwd out [B*L, 3d]
+  DropArg drop;        // dropout on the attention probabilities (modeling_bert.py:238); element (b,h,q,j): row = (b*H+h)*L+q, quad = j/4
 };
 
 __device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return umma_smem_desc(addr, 16, 1024); }                // K-major
@@ -105,6 +106,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const float sc = p.scale * LOG2E;
   const int split = ((p.lk_pad >> 1) + 15) & ~15;
   const int c_begin = half ? split : 0, c_end = half ? p.lk_pad : split;
+  const DropCtx dc = drop_ctx(p.drop);
+  const uint32_t drow = (uint32_t)((b * p.H + h) * p.L + q);
   float mx = -INFINITY;
   {
     uint32_t r[16], rn[16];
@@ -138,6 +141,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < 16; ++j) {
         pv[j] = exp2f(fmaf(__uint_as_float(r[j]), sc, m[j] - mx));
         sum += pv[j];
+      }
+      if (dc.on) {       // the row sum (softmax denominator) is taken before dropout, the mask only multiplies P
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 mm = drop_mult4(dc, drow, (c0 >> 2) + j4);
+          pv[4 * j4] *= mm.x; pv[4 * j4 + 1] *= mm.y; pv[4 * j4 + 2] *= mm.z; pv[4 * j4 + 3] *= mm.w;
+        }
       }
       store_row8_sw128(sP, row, c0, pv);
       store_row8_sw128(sP, row, c0 + 8, pv + 8);
@@ -207,7 +217,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sV = sK + k_bytes;
   uint8_t* sP = sV + k_bytes;                     // P, overwritten in place by dS once dV += P^T dO has completed
   uint8_t* sDS = sP;
-  float* smask = reinterpret_cast<float*>(sP + ps_bytes);         // [256]
+  const DropCtx dc = drop_ctx(p.drop);
+  uint8_t* sPd = sP + (dc.on ? ps_bytes : 0);     // dropout: the dV MMA reads the MASKED probabilities from a second tile
+  float* smask = reinterpret_cast<float*>(sPd + ps_bytes);        // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smask + 256);      // kv, qdo[0], qdo[1], s, dp, dq
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
 
@@ -226,7 +238,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16);
   const int split = ((p.lk_pad >> 1) + 15) & ~15;   // balance the VALID key columns between the two halves
   const int c_begin = half ? split : 0, c_end = half ? kt_pad : split;
-  const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sDS);
+  const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sPd), aDS = smem_u32(sDS);
   const float sc = p.scale * LOG2E;
   const int ksteps = p.lk_pad >> 4;
 
@@ -246,6 +258,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row = q4 * 32 + lane;
     const int q = qt * 128 + row;
     const bool qvalid = q < p.L;
+    const uint32_t drow = (uint32_t)((b * p.H + h) * p.L + q);
     // ---- loads + S = Q K^T
     if (tid == 0) {
       if (qt + 1 < p.q_tiles) {   // prefetch the next query tile into the other buffer (its last readers finished with tile qt-1)
@@ -299,6 +312,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       store_row8_sw128(sP, row, c0, pv);
       store_row8_sw128(sP, row, c0 + 8, pv + 8);
+      if (dc.on) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 mm = drop_mult4(dc, drow, (c0 >> 2) + j4);
+          pv[4 * j4] *= mm.x; pv[4 * j4 + 1] *= mm.y; pv[4 * j4 + 2] *= mm.z; pv[4 * j4 + 3] *= mm.w;
+        }
+        store_row8_sw128(sPd, row, c0, pv);
+        store_row8_sw128(sPd, row, c0 + 8, pv + 8);
+      }
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -330,6 +352,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_wait_ld();
         const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&pa);
         const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&pb);
+        if (dc.on) {     // dP = dP~ o mask (P~ = P o mask is what fed the value matmul)
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 mm = drop_mult4(dc, drow, (c0 >> 2) + j4);
+            r[4 * j4] = __float_as_uint(__uint_as_float(r[4 * j4]) * mm.x); r[4 * j4 + 1] = __float_as_uint(__uint_as_float(r[4 * j4 + 1]) * mm.y);
+            r[4 * j4 + 2] = __float_as_uint(__uint_as_float(r[4 * j4 + 2]) * mm.z); r[4 * j4 + 3] = __float_as_uint(__uint_as_float(r[4 * j4 + 3]) * mm.w);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float2 x = __bfloat1622float2(a2[j]), y = __bfloat1622float2(b2[j]);
@@ -426,7 +456,7 @@ static int check_shapes(const char* who, int B, int L, int H, int d) {
 using namespace clipk;
 
 extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void* ctx, float* lse, int B, int L, int H, int d,
-                                   cudaStream_t stream) {
+                                   const clipk_dropout_t* drop, cudaStream_t stream) {
   int rc = check_shapes("attention_fwd", B, L, H, d);
   if (rc) return rc;
   AttnParams p{};
@@ -435,6 +465,7 @@ extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void*
   p.q_tiles = (L + 127) / 128;
   p.scale = 0.125f;
   p.mask = key_mask; p.ctx = (bf16*)ctx; p.lse = lse;
+  p.drop = make_drop_arg(drop);
   CUtensorMap tQ, tKV;
   if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, p.lk_pad))) return rc;
@@ -454,7 +485,7 @@ extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void*
 }
 
 extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
-                                   int B, int L, int H, int d, cudaStream_t stream) {
+                                   int B, int L, int H, int d, const clipk_dropout_t* drop, cudaStream_t stream) {
   int rc = check_shapes("attention_bwd", B, L, H, d);
   if (rc) return rc;
   AttnParams p{};
@@ -464,13 +495,15 @@ extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const
   p.scale = 0.125f;
   p.mask = key_mask; p.lse = const_cast<float*>(lse);
   p.ctx_in = (const bf16*)ctx; p.dctx = (const bf16*)dctx; p.dqkv = (bf16*)dqkv;
+  p.drop = make_drop_arg(drop);
+  if (p.drop.on && L > 128) { set_error("attention_bwd: attention dropout is implemented for L <= 128 (the text tower)"); return CLIPK_ERR_UNSUPPORTED; }
   CUtensorMap tQ, tKV, tDO;
   if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, p.lk_pad))) return rc;
   if ((rc = make_tmap_2d_bf16(&tDO, dctx, (uint64_t)d, (uint64_t)B * L, (uint64_t)d, 64, 128))) return rc;
   const int k_bytes = p.lk_pad * 128;
   const int n_kt = p.lk_pad > 128 ? 2 : 1;
-  const int smem = 4 * 16384 + 2 * k_bytes + (n_kt * 2 * 16384) + 1024 + 64 + 1024;
+  const int smem = 4 * 16384 + 2 * k_bytes + (n_kt * 2 * 16384) * (p.drop.on ? 2 : 1) + 1024 + 64 + 1024;
   static int configured = 0;
   if (configured < smem) {
     CLIPK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

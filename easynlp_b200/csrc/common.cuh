@@ -28,6 +28,8 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
                       uint32_t box_inner, uint32_t box_outer);
 int sm_count();
 void note_launch(int n = 1);
+struct DropArg;
+DropArg make_drop_arg(const void* clipk_dropout);   // NULL / p <= 0 -> off
 
 // ------------------------------------------------------------------------------------------ misc device
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -213,6 +215,42 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
 
 // byte offset of element (row r, 16-byte chunk c) inside a [rows x 128 B] SWIZZLE_128B tile whose base is 1024-B aligned
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t chunk16) { return r * 128u + ((chunk16 ^ (r & 7u)) << 4); }
+
+// ------------------------------------------------------------------------------------------ dropout (Philox4x32-10)
+// Counter-based RNG: the keep/drop decision of an element depends only on (seed, per-step device offset, site, element index), so
+// the backward kernels regenerate the forward masks instead of storing them.  One call yields 4 independent 32-bit draws.
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+struct DropCtx {       // resolved on the device from clipk_dropout_t
+  uint32_t k0, k1, site, thresh;
+  float scale;         // 1 / (1 - p)
+  bool on;
+};
+struct DropArg {       // built on the host (make_drop_arg) and passed by value to kernels
+  uint32_t k0, k1, site, thresh;
+  float scale;
+  const unsigned int* dev_offset;
+  int on;
+};
+__device__ __forceinline__ DropCtx drop_ctx(const DropArg& a) {
+  DropCtx d;
+  d.k0 = a.k0 ^ (a.dev_offset ? *a.dev_offset : 0u); d.k1 = a.k1; d.site = a.site; d.thresh = a.thresh; d.scale = a.scale; d.on = a.on != 0;
+  return d;
+}
+// multipliers (0 or 1/(1-p)) for the 4 consecutive elements starting at element index 4*quad of row `row`
+__device__ __forceinline__ float4 drop_mult4(const DropCtx& d, uint32_t row, uint32_t quad) {
+  const uint4 r = philox4x32(row, quad, d.site, 0x2545F491u, d.k0, d.k1);
+  return make_float4(r.x >= d.thresh ? d.scale : 0.f, r.y >= d.thresh ? d.scale : 0.f, r.z >= d.thresh ? d.scale : 0.f,
+                     r.w >= d.thresh ? d.scale : 0.f);
+}
 
 // ------------------------------------------------------------------------------------------ math
 __device__ __forceinline__ float quick_gelu_f(float x) { return x / (1.0f + __expf(-1.702f * x)); }

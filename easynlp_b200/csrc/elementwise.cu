@@ -31,10 +31,14 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             long long ldadd, float* __restrict__ x_out, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, bf16* __restrict__ y_bf16,
                                                             float* __restrict__ y_f32, float* __restrict__ mean_out,
-                                                            float* __restrict__ rstd_out, int rows, int d) {
+                                                            float* __restrict__ rstd_out, int rows, int d, const DropArg da,
+                                                            const int drop_mode) {
+  // drop_mode 1: dropout on `add` (BertSelfOutput / BertOutput: LN(dropout(dense) + input), modeling_bert.py:266-268,344-346)
+  // drop_mode 2: dropout on the normalised output (BertEmbeddings, modeling_bert.py:127-128)
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  const DropCtx dc = drop_ctx(da);
   const float* xr = x + (long long)row * ldx;
   float4 v[NV];
   float s = 0.f;
@@ -44,7 +48,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     const bf16* ar = add + (long long)row * ldadd;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float4 a = ld_bf4(ar + (lane + 32 * i) * 4);
+      float4 a = ld_bf4(ar + (lane + 32 * i) * 4);
+      if (dc.on && drop_mode == 1) { const float4 m = drop_mult4(dc, row, lane + 32 * i); a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w; }
       v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
     }
   }
@@ -73,6 +78,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     o.y = (v[i].y - mean) * rstd * g.y + b.y;
     o.z = (v[i].z - mean) * rstd * g.z + b.z;
     o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (dc.on && drop_mode == 2) { const float4 m = drop_mult4(dc, row, lane + 32 * i); o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w; }
     if (y_f32) st_f4(y_f32 + (long long)row * d + c, o);
     if (y_bf16) st_bf4(y_bf16 + (long long)row * d + c, o);
   }
@@ -89,8 +95,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
                                                             const float* __restrict__ rstd_in, const float* __restrict__ dx_add,
                                                             float* __restrict__ dx_f32, long long lddx, bf16* __restrict__ dx_bf16,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            float* __restrict__ dbias, int rows, int d) {
+                                                            float* __restrict__ dbias, int rows, int d, const DropArg da,
+                                                            const int drop_mode) {
+  // drop_mode 1: forward was LN(x + dropout(t)): the gradient handed to t's producers (dx_bf16, dbias) carries the mask, the
+  //              residual path (dx_f32) does not.   drop_mode 2: forward was dropout(LN(x)): the incoming gradient is masked first.
   __shared__ float red[3][8][32 * 4];  // [which][warp][lane*4]  (per i iteration)
+  const DropCtx dc = drop_ctx(da);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarp = blockDim.x >> 5;
@@ -113,6 +123,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
       float4 dv = dy_is_f32 ? ld_f4(reinterpret_cast<const float*>(dy) + (long long)row * d + c)
                             : ld_bf4(reinterpret_cast<const bf16*>(dy) + (long long)row * d + c);
       if (dy_add) { float4 a = ld_f4(dy_add + (long long)row * d + c); dv.x += a.x; dv.y += a.y; dv.z += a.z; dv.w += a.w; }
+      if (dc.on && drop_mode == 2) { const float4 m = drop_mult4(dc, row, lane + 32 * i); dv.x *= m.x; dv.y *= m.y; dv.z *= m.z; dv.w *= m.w; }
       xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd; xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
       ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
       ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
@@ -131,8 +142,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
       o.z = rstd * (g[i].z - s1 - xh[i].z * s2);
       o.w = rstd * (g[i].w - s1 - xh[i].w * s2);
       if (dx_add) { float4 a = ld_f4(dx_add + (long long)row * d + c); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-      ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;
       if (dx_f32) st_f4(dx_f32 + (long long)row * lddx + c, o);
+      if (dc.on && drop_mode == 1) { const float4 m = drop_mult4(dc, row, lane + 32 * i); o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w; }
+      ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;
       if (dx_bf16) st_bf4(dx_bf16 + (long long)row * d + c, o);
     }
   }
@@ -330,6 +342,16 @@ __global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ x, 
   }
 }
 
+// multipliers of a [rows, cols] dropout site, exactly as drop_mult4 yields them inside the fused kernels
+__global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ out, int rows, int cols, const DropArg da) {
+  const DropCtx dc = drop_ctx(da);
+  const long long total4 = (long long)rows * cols / 4;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
+    const uint32_t row = (uint32_t)(t / (cols / 4)), quad = (uint32_t)(t % (cols / 4));
+    st_f4(out + t * 4, dc.on ? drop_mult4(dc, row, quad) : make_float4(1.f, 1.f, 1.f, 1.f));
+  }
+}
+
 static inline int grid_for(long long work_items, int per_cta) {
   long long g = (work_items + per_cta - 1) / per_cta;
   long long cap = (long long)sm_count() * 8;
@@ -350,12 +372,13 @@ using namespace clipk;
 
 extern "C" int clipk_layernorm_fwd(const float* x, long long ldx, const void* add_bf16, long long ldadd, float* x_out, const float* gamma,
                                    const float* beta, float eps, void* y_bf16, float* y_f32, float* mean, float* rstd, int rows, int d,
-                                   cudaStream_t stream) {
+                                   const clipk_dropout_t* drop, int drop_mode, cudaStream_t stream) {
   if (rows <= 0) return 0;
   if (d % 128 || d > 128 * LN_MAXV || (ldx % 4) || (ldadd % 4)) { set_error("layernorm_fwd: d=%d ldx=%lld unsupported", d, ldx); return CLIPK_ERR_UNSUPPORTED; }
   const int nv = d / 128;
   dim3 grid((rows + 7) / 8), block(256);
-#define LAUNCH(NV) layernorm_fwd_kernel<NV><<<grid, block, 0, stream>>>(x, ldx, (const bf16*)add_bf16, ldadd, x_out, gamma, beta, eps, (bf16*)y_bf16, y_f32, mean, rstd, rows, d)
+  const DropArg da = make_drop_arg(drop);
+#define LAUNCH(NV) layernorm_fwd_kernel<NV><<<grid, block, 0, stream>>>(x, ldx, (const bf16*)add_bf16, ldadd, x_out, gamma, beta, eps, (bf16*)y_bf16, y_f32, mean, rstd, rows, d, da, drop_mode)
   LN_DISPATCH(nv, LAUNCH)
 #undef LAUNCH
   note_launch();
@@ -365,7 +388,8 @@ extern "C" int clipk_layernorm_fwd(const float* x, long long ldx, const void* ad
 
 extern "C" int clipk_layernorm_bwd(const void* dy, int dy_is_f32, const float* dy_add, const float* x, long long ldx, const float* gamma,
                                    const float* mean, const float* rstd, const float* dx_add, float* dx_f32, long long lddx,
-                                   void* dx_bf16, float* dgamma, float* dbeta, float* dbias, int rows, int d, cudaStream_t stream) {
+                                   void* dx_bf16, float* dgamma, float* dbeta, float* dbias, int rows, int d, const clipk_dropout_t* drop,
+                                   int drop_mode, cudaStream_t stream) {
   if (rows <= 0) return 0;
   if (d % 128 || d > 128 * LN_MAXV || (ldx % 4) || (lddx % 4)) { set_error("layernorm_bwd: d=%d unsupported", d); return CLIPK_ERR_UNSUPPORTED; }
   const int nv = d / 128;
@@ -373,7 +397,8 @@ extern "C" int clipk_layernorm_bwd(const void* dy, int dy_is_f32, const float* d
   const int cap = sm_count() * 4;
   if (g > cap) g = cap;
   dim3 grid(g), block(256);
-#define LAUNCH(NV) layernorm_bwd_kernel<NV><<<grid, block, 0, stream>>>(dy, dy_is_f32, dy_add, x, ldx, gamma, mean, rstd, dx_add, dx_f32, lddx, (bf16*)dx_bf16, dgamma, dbeta, dbias, rows, d)
+  const DropArg da = make_drop_arg(drop);
+#define LAUNCH(NV) layernorm_bwd_kernel<NV><<<grid, block, 0, stream>>>(dy, dy_is_f32, dy_add, x, ldx, gamma, mean, rstd, dx_add, dx_f32, lddx, (bf16*)dx_bf16, dgamma, dbeta, dbias, rows, d, da, drop_mode)
   LN_DISPATCH(nv, LAUNCH)
 #undef LAUNCH
   note_launch();
@@ -468,6 +493,14 @@ extern "C" int clipk_axpy(const float* x, float* y, float alpha, long long n, cu
   if (n % 4) { set_error("axpy: n %% 4 != 0"); return CLIPK_ERR_ARG; }
   if (n == 0) return 0;
   axpy_kernel<<<grid_for(n / 4, 256 * 4), 256, 0, stream>>>(x, y, alpha, n / 4);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_dropout_mask(float* out, int rows, int cols, const clipk_dropout_t* drop, cudaStream_t stream) {
+  if (cols % 4) { set_error("dropout_mask: cols %% 4 != 0"); return CLIPK_ERR_ARG; }
+  dropout_mask_kernel<<<grid_for((long long)rows * cols / 4, 256 * 4), 256, 0, stream>>>(out, rows, cols, make_drop_arg(drop));
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

@@ -54,6 +54,14 @@ class ClipEngine:
         self._saved = None
         self.norm_and_coef = torch.zeros(2, device=self.dev)
         self._norm_ws = torch.zeros(1024, dtype=torch.float64, device=self.dev)
+        # device-resident optimizer step counter (also the per-step dropout offset) and {lr, step size}
+        self._dev_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._dev_hyper = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        # BERT-tower dropout (nn.Dropout in modeling_bert.py:85,128,238,267,345); the ViT tower has none
+        self.p_hidden = float(cfg.get("text_hidden_dropout_prob", 0.0) or 0.0)
+        self.p_attn = float(cfg.get("text_attention_probs_dropout_prob", 0.0) or 0.0)
+        self.dropout_seed = 0x5EED_C11B
+        self._drops = {}
 
     # ------------------------------------------------------------------ buffers
     def buf(self, name, shape, dtype):
@@ -190,20 +198,31 @@ class ClipEngine:
                  mode=L.EPI_ATOMIC_ADD, splits=_splits_for(W, kdim, npatch))
 
     # ------------------------------------------------------------------ BERT
-    def bert_forward(self, ids: torch.Tensor, save: bool):
+    def _drop(self, train: bool, p: float, site: int):
+        """clipk_dropout_t of one call site (None in eval mode / p == 0); the structs are cached so their addresses stay valid"""
+        if not train or p <= 0.0:
+            return None
+        key = (p, site)
+        d = self._drops.get(key)
+        if d is None:
+            d = ops.make_dropout(p, self.dropout_seed, site, self._dev_step)
+            self._drops[key] = d
+        return d
+
+    def bert_forward(self, ids: torch.Tensor, save: bool, train: bool = False):
         P_ = self.params; H = self.H; I = self.I; B, Lt = ids.shape; M = B * Lt; Hh = self.Ht
         assert ids.dtype == torch.int64 and ids.is_contiguous()
         if Lt > self.cfg["text_max_position_embeddings"]:
             raise ValueError("sequence longer than the position table")
         eps = 1e-12                                                   # modeling_chineseclip.py:311
-        st = {"B": B, "Lt": Lt, "ids": ids, "layers": []}
+        st = {"B": B, "Lt": Lt, "ids": ids, "layers": [], "train": train}
         st["e"] = self.f32("t.e", M, H); st["mask"] = self.f32("t.mask", M)
         ops.bert_embed(ids.view(-1), P_.p("bert.embeddings.word_embeddings.weight"), P_.p("bert.embeddings.position_embeddings.weight"),
                        P_.p("bert.embeddings.token_type_embeddings.weight"), st["e"], M, Lt, H, self.cfg["vocab_size"], key_mask=st["mask"])
         x = self.f32("t.x.0", M, H); xb = self.bf("t.xb.0", M, H)
         st["me"] = self.f32("t.me", M); st["re"] = self.f32("t.re", M)
         ops.layernorm_fwd(st["e"], P_.p("bert.embeddings.LayerNorm.weight"), P_.p("bert.embeddings.LayerNorm.bias"), eps, xb, x,
-                          st["me"], st["re"])
+                          st["me"], st["re"], drop=self._drop(train, self.p_hidden, 1), drop_mode=2)
         tbr = self.bf("t.tbr", M, H)                 # bf16 branch output of attention.output.dense / output.dense
         for i in range(self.nt):
             p = f"bert.encoder.layer.{i}."
@@ -212,13 +231,14 @@ class ClipEngine:
             ly["qkv"] = self.bf(tag + "qkv", M, 3 * H)
             ops.gemm(xb, P_.w(p + "attention.self.query.weight", (3 * H, H)), ly["qkv"], bias=P_.p(p + "attention.self.query.bias", (3 * H,)))
             ly["ctx"] = self.bf(tag + "ctx", M, H); ly["lse"] = self.f32(tag + "lse", B * Hh * Lt)
-            ops.attention_fwd(ly["qkv"], st["mask"], ly["ctx"], ly["lse"], B, Lt, Hh)
+            ops.attention_fwd(ly["qkv"], st["mask"], ly["ctx"], ly["lse"], B, Lt, Hh, drop=self._drop(train, self.p_attn, 16 * (i + 1)))
             ops.gemm(ly["ctx"], P_.w(p + "attention.output.dense.weight"), tbr, bias=P_.p(p + "attention.output.dense.bias"))
             ly["s1"] = self.f32(tag + "s1", M, H)
             ly["y1"] = self.f32(tag + "y1", M, H); ly["y1b"] = self.bf(tag + "y1b", M, H)
             ly["m1"] = self.f32(tag + "m1", M); ly["r1"] = self.f32(tag + "r1", M)
             ops.layernorm_fwd(x, P_.p(p + "attention.output.LayerNorm.weight"), P_.p(p + "attention.output.LayerNorm.bias"), eps,
-                              ly["y1b"], ly["y1"], ly["m1"], ly["r1"], add=tbr, x_out=ly["s1"])      # LN(dense(ctx) + input)
+                              ly["y1b"], ly["y1"], ly["m1"], ly["r1"], add=tbr, x_out=ly["s1"],      # LN(dropout(dense(ctx)) + input)
+                              drop=self._drop(train, self.p_hidden, 16 * (i + 1) + 1), drop_mode=1)
             ly["z"] = self.bf(tag + "z", M, I); ly["a"] = self.bf(tag + "a", M, I)                  # z = gelu'(.) saved for backward
             ops.gemm(ly["y1b"], P_.w(p + "intermediate.dense.weight"), ly["z"], bias=P_.p(p + "intermediate.dense.bias"),
                      mode=L.EPI_ERF_GELU, out2=ly["a"])
@@ -228,7 +248,7 @@ class ClipEngine:
             xb = self.bf(f"t.xb.{i + 1}" if save else f"t.xb.t{i % 2}", M, H)
             ly["m2"] = self.f32(tag + "m2", M); ly["r2"] = self.f32(tag + "r2", M)
             ops.layernorm_fwd(ly["y1"], P_.p(p + "output.LayerNorm.weight"), P_.p(p + "output.LayerNorm.bias"), eps, xb, x, ly["m2"], ly["r2"],
-                              add=tbr, x_out=ly["s2"])
+                              add=tbr, x_out=ly["s2"], drop=self._drop(train, self.p_hidden, 16 * (i + 1) + 2), drop_mode=1)
             st["layers"].append(ly)
         st["xb_final"] = xb
         st["feat"] = self.f32("t.feat", B, self.E)
@@ -240,6 +260,7 @@ class ClipEngine:
 
     def bert_backward(self, st, d_embeds: torch.Tensor):
         P_ = self.params; H = self.H; I = self.I; B = st["B"]; Lt = st["Lt"]; M = B * Lt; Hh = self.Ht; E = self.E
+        train = st.get("train", False)
         dfeat_b = self.bf("t.dfeat_b", B, E)
         ops.l2norm_bwd(d_embeds, st["embeds"], st["norm"], None, dfeat_b, B, E)
         cls_rows = st["xb_final"].view(B, Lt * H)[:, :H]
@@ -255,7 +276,8 @@ class ClipEngine:
             p = f"bert.encoder.layer.{i}."
             ly = st["layers"][i]
             ops.layernorm_bwd(dy, ly["s2"], P_.p(p + "output.LayerNorm.weight"), ly["m2"], ly["r2"], dy_add=dy_add, dx_f32=ds2, dx_bf16=ds2b,
-                              dgamma=P_.g(p + "output.LayerNorm.weight"), dbeta=P_.g(p + "output.LayerNorm.bias"), dbias=P_.g(p + "output.dense.bias"))
+                              dgamma=P_.g(p + "output.LayerNorm.weight"), dbeta=P_.g(p + "output.LayerNorm.bias"), dbias=P_.g(p + "output.dense.bias"),
+                              drop=self._drop(train, self.p_hidden, 16 * (i + 1) + 2), drop_mode=1)
             ops.gemm(ds2b, ly["a"], P_.g(p + "output.dense.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD, splits=_splits_for(H, I, M))
             ops.gemm(ds2b, P_.w(p + "output.dense.weight"), dz, b_mn_major=1, mode=L.EPI_MUL_AUX, aux=ly["z"])
             ops.colsum(dz, P_.g(p + "intermediate.dense.bias"), M, I)
@@ -263,11 +285,12 @@ class ClipEngine:
             ops.gemm(dz, P_.w(p + "intermediate.dense.weight"), dpart, b_mn_major=1)
             ops.layernorm_bwd(dpart, ly["s1"], P_.p(p + "attention.output.LayerNorm.weight"), ly["m1"], ly["r1"], dy_add=ds2, dx_f32=ds1,
                               dx_bf16=ds1b, dgamma=P_.g(p + "attention.output.LayerNorm.weight"),
-                              dbeta=P_.g(p + "attention.output.LayerNorm.bias"), dbias=P_.g(p + "attention.output.dense.bias"))
+                              dbeta=P_.g(p + "attention.output.LayerNorm.bias"), dbias=P_.g(p + "attention.output.dense.bias"),
+                              drop=self._drop(train, self.p_hidden, 16 * (i + 1) + 1), drop_mode=1)
             ops.gemm(ds1b, ly["ctx"], P_.g(p + "attention.output.dense.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
                      splits=_splits_for(H, H, M))
             ops.gemm(ds1b, P_.w(p + "attention.output.dense.weight"), dctx, b_mn_major=1)
-            ops.attention_bwd(ly["qkv"], st["mask"], ly["ctx"], ly["lse"], dctx, dqkv, B, Lt, Hh)
+            ops.attention_bwd(ly["qkv"], st["mask"], ly["ctx"], ly["lse"], dctx, dqkv, B, Lt, Hh, drop=self._drop(train, self.p_attn, 16 * (i + 1)))
             ops.colsum(dqkv, P_.g(p + "attention.self.query.bias", (3 * H,)), M, 3 * H)
             ops.gemm(dqkv, ly["xb_in"], P_.g(p + "attention.self.query.weight", (3 * H, H)), a_mn_major=1, b_mn_major=1,
                      mode=L.EPI_ATOMIC_ADD, splits=_splits_for(3 * H, H, M))
@@ -277,7 +300,8 @@ class ClipEngine:
             dy, dy_add = dxp, ds1
         de = self.f32("t.de", M, H)
         ops.layernorm_bwd(dy, st["e"], P_.p("bert.embeddings.LayerNorm.weight"), st["me"], st["re"], dy_add=dy_add, dx_f32=de,
-                          dgamma=P_.g("bert.embeddings.LayerNorm.weight"), dbeta=P_.g("bert.embeddings.LayerNorm.bias"))
+                          dgamma=P_.g("bert.embeddings.LayerNorm.weight"), dbeta=P_.g("bert.embeddings.LayerNorm.bias"),
+                          drop=self._drop(train, self.p_hidden, 1), drop_mode=2)
         ops.bert_embed_bwd(st["ids"].view(-1), de, P_.g("bert.embeddings.word_embeddings.weight"), M, H, self.cfg["vocab_size"])
         ops.colsum(de, P_.g("bert.embeddings.position_embeddings.weight").view(-1)[:Lt * H], B, Lt * H)
         ops.colsum(de, P_.g("bert.embeddings.token_type_embeddings.weight")[0], M, H)
@@ -331,13 +355,15 @@ class ClipEngine:
             out["text_embeds"] = self.bert_forward(ids, save=False)["embeds"]
         return out
 
-    def forward(self, pixels, ids, save=True, want_logits=True, distributed=False):
+    def forward(self, pixels, ids, save=True, want_logits=True, distributed=False, train=None):
         """Both towers + the contrastive head.  distributed=True: all-gather the embedding shards over the default process
         group and take the loss over the GLOBAL batch (labels offset by rank * local_B); 'loss' is then this rank's share
         (sum over ranks = global loss) and 'logits_per_text' the local [b, G] strip."""
         from . import distributed as D
+        if train is None:
+            train = save           # training step <=> activations are kept; dropout is active only then
         v = self.vit_forward(pixels, save)
-        t = self.bert_forward(ids, save)
+        t = self.bert_forward(ids, save, train=train)
         if distributed and D.world_size() > 1:
             B = pixels.shape[0]; Wd = D.world_size()
             gi = D.gather_rows(v["embeds"], self.f32("l.gi", Wd * B, self.E))
@@ -383,9 +409,6 @@ class ClipEngine:
         P_ = self.params
         P_.step += 1
         n_tr, n_dec = P_.n_trainable, P_.n_decay
-        if not hasattr(self, "_dev_step"):
-            self._dev_step = torch.full((1,), P_.step - 1, dtype=torch.int32, device=self.dev)
-            self._dev_hyper = torch.zeros(2, dtype=torch.float32, device=self.dev)
         ops.adam_schedule(self._dev_step, self._dev_hyper, float(lr), int(warmup_steps), int(t_total))
         coef = None
         if max_grad_norm and max_grad_norm > 0:

@@ -93,6 +93,20 @@ def gemm(a, b, out, *, a_mn_major=0, b_mn_major=0, mode=L.EPI_LINEAR, bias=None,
     return out
 
 
+def make_dropout(p, seed, site, dev_offset=None):
+    """clipk_dropout_t for one call site (None when p == 0).  dev_offset: optional uint32/int32 device tensor xor-ed into the key."""
+    if not p or p <= 0.0:
+        return None
+    d = L_.Dropout()
+    d.p = float(p); d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF; d.site = int(site)
+    d.dev_offset = dev_offset.data_ptr() if dev_offset is not None else None
+    return d
+
+
+def _dp(d):
+    return C.byref(d) if d is not None else None
+
+
 def _f32(t):
     assert t is None or (t.dtype == torch.float32 and t.is_cuda), "expected a CUDA float32 tensor"
     return _ptr(t)
@@ -104,26 +118,26 @@ def _b16(t):
 
 
 @_op
-def attention_fwd(qkv, key_mask, ctx, lse, B, L, H):
+def attention_fwd(qkv, key_mask, ctx, lse, B, L, H, drop=None):
     d = H * 64
     assert qkv.shape == (B * L, 3 * d) and qkv.is_contiguous() and ctx.shape == (B * L, d) and ctx.is_contiguous()
     assert lse.numel() == B * H * L
     with _traced("attention_fwd", 4.0 * B * H * L * L * 64):
-        L_.check(L_.lib().clipk_attention_fwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), B, L, H, d, _stream()), "attention_fwd")
+        L_.check(L_.lib().clipk_attention_fwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), B, L, H, d, _dp(drop), _stream()), "attention_fwd")
 
 
 @_op
-def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H):
+def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H, drop=None):
     d = H * 64
     assert dqkv.shape == (B * L, 3 * d) and dqkv.is_contiguous() and dctx.shape == (B * L, d) and dctx.is_contiguous()
     with _traced("attention_bwd", 10.0 * B * H * L * L * 64):
         L_.check(L_.lib().clipk_attention_bwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), _b16(dctx), _b16(dqkv), B, L, H, d,
-                                              _stream()), "attention_bwd")
+                                              _dp(drop), _stream()), "attention_bwd")
 
 
 @_op
 def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None, rows=None, ldx=None, add=None, ldadd=None,
-                  x_out=None):
+                  x_out=None, drop=None, drop_mode=0):
     d = gamma.numel()
     if rows is None:
         rows = x.numel() // d
@@ -132,12 +146,12 @@ def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=
     if add is not None and ldadd is None:
         ldadd = d
     L_.check(L_.lib().clipk_layernorm_fwd(_f32(x), ldx, _b16(add), ldadd or 0, _f32(x_out), _f32(gamma), _f32(beta), eps, _b16(y_bf16),
-                                          _f32(y_f32), _f32(mean), _f32(rstd), rows, d, _stream()), "layernorm_fwd")
+                                          _f32(y_f32), _f32(mean), _f32(rstd), rows, d, _dp(drop), int(drop_mode), _stream()), "layernorm_fwd")
 
 
 @_op
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, dy_add=None, dx_add=None, dx_f32=None, dx_bf16=None, dgamma=None, dbeta=None,
-                  dbias=None, rows=None, ldx=None, lddx=None):
+                  dbias=None, rows=None, ldx=None, lddx=None, drop=None, drop_mode=0):
     d = gamma.numel()
     if rows is None:
         rows = mean.numel()
@@ -147,7 +161,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dy_add=None, dx_add=None, dx_f32=
     assert dy.dtype in (torch.float32, torch.bfloat16)
     L_.check(L_.lib().clipk_layernorm_bwd(_ptr(dy), is_f32, _f32(dy_add), _f32(x), ldx, _f32(gamma), _f32(mean), _f32(rstd),
                                           _f32(dx_add), _f32(dx_f32), lddx, _b16(dx_bf16), _f32(dgamma), _f32(dbeta),
-                                          _f32(dbias), rows, d, _stream()), "layernorm_bwd")
+                                          _f32(dbias), rows, d, _dp(drop), int(drop_mode), _stream()), "layernorm_bwd")
 
 
 @_op
@@ -251,3 +265,8 @@ def retrieval_rank(Q, K, rank_out, label_offset=0):
     nq, E = Q.shape
     assert rank_out.dtype == torch.int32 and rank_out.numel() == nq and Q.is_contiguous() and K.is_contiguous()
     L_.check(L_.lib().clipk_retrieval_rank(_f32(Q), _f32(K), label_offset, _ptr(rank_out), nq, K.shape[0], E, _stream()), "retrieval_rank")
+
+
+@_op
+def dropout_mask(out, rows, cols, drop):
+    L_.check(L_.lib().clipk_dropout_mask(_f32(out), rows, cols, _dp(drop), _stream()), "dropout_mask")

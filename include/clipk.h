@@ -73,16 +73,32 @@ typedef struct {
 int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N, int K,
                     const clipk_epilogue_t* epi, int splits, cudaStream_t stream);
 
+/* -------------------------------------------------------------------------------------------- dropout
+ * Inverted dropout (keep with prob 1-p, scale 1/(1-p)) as in nn.Dropout of the BERT tower (modeling_bert.py:85,128,238,267,345).
+ * Masks are never stored: forward and backward regenerate them from Philox4x32-10 keyed by
+ * (seed ^ *dev_offset, site) and the element index.  dev_offset (optional device uint32, e.g. the optimizer's step counter)
+ * makes the mask change every step even when the launches are replayed from a CUDA graph.  p == 0 or a NULL pointer = off. */
+typedef struct {
+  float p;
+  unsigned long long seed;
+  const unsigned int* dev_offset;
+  unsigned int site;         /* distinct per dropout call site (layer, position in the layer) */
+} clipk_dropout_t;
+/* writes the multipliers (0 or 1/(1-p)) of a [rows, cols] site exactly as the fused kernels apply them (tests / debugging) */
+int clipk_dropout_mask(float* out, int rows, int cols, const clipk_dropout_t* drop, cudaStream_t stream);
+
 /* -------------------------------------------------------------------------------------------- attention
  * Fused softmax(Q K^T / 8 + key_mask) V for head dim 64 on packed projections qkv[B*L, 3d] (Q|K|V blocks, head h at
  * columns h*64).  Replaces nn.MultiheadAttention's SDPA (modeling_chineseclip.py:188,198-200) and BertSelfAttention
  * (modeling_bert.py:210-244, additive mask from modeling_utils.py:438-439).  L <= 256.
  * key_mask: optional f32 [B, L] additive (0 / -10000).  lse: f32 [B, H, L] saved for backward.                  */
 int clipk_attention_fwd(const void* qkv, const float* key_mask, void* ctx, float* lse, int B, int L, int H, int d,
+                        const clipk_dropout_t* drop /* optional: dropout on the probabilities, row = (b*H+h)*L+q, col = key */,
                         cudaStream_t stream);
 /* dqkv[B*L, 3d] (bf16) from dctx[B*L, d] (bf16); ctx / lse are the forward outputs.                             */
 int clipk_attention_bwd(const void* qkv, const float* key_mask, const void* ctx, const float* lse, const void* dctx,
-                        void* dqkv, int B, int L, int H, int d, cudaStream_t stream);
+                        void* dqkv, int B, int L, int H, int d, const clipk_dropout_t* drop /* same as forward; L <= 128 */,
+                        cudaStream_t stream);
 
 /* -------------------------------------------------------------------------------------------- LayerNorm
  * y = (x - mean) * rstd * gamma + beta over the last dim d (d % 128 == 0, d <= 1024), fp32 statistics
@@ -93,12 +109,15 @@ int clipk_attention_bwd(const void* qkv, const float* key_mask, const void* ctx,
  * `dense(...) + input_tensor` of modeling_bert.py:266,344 without a residual read in the GEMM epilogue.               */
 int clipk_layernorm_fwd(const float* x, long long ldx, const void* add_bf16, long long ldadd, float* x_out,
                         const float* gamma, const float* beta, float eps, void* y_bf16, float* y_f32, float* mean,
-                        float* rstd, int rows, int d, cudaStream_t stream);
+                        float* rstd, int rows, int d, const clipk_dropout_t* drop /* optional */,
+                        int drop_mode /* 1: dropout(add) before the sum; 2: dropout on the outputs */, cudaStream_t stream);
 /* g = dy (+ dy_add); dx = LN'(g) (+ dx_add) -> dx_f32 (stride lddx) / dx_bf16; dgamma, dbeta, dbias(=colsum dx) are
  * ACCUMULATED with fp32 atomics (optional).                                                                     */
 int clipk_layernorm_bwd(const void* dy, int dy_is_f32, const float* dy_add, const float* x, long long ldx,
                         const float* gamma, const float* mean, const float* rstd, const float* dx_add, float* dx_f32,
                         long long lddx, void* dx_bf16, float* dgamma, float* dbeta, float* dbias, int rows, int d,
+                        const clipk_dropout_t* drop /* optional */,
+                        int drop_mode /* 1: mask dx_bf16 + dbias (fwd mode 1); 2: mask the incoming gradient (fwd mode 2) */,
                         cudaStream_t stream);
 
 /* out[n] += sum over rows of x[rows, n] (bf16 or f32, row stride ldx): bias / positional / token-type gradients */

@@ -168,7 +168,7 @@ def _ln(x: Tensor, w: Tensor, b: Tensor, eps: float) -> Tensor:
 
 
 def _mha(x: Tensor, w_in: Tensor, b_in: Tensor, w_out: Tensor, b_out: Tensor, heads: int,
-         add_mask: Optional[Tensor] = None) -> Tensor:
+         add_mask: Optional[Tensor] = None, prob_mult: Optional[Tensor] = None) -> Tensor:
     """softmax(QK^T/sqrt(dh) + mask)V on [B, L, d] (nn.MultiheadAttention semantics,
     packed in_proj, modeling_chineseclip.py:188,198-200)."""
     B, L, d = x.shape
@@ -182,6 +182,8 @@ def _mha(x: Tensor, w_in: Tensor, b_in: Tensor, w_out: Tensor, b_out: Tensor, he
     if add_mask is not None:
         s = s + add_mask
     p = s.softmax(dim=-1)
+    if prob_mult is not None:           # explicit dropout multipliers (0 or 1/(1-p)) on the attention probabilities
+        p = p * prob_mult
     o = (p @ v).transpose(1, 2).reshape(B, L, d)
     return o @ w_out.t() + b_out
 
@@ -213,9 +215,12 @@ def vit_forward(sd: Dict[str, Tensor], cfg: dict, pixels: Tensor, taps: Optional
 
 
 # --------------------------------------------------------------------------- BERT
-def bert_forward(sd: Dict[str, Tensor], cfg: dict, ids: Tensor, taps: Optional[dict] = None) -> Tensor:
+def bert_forward(sd: Dict[str, Tensor], cfg: dict, ids: Tensor, taps: Optional[dict] = None,
+                 drop: Optional[dict] = None) -> Tensor:
     """BertModel(text, attention_mask = ids != 0)[0] -> last_hidden_state [B, L, H].
-    Dropout is the identity (eval / p = 0), as in every parity run."""
+    Dropout is the identity unless `drop` supplies explicit multiplier tensors (0 or 1/(1-p)) for the reference's nn.Dropout
+    sites: drop["emb"] [B,L,H] (modeling_bert.py:128), drop[("attn", i)] [B,heads,L,L] (:238), drop[("self_out", i)] and
+    drop[("out", i)] [B,L,H] (:267,345) -- used to test the fused Philox dropout of the CUDA path with ITS masks."""
     H = cfg["text_hidden_size"]; heads = cfg["text_num_attention_heads"]
     B, L = ids.shape
     eps = 1e-12                                                  # modeling_chineseclip.py:311
@@ -223,6 +228,9 @@ def bert_forward(sd: Dict[str, Tensor], cfg: dict, ids: Tensor, taps: Optional[d
          + sd["bert.embeddings.token_type_embeddings.weight"][0]
          + sd["bert.embeddings.position_embeddings.weight"][:L])
     x = F.layer_norm(x, (H,), sd["bert.embeddings.LayerNorm.weight"], sd["bert.embeddings.LayerNorm.bias"], eps)
+    drop = drop or {}
+    if "emb" in drop:
+        x = x * drop["emb"]
     if taps is not None:
         taps["bert.emb"] = x
     mask = (1.0 - ids.ne(0).to(x.dtype))[:, None, None, :] * -10000.0   # modeling_utils.py:438-439
@@ -233,11 +241,15 @@ def bert_forward(sd: Dict[str, Tensor], cfg: dict, ids: Tensor, taps: Optional[d
         w_in = torch.cat([sd[p + f"attention.self.{n}.weight"] for n in ("query", "key", "value")], 0)
         b_in = torch.cat([sd[p + f"attention.self.{n}.bias"] for n in ("query", "key", "value")], 0)
         a = _mha(x, w_in, b_in, sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"],
-                 heads, mask)
+                 heads, mask, drop.get(("attn", i)))
+        if ("self_out", i) in drop:
+            a = a * drop[("self_out", i)]
         x = F.layer_norm(a + x, (H,), sd[p + "attention.output.LayerNorm.weight"],
                          sd[p + "attention.output.LayerNorm.bias"], eps)
         h = act(x @ sd[p + "intermediate.dense.weight"].t() + sd[p + "intermediate.dense.bias"])
         h = h @ sd[p + "output.dense.weight"].t() + sd[p + "output.dense.bias"]
+        if ("out", i) in drop:
+            h = h * drop[("out", i)]
         x = F.layer_norm(h + x, (H,), sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"], eps)
         if taps is not None:
             taps[f"bert.layer{i}"] = x
@@ -246,14 +258,14 @@ def bert_forward(sd: Dict[str, Tensor], cfg: dict, ids: Tensor, taps: Optional[d
 
 # --------------------------------------------------------------------------- CLIP head
 def clip_forward(sd: Dict[str, Tensor], cfg: dict, pixels: Optional[Tensor], ids: Optional[Tensor],
-                 taps: Optional[dict] = None) -> dict:
+                 taps: Optional[dict] = None, drop: Optional[dict] = None) -> dict:
     """CLIPApp.forward for model_type == chinese_clip (appzoo/clip/model.py:106-150)."""
     image_embeds = text_embeds = None
     if pixels is not None:
         f = vit_forward(sd, cfg, pixels, taps)
         image_embeds = f / f.norm(dim=-1, keepdim=True)
     if ids is not None:
-        t = bert_forward(sd, cfg, ids, taps)[:, 0, :] @ sd["text_projection"]
+        t = bert_forward(sd, cfg, ids, taps, drop)[:, 0, :] @ sd["text_projection"]
         text_embeds = t / t.norm(dim=-1, keepdim=True)
     out = {"image_embeds": image_embeds, "text_embeds": text_embeds}
     if image_embeds is not None and text_embeds is not None:
