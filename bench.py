@@ -6,7 +6,7 @@
 
 One "step" = one full training step on a synthetic batch of `--batch` (default 256) pairs per GPU:
     zero_grad -> ViT + BERT forward -> (all-gather embeddings) -> fused InfoNCE -> backward -> (grad all-reduce) ->
-    global-norm clip + AdamW   (nothing skipped; dropout p = 0, stated in `config`).
+    global-norm clip + AdamW   (nothing skipped; BERT-tower dropout 0.1 as in the reference config, fused Philox masks).
 `value`  : device-resident inputs, K steps timed with CUDA events between barrier + synchronize, max over ranks.
 `e2e`    : the same step through the public plugin API (CLIPApp.forward / compute_loss / loss.backward / optimizer) with
            pinned HOST inputs copied every step and the loss read back every step (as Trainer does, core/trainer.py:617-622,342).
@@ -31,8 +31,8 @@ FLOPS_TRAIN_PER_PAIR = 3 * FLOPS_FWD_PER_PAIR
 
 def b16_config():
     return dict(model_type="chinese_clip", embed_dim=512, image_resolution=224, vision_layers=12, vision_width=768,
-                vision_patch_size=16, vocab_size=21128, text_attention_probs_dropout_prob=0.0, text_hidden_act="gelu",
-                text_hidden_dropout_prob=0.0, text_hidden_size=768, text_initializer_range=0.02, text_intermediate_size=3072,
+                vision_patch_size=16, vocab_size=21128, text_attention_probs_dropout_prob=0.1, text_hidden_act="gelu",
+                text_hidden_dropout_prob=0.1, text_hidden_size=768, text_initializer_range=0.02, text_intermediate_size=3072,
                 text_max_position_embeddings=512, text_num_attention_heads=12, text_num_hidden_layers=12, text_type_vocab_size=2)
 
 
@@ -97,7 +97,7 @@ def oracle_cpu_throughput(batch, seq_len, steps, warmup):
     from oracle import clip_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = b16_config()
+    cfg = b16_config()      # the oracle's dropout is the identity (no RNG work on the CPU arm)
     sd = O.init_state_dict(cfg, seed=1234)
     pixels, ids = O.synthetic_batch(cfg, batch, seq_len=seq_len, seed=1234)
     st = {}
@@ -271,7 +271,7 @@ def run_native(args):
                 "config": {"workload": "CLIP ViT-B/16 + BERT-base contrastive training step (BASELINE configs[1]): fwd + InfoNCE + bwd + clip + AdamW",
                            "per_gpu_batch": B, "global_batch": world * B, "seq_len": Lt, "image": "224x224x3 fp32", "parallelism": f"dp{world}",
                            "loss": "global-batch InfoNCE via embedding all-gather" if dist_on else "local == global batch",
-                           "dropout": 0.0, "l2": "per-step working set (~15 GB of activations) >> 126 MB L2; no explicit flush needed",
+                           "dropout": "text tower hidden 0.1 / attention-probs 0.1 (fused Philox, masks regenerated in backward); ViT tower has none", "l2": "per-step working set (~15 GB of activations) >> 126 MB L2; no explicit flush needed",
                            "init": "random-init weights of the named architecture (no checkpoints reachable)",
                            "launch": "one CUDA graph per step" if use_graph else "eager launches"},
                 "loss": loss_val, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}

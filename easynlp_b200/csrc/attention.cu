@@ -197,7 +197,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 // ====================================================================================================== backward
 // TMEM map (512 columns): [0,256) S -> dP -> dQ(64) ; [256,384) dV key-tiles 0,1 ; [384,512) dK key-tiles 0,1
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+constexpr int ATT_BWD_THREADS = 512;   // 16 warps: TMEM lane quarter (w & 3) x column quarter (w >> 2)
+
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmDO,
                 const AttnParams p) {
   // 1024-B aligned dynamic smem (SWIZZLE_128B atoms); indexing the __shared__ array directly keeps the address space known to
@@ -206,7 +208,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q4 = warp & 3, half = warp >> 2;     // TMEM lane quarter (one thread per row) / column half
+  const int q4 = warp & 3, part = warp >> 2;     // TMEM lane quarter (one thread per row) / column quarter
   const int k_bytes = p.lk_pad * 128;
   const int n_kt = p.lk_pad > 128 ? 2 : 1;       // 128-key tiles of dK / dV
   const int kt_pad = n_kt * 128;
@@ -229,15 +231,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_holder, 512);
-  for (int j = tid; j < 256; j += ATT_THREADS)
+  for (int j = tid; j < 256; j += ATT_BWD_THREADS)
     smask[j] = (j < p.L) ? (p.mask ? p.mask[(long long)b * p.L + j] * LOG2E : 0.f) : -INFINITY;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
   const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16);
-  const int split = ((p.lk_pad >> 1) + 15) & ~15;   // balance the VALID key columns between the two halves
-  const int c_begin = half ? split : 0, c_end = half ? kt_pad : split;
+  // key columns are split between the 4 column quarters at multiples of 16, balancing the VALID keys; the last quarter also
+  // zero-fills [lk_pad, kt_pad)
+  const int c_begin = ((p.lk_pad * part / 4) + 15) & ~15;
+  const int c_end = part == 3 ? kt_pad : min(kt_pad, ((p.lk_pad * (part + 1) / 4) + 15) & ~15);
   const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sPd), aDS = smem_u32(sDS);
   const float sc = p.scale * LOG2E;
   const int ksteps = p.lk_pad >> 4;
@@ -395,13 +399,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(&bars[5], ph);
     tc_fence_after();
     {
-      bf16* dst = p.dqkv + (long long)(b * p.L + q) * (3 * p.d) + h * 64 + half * 32;
-      uint32_t r[32];
-      tmem_ld_x32(t_row + half * 32, r);
+      bf16* dst = p.dqkv + (long long)(b * p.L + q) * (3 * p.d) + h * 64 + part * 16;
+      uint32_t r[16];
+      tmem_ld_x16(t_row + part * 16, r);
       tmem_wait_ld();
       if (qvalid) {
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
+        for (int s4 = 0; s4 < 2; ++s4) {
           uint4 o;
           o.x = pack_bf16x2(__uint_as_float(r[s4 * 8 + 0]), __uint_as_float(r[s4 * 8 + 1]));
           o.y = pack_bf16x2(__uint_as_float(r[s4 * 8 + 2]), __uint_as_float(r[s4 * 8 + 3]));
@@ -416,27 +420,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
   }
 
-  // ---- epilogue: dK, dV rows (one thread per key; column half 0 writes dV, half 1 writes dK)
+  // ---- epilogue: dK, dV rows (one thread per key; quarters 0,1 write the two 32-column halves of dV, quarters 2,3 of dK)
   for (int mt = 0; mt < n_kt; ++mt) {
     const int key = mt * 128 + q4 * 32 + lane;
     const bool kvalid = key < p.L;
-    bf16* dst = p.dqkv + (long long)(b * p.L + key) * (3 * p.d) + (half == 0 ? 2 : 1) * p.d + h * 64;
-    const uint32_t tcol = (half == 0 ? 256 : 384) + mt * 64;
+    const int which = part >> 1, ch = part & 1;
+    bf16* dst = p.dqkv + (long long)(b * p.L + key) * (3 * p.d) + (which == 0 ? 2 : 1) * p.d + h * 64 + ch * 32;
+    const uint32_t tcol = (which == 0 ? 256 : 384) + mt * 64 + ch * 32;
+    uint32_t r[32];
+    tmem_ld_x32(t_row + tcol, r);
+    tmem_wait_ld();
+    if (kvalid) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(t_row + tcol + c * 32, r);
-      tmem_wait_ld();
-      if (kvalid) {
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(r[s4 * 8 + 0]), __uint_as_float(r[s4 * 8 + 1]));
-          o.y = pack_bf16x2(__uint_as_float(r[s4 * 8 + 2]), __uint_as_float(r[s4 * 8 + 3]));
-          o.z = pack_bf16x2(__uint_as_float(r[s4 * 8 + 4]), __uint_as_float(r[s4 * 8 + 5]));
-          o.w = pack_bf16x2(__uint_as_float(r[s4 * 8 + 6]), __uint_as_float(r[s4 * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + c * 32 + s4 * 8) = o;
-        }
+      for (int s4 = 0; s4 < 4; ++s4) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(r[s4 * 8 + 0]), __uint_as_float(r[s4 * 8 + 1]));
+        o.y = pack_bf16x2(__uint_as_float(r[s4 * 8 + 2]), __uint_as_float(r[s4 * 8 + 3]));
+        o.z = pack_bf16x2(__uint_as_float(r[s4 * 8 + 4]), __uint_as_float(r[s4 * 8 + 5]));
+        o.w = pack_bf16x2(__uint_as_float(r[s4 * 8 + 6]), __uint_as_float(r[s4 * 8 + 7]));
+        *reinterpret_cast<uint4*>(dst + s4 * 8) = o;
       }
     }
   }
@@ -509,7 +511,7 @@ extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const
     CLIPK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  attn_bwd_kernel<<<dim3(H, B), ATT_THREADS, smem, stream>>>(tQ, tKV, tDO, p);
+  attn_bwd_kernel<<<dim3(H, B), ATT_BWD_THREADS, smem, stream>>>(tQ, tKV, tDO, p);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

@@ -89,32 +89,33 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 //   dx  = rstd * (g - mean_d(g) - xhat * mean_d(g * xhat))  [+ dx_add]
 //   dgamma += sum_rows (dy+dy_add) * xhat ; dbeta += sum_rows (dy+dy_add) ; dbias += sum_rows dx   (fp32 atomics)
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_is_f32, const float* __restrict__ dy_add,
-                                                            const float* __restrict__ x, long long ldx,
-                                                            const float* __restrict__ gamma, const float* __restrict__ mean_in,
-                                                            const float* __restrict__ rstd_in, const float* __restrict__ dx_add,
-                                                            float* __restrict__ dx_f32, long long lddx, bf16* __restrict__ dx_bf16,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            float* __restrict__ dbias, int rows, int d, const DropArg da,
-                                                            const int drop_mode) {
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_is_f32, const float* __restrict__ dy_add,
+                                                               const float* __restrict__ x, long long ldx,
+                                                               const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                               const float* __restrict__ rstd_in, const float* __restrict__ dx_add,
+                                                               float* __restrict__ dx_f32, long long lddx, bf16* __restrict__ dx_bf16,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                               float* __restrict__ dbias, int rows, int d, const DropArg da,
+                                                               const int drop_mode) {
   // drop_mode 1: forward was LN(x + dropout(t)): the gradient handed to t's producers (dx_bf16, dbias) carries the mask, the
   //              residual path (dx_f32) does not.   drop_mode 2: forward was dropout(LN(x)): the incoming gradient is masked first.
-  __shared__ float red[3][8][32 * 4];  // [which][warp][lane*4]  (per i iteration)
+  // The per-column partial sums (dgamma, dbeta, dbias) live in per-warp shared-memory rows (a lane only ever touches its own
+  // columns, so plain read-modify-write is race-free): registers stay <= 128 and two CTAs fit per SM for latency hiding.
+  extern __shared__ float acc_smem[];            // [nwarp][3][d]
   const DropCtx dc = drop_ctx(da);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarp = blockDim.x >> 5;
-  float4 ag[NV], ab[NV], ad[NV];
+  float* acc = acc_smem + (size_t)warp * 3 * d;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 gm[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) gm[i] = ld_f4(gamma + (lane + 32 * i) * 4);
-
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    st_f4(acc + c, make_float4(0.f, 0.f, 0.f, 0.f)); st_f4(acc + d + c, make_float4(0.f, 0.f, 0.f, 0.f)); st_f4(acc + 2 * d + c, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
   for (int row = blockIdx.x * nwarp + warp; row < rows; row += gridDim.x * nwarp) {
     const float mean = mean_in[row], rstd = rstd_in[row];
     const float* xr = x + (long long)row * ldx;
-    float4 xh[NV], g[NV];
+    float4 xh[NV], dvv[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -125,45 +126,43 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
       if (dy_add) { float4 a = ld_f4(dy_add + (long long)row * d + c); dv.x += a.x; dv.y += a.y; dv.z += a.z; dv.w += a.w; }
       if (dc.on && drop_mode == 2) { const float4 m = drop_mult4(dc, row, lane + 32 * i); dv.x *= m.x; dv.y *= m.y; dv.z *= m.z; dv.w *= m.w; }
       xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd; xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
-      ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
-      ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
-      g[i].x = dv.x * gm[i].x; g[i].y = dv.y * gm[i].y; g[i].z = dv.z * gm[i].z; g[i].w = dv.w * gm[i].w;
-      s1 += g[i].x + g[i].y + g[i].z + g[i].w;
-      s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+      dvv[i] = dv;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float gx = dv.x * gm.x, gy = dv.y * gm.y, gz = dv.z * gm.z, gw = dv.w * gm.w;
+      s1 += gx + gy + gz + gw;
+      s2 += gx * xh[i].x + gy * xh[i].y + gz * xh[i].z + gw * xh[i].w;
     }
     s1 = warp_sum(s1) / d;
     s2 = warp_sum(s2) / d;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + 32 * i) * 4;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 dv = dvv[i];
       float4 o;
-      o.x = rstd * (g[i].x - s1 - xh[i].x * s2);
-      o.y = rstd * (g[i].y - s1 - xh[i].y * s2);
-      o.z = rstd * (g[i].z - s1 - xh[i].z * s2);
-      o.w = rstd * (g[i].w - s1 - xh[i].w * s2);
+      o.x = rstd * (dv.x * gm.x - s1 - xh[i].x * s2);
+      o.y = rstd * (dv.y * gm.y - s1 - xh[i].y * s2);
+      o.z = rstd * (dv.z * gm.z - s1 - xh[i].z * s2);
+      o.w = rstd * (dv.w * gm.w - s1 - xh[i].w * s2);
       if (dx_add) { float4 a = ld_f4(dx_add + (long long)row * d + c); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
       if (dx_f32) st_f4(dx_f32 + (long long)row * lddx + c, o);
       if (dc.on && drop_mode == 1) { const float4 m = drop_mult4(dc, row, lane + 32 * i); o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w; }
-      ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;
       if (dx_bf16) st_bf4(dx_bf16 + (long long)row * d + c, o);
+      float4 a0 = ld_f4(acc + c), a1 = ld_f4(acc + d + c), a2 = ld_f4(acc + 2 * d + c);
+      a0.x += dv.x * xh[i].x; a0.y += dv.y * xh[i].y; a0.z += dv.z * xh[i].z; a0.w += dv.w * xh[i].w;
+      a1.x += dv.x; a1.y += dv.y; a1.z += dv.z; a1.w += dv.w;
+      a2.x += o.x; a2.y += o.y; a2.z += o.z; a2.w += o.w;
+      st_f4(acc + c, a0); st_f4(acc + d + c, a1); st_f4(acc + 2 * d + c, a2);
     }
   }
   // cross-warp reduction of the per-column partials, then one atomic per column per CTA
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    __syncthreads();
-    st_f4(&red[0][warp][lane * 4], ag[i]);
-    st_f4(&red[1][warp][lane * 4], ab[i]);
-    st_f4(&red[2][warp][lane * 4], ad[i]);
-    __syncthreads();
-    for (int t = threadIdx.x; t < 3 * 128; t += blockDim.x) {
-      const int which = t / 128, cc = t % 128;
-      float s = 0.f;
-      for (int w = 0; w < nwarp; ++w) s += red[which][w][cc];
-      const int col = (cc >> 2) * 4 + 128 * i + (cc & 3);  // lane*4 + 128*i + component
-      float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
-      if (dst) atomicAdd(dst + col, s);
-    }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 3 * d; t += blockDim.x) {
+    float sum = 0.f;
+    for (int w = 0; w < nwarp; ++w) sum += acc_smem[(size_t)w * 3 * d + t];
+    const int which = t / d, col = t - which * d;
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+    if (dst) atomicAdd(dst + col, sum);
   }
 }
 
@@ -394,11 +393,17 @@ extern "C" int clipk_layernorm_bwd(const void* dy, int dy_is_f32, const float* d
   if (d % 128 || d > 128 * LN_MAXV || (ldx % 4) || (lddx % 4)) { set_error("layernorm_bwd: d=%d unsupported", d); return CLIPK_ERR_UNSUPPORTED; }
   const int nv = d / 128;
   int g = (rows + 7) / 8;
-  const int cap = sm_count() * 4;
+  const int cap = sm_count() * 8;     // 2 CTAs / SM resident (<= 128 registers), 4 waves of row groups
   if (g > cap) g = cap;
   dim3 grid(g), block(256);
   const DropArg da = make_drop_arg(drop);
-#define LAUNCH(NV) layernorm_bwd_kernel<NV><<<grid, block, 0, stream>>>(dy, dy_is_f32, dy_add, x, ldx, gamma, mean, rstd, dx_add, dx_f32, lddx, (bf16*)dx_bf16, dgamma, dbeta, dbias, rows, d, da, drop_mode)
+  const int smem = 8 * 3 * d * (int)sizeof(float);
+#define LAUNCH(NV)                                                                                                               \
+  {                                                                                                                              \
+    static bool cfg = false;                                                                                                     \
+    if (!cfg) { CLIPK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4)); cfg = true; } \
+    layernorm_bwd_kernel<NV><<<grid, block, smem, stream>>>(dy, dy_is_f32, dy_add, x, ldx, gamma, mean, rstd, dx_add, dx_f32, lddx, (bf16*)dx_bf16, dgamma, dbeta, dbias, rows, d, da, drop_mode); \
+  }
   LN_DISPATCH(nv, LAUNCH)
 #undef LAUNCH
   note_launch();
