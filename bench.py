@@ -149,7 +149,8 @@ def run_native(args):
     d_pixels = pixels.to(dev); d_ids = ids.to(dev)
     lr = 1e-5
 
-    use_graph = not args.no_graph
+    # multi-GPU steps contain NCCL collectives: launched eagerly unless --graph-multi (NCCL capture is left opt-in)
+    use_graph = (not args.no_graph) and (world == 1 or args.graph_multi)
 
     def step(px, tk):
         return eng.train_step(px, tk, lr=lr, weight_decay=1e-4, max_grad_norm=1.0, distributed=dist_on, use_graph=use_graph)["loss"]
@@ -232,10 +233,11 @@ def run_native(args):
     # ---- roofline of the dominant kernel: every GEMM launch of one step timed with events on the launching stream
     peaks, peak_kind = measured_peaks()
     roofline = None
+    # every rank runs the traced step (it contains the collectives); only rank 0 records events
+    ops.TRACE = [] if rank == 0 else None
+    eng.train_step(d_pixels, d_ids, lr=lr, weight_decay=1e-4, max_grad_norm=1.0, distributed=dist_on, use_graph=False)
+    torch.cuda.synchronize(); D.barrier()
     if rank == 0:
-        ops.TRACE = []
-        eng.train_step(d_pixels, d_ids, lr=lr, weight_decay=1e-4, max_grad_norm=1.0, distributed=dist_on, use_graph=False)
-        torch.cuda.synchronize()
         tr = ops.TRACE; ops.TRACE = None
         agg = {}; shapes = {}
         for label, fl, by, s, e in tr:
@@ -290,6 +292,7 @@ def main():
     ap.add_argument("--seq-len", type=int, default=77)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured CUDA graph")
+    ap.add_argument("--graph-multi", action="store_true", help="also capture the step (incl. NCCL collectives) into a CUDA graph when world > 1")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
