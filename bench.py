@@ -256,7 +256,7 @@ def run_native(args):
                     "avg_launch_ms": g[2] / max(1, g[0]),
                     "step_breakdown_ms": {k: round(v[2], 3) for k, v in agg.items()} | {"step_total": round(ms_per_step, 3)},
                     "gemm_shapes_MxNxK|majors|mode": gemm_shapes,
-                    "attention_tflops": {k: (agg[k][1] / (agg[k][2] * 1e-3) / 1e12) for k in agg if k.startswith("attention")},
+                    "attention_tflops": {k: round(agg[k][1] / (agg[k][2] * 1e-3) / 1e12, 1) for k in agg if k.startswith("attention")},
                     "whole_step_frac_of_peak": (B * FLOPS_TRAIN_PER_PAIR / (ms_per_step * 1e-3) / 1e12) / peak}
 
     # ---- CPU baseline: the oracle port on the host cores (rank 0, N = 1 only), bounded sample

@@ -21,7 +21,7 @@ class Dropout(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [("mode", C.c_int), ("out_dtype", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int),
                 ("out2", C.c_void_p), ("ldo2", C.c_int), ("bias", C.c_void_p), ("residual", C.c_void_p),
-                ("ldr", C.c_int), ("aux", C.c_void_p), ("ldaux", C.c_int), ("alpha", C.c_float)]
+                ("ldr", C.c_int), ("aux", C.c_void_p), ("ldaux", C.c_int), ("alpha", C.c_float), ("colsum", C.c_void_p)]
 
 
 _lib = None

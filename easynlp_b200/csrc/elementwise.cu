@@ -168,47 +168,30 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const void* __res
 
 // ------------------------------------------------------------------------------------------------ column sum
 // out[n] += sum_rows x[rows, n]  (bias gradients; also d(pos-embed), d(type-embed)); n % 4 == 0
-// A CTA streams whole row segments: 256 threads x 8 columns = 2048 consecutive columns (4 KB bf16 / 8 KB fp32 per row), rows
-// unrolled 4x for loads in flight -> DRAM sees long sequential bursts instead of 256-B fragments.
 __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x, int is_f32, long long ldx, float* __restrict__ out,
                                                      int rows, int n, int rows_per_cta) {
-  const int c8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (c8 >= n) return;
+  const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c4 >= n) return;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(rows, r0 + rows_per_cta);
-  float a[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = 0.f;
-  auto load8 = [&](int r, float* v) {
-    if (is_f32) {
-      const float* p = reinterpret_cast<const float*>(x) + (long long)r * ldx + c8;
-      const float4 u = ld_f4(p), w = ld_f4(p + 4);
-      v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; v[4] = w.x; v[5] = w.y; v[6] = w.z; v[7] = w.w;
-    } else {
-      const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(x) + (long long)r * ldx + c8);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
-    }
-  };
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   int r = r0;
-  for (; r + 4 <= r1; r += 4) {
-    float v[4][8];
+  // 8 independent row loads in flight per thread: the kernel is pure HBM streaming
+  for (; r + 8 <= r1; r += 8) {
+    float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) load8(r + u, v[u]);
+    for (int u = 0; u < 8; ++u)
+      v[u] = is_f32 ? ld_f4(reinterpret_cast<const float*>(x) + (long long)(r + u) * ldx + c4)
+                    : ld_bf4(reinterpret_cast<const bf16*>(x) + (long long)(r + u) * ldx + c4);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] += v[u][j];
+    for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
   }
   for (; r < r1; ++r) {
-    float v[8];
-    load8(r, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] += v[j];
+    float4 v = is_f32 ? ld_f4(reinterpret_cast<const float*>(x) + (long long)r * ldx + c4)
+                      : ld_bf4(reinterpret_cast<const bf16*>(x) + (long long)r * ldx + c4);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(out + c8 + j, a[j]);
+  atomicAdd(out + c4, a.x); atomicAdd(out + c4 + 1, a.y); atomicAdd(out + c4 + 2, a.z); atomicAdd(out + c4 + 3, a.w);
 }
 
 // ------------------------------------------------------------------------------------------------ patch im2col
@@ -413,9 +396,9 @@ extern "C" int clipk_layernorm_bwd(const void* dy, int dy_is_f32, const float* d
 
 extern "C" int clipk_colsum(const void* x, int is_f32, long long ldx, float* out, int rows, int n, cudaStream_t stream) {
   if (rows <= 0 || n <= 0) return 0;
-  if (n % 8 || ldx % 8) { set_error("colsum: n=%d ldx=%lld must be multiples of 8", n, ldx); return CLIPK_ERR_ARG; }
-  const int bx = (n / 8 + 255) / 256;
-  int by = (sm_count() * 8 + bx - 1) / bx;
+  if (n % 4 || ldx % 4) { set_error("colsum: n=%d ldx=%lld must be multiples of 4", n, ldx); return CLIPK_ERR_ARG; }
+  const int bx = (n / 4 + 255) / 256;
+  int by = (sm_count() * 16 + bx - 1) / bx;
   int rows_per = (rows + by - 1) / by;
   if (rows_per < 32) rows_per = 32;
   by = (rows + rows_per - 1) / rows_per;

@@ -56,7 +56,7 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, const float* slab
     const int rr = 4 * i + sub_r;
     v[i] = *reinterpret_cast<const float4*>(slab + rr * 32 + (((sub_c >> 2) ^ (rr & 7)) << 2));
   }
-  if (!col_ok) return;
+  if (!col_ok) return;      // warp-uniform whenever N % 32 == 0 (required for the colsum shuffles, checked on the host)
   const float al = e.alpha;
   float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
@@ -116,6 +116,19 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, const float* slab
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i].x += r[i].x; v[i].y += r[i].y; v[i].z += r[i].z; v[i].w += r[i].w; }
+  }
+  if (e.colsum) {
+    // column sums of this [32 rows x 32 cols] chunk: 8 rows in registers, then the 4 row groups of the warp (lane bits 3,4)
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (row0 + 4 * i + sub_r < p.M) { cs.x += v[i].x; cs.y += v[i].y; cs.z += v[i].z; cs.w += v[i].w; }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+      cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+    }
+    if (sub_r == 0) atomicAdd(reinterpret_cast<float4*>(e.colsum + col), cs);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -516,6 +529,7 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   if (splits > 1 && epi->mode != CLIPK_EPI_ATOMIC_ADD) { set_error("clipk_gemm_bf16: split-K requires CLIPK_EPI_ATOMIC_ADD"); return CLIPK_ERR_ARG; }
   if (epi->mode == CLIPK_EPI_ATOMIC_ADD && epi->out_dtype != CLIPK_F32) { set_error("clipk_gemm_bf16: atomic epilogue needs fp32 output"); return CLIPK_ERR_ARG; }
   if ((epi->mode == CLIPK_EPI_QUICK_GELU || epi->mode == CLIPK_EPI_ERF_GELU) && !epi->out2) { set_error("clipk_gemm_bf16: GELU epilogue needs out2"); return CLIPK_ERR_ARG; }
+  if (epi->colsum && (N % 32)) { set_error("clipk_gemm_bf16: the fused column sum needs N %% 32 == 0"); return CLIPK_ERR_ARG; }
   if (epi->mode == CLIPK_EPI_MUL_AUX && !epi->aux) { set_error("clipk_gemm_bf16: MUL_AUX epilogue needs aux"); return CLIPK_ERR_ARG; }
   if (epi->mode < 0 || epi->mode > CLIPK_EPI_ATOMIC_ADD) { set_error("clipk_gemm_bf16: unknown epilogue mode %d", epi->mode); return CLIPK_ERR_ARG; }
 

@@ -165,8 +165,8 @@ class ClipEngine:
             # MLP
             ops.gemm(dXb, ly["a"], P_.g(p + "mlp.c_proj.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
                      splits=_splits_for(W, 4 * W, M))
-            ops.gemm(dXb, P_.w(p + "mlp.c_proj.weight"), dz, b_mn_major=1, mode=L.EPI_MUL_AUX, aux=ly["z"])
-            ops.colsum(dz, P_.g(p + "mlp.c_fc.bias"), M, 4 * W)
+            ops.gemm(dXb, P_.w(p + "mlp.c_proj.weight"), dz, b_mn_major=1, mode=L.EPI_MUL_AUX, aux=ly["z"],
+                     colsum=P_.g(p + "mlp.c_fc.bias"))            # dz = (dX W) o act'(z); its column sums = d(c_fc.bias)
             ops.gemm(dz, ly["h2"], P_.g(p + "mlp.c_fc.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
                      splits=_splits_for(4 * W, W, M))
             ops.gemm(dz, P_.w(p + "mlp.c_fc.weight"), dh, b_mn_major=1)
@@ -279,8 +279,8 @@ class ClipEngine:
                               dgamma=P_.g(p + "output.LayerNorm.weight"), dbeta=P_.g(p + "output.LayerNorm.bias"), dbias=P_.g(p + "output.dense.bias"),
                               drop=self._drop(train, self.p_hidden, 16 * (i + 1) + 2), drop_mode=1)
             ops.gemm(ds2b, ly["a"], P_.g(p + "output.dense.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD, splits=_splits_for(H, I, M))
-            ops.gemm(ds2b, P_.w(p + "output.dense.weight"), dz, b_mn_major=1, mode=L.EPI_MUL_AUX, aux=ly["z"])
-            ops.colsum(dz, P_.g(p + "intermediate.dense.bias"), M, I)
+            ops.gemm(ds2b, P_.w(p + "output.dense.weight"), dz, b_mn_major=1, mode=L.EPI_MUL_AUX, aux=ly["z"],
+                     colsum=P_.g(p + "intermediate.dense.bias"))
             ops.gemm(dz, ly["y1b"], P_.g(p + "intermediate.dense.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD, splits=_splits_for(I, H, M))
             ops.gemm(dz, P_.w(p + "intermediate.dense.weight"), dpart, b_mn_major=1)
             ops.layernorm_bwd(dpart, ly["s1"], P_.p(p + "attention.output.LayerNorm.weight"), ly["m1"], ly["r1"], dy_add=ds2, dx_f32=ds1,

@@ -55,7 +55,7 @@ def _stream():
 
 @_op
 def gemm(a, b, out, *, a_mn_major=0, b_mn_major=0, mode=L.EPI_LINEAR, bias=None, residual=None, out2=None, aux=None,
-         alpha=1.0, splits=1):
+         alpha=1.0, splits=1, colsum=None):
     """out[M,N] = epilogue(op(a) @ op(b)^T); see include/clipk.h clipk_gemm_bf16."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
     assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
@@ -87,6 +87,9 @@ def gemm(a, b, out, *, a_mn_major=0, b_mn_major=0, mode=L.EPI_LINEAR, bias=None,
         assert aux.dtype == torch.bfloat16 and aux.shape == (M, N) and aux.stride(1) == 1
         e.aux = aux.data_ptr(); e.ldaux = aux.stride(0)
     e.alpha = alpha
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.numel() == N and colsum.is_contiguous()
+        e.colsum = colsum.data_ptr()
     with _traced(f"gemm|{M}x{N}x{K}|{int(a_mn_major)}{int(b_mn_major)}|m{mode}{'r' if residual is not None else ''}{'f' if out.dtype == torch.float32 else 'b'}", 2.0 * M * N * K):
         L.check(L.lib().clipk_gemm_bf16(_ptr(a), a.stride(0), int(a_mn_major), _ptr(b), b.stride(0), int(b_mn_major),
                                         M, N, K, C.byref(e), int(splits), _stream()), "clipk_gemm_bf16")
@@ -122,7 +125,7 @@ def attention_fwd(qkv, key_mask, ctx, lse, B, L, H, drop=None):
     d = H * 64
     assert qkv.shape == (B * L, 3 * d) and qkv.is_contiguous() and ctx.shape == (B * L, d) and ctx.is_contiguous()
     assert lse.numel() == B * H * L
-    with _traced("attention_fwd", 4.0 * B * H * L * L * 64):
+    with _traced(f"attention_fwd|L{L}", 4.0 * B * H * L * L * 64):
         L_.check(L_.lib().clipk_attention_fwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), B, L, H, d, _dp(drop), _stream()), "attention_fwd")
 
 
@@ -130,7 +133,7 @@ def attention_fwd(qkv, key_mask, ctx, lse, B, L, H, drop=None):
 def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H, drop=None):
     d = H * 64
     assert dqkv.shape == (B * L, 3 * d) and dqkv.is_contiguous() and dctx.shape == (B * L, d) and dctx.is_contiguous()
-    with _traced("attention_bwd", 10.0 * B * H * L * L * 64):
+    with _traced(f"attention_bwd|L{L}", 10.0 * B * H * L * L * 64):
         L_.check(L_.lib().clipk_attention_bwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), _b16(dctx), _b16(dqkv), B, L, H, d,
                                               _dp(drop), _stream()), "attention_bwd")
 

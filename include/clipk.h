@@ -63,6 +63,7 @@ typedef struct {
   const void* aux;       /* bf16 [M, ldaux] multiplier for CLIPK_EPI_MUL_AUX (the saved activation derivative) */
   int ldaux;
   float alpha;           /* 0 is read as 1 */
+  float* colsum;         /* optional f32 [N]: += column sums of the stored output (bias gradient of the producing layer) */
 } clipk_epilogue_t;
 
 /* D[M,N] = epilogue(op(A) x op(B)), bf16 operands, fp32 accumulation in TMEM (tcgen05).

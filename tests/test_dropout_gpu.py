@@ -129,7 +129,9 @@ def test_model_with_dropout_matches_oracle_given_the_same_masks():
     # the eval-mode loss differs clearly from the dropout loss, so agreement below is evidence the masks were applied identically
     ref_eval = O.clip_loss(O.clip_forward(sd, cfg, pixels, ids)["logits_per_text"]).item()
     assert abs(loss.item() - ref_eval) > 5e-3
-    assert abs(out["loss"].item() - loss.item()) < 4e-3 * loss.item(), (out["loss"].item(), loss.item(), ref_eval)
+    # 1 %: 10-pair tiny model (bf16 noise is ~0.3 % here even without dropout); the eval-mode loss is 5 % away
+    assert abs(out["loss"].item() - loss.item()) < 1e-2 * loss.item(), (out["loss"].item(), loss.item(), ref_eval)
+    assert abs(out["loss"].item() - loss.item()) < 0.25 * abs(ref_eval - loss.item())
     assert (out["text_embeds"].cpu() - ref["text_embeds"]).abs().max().item() < 6e-3
     gnorm = math.sqrt(sum(float(g.double().norm()) ** 2 for g in grads if g is not None))
     for k, gr in zip(names, grads):

@@ -75,9 +75,10 @@ def test_gemm_epilogues():
         assert_close(a, y, 1e-2, 1e-2, "act")
         assert_close(g, zz.grad, 1e-2, 1e-2, "act'")
         # backward epilogue: out = acc * aux
-        o = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-        ops.gemm(A, W, o, mode=L.EPI_MUL_AUX, aux=g)
+        o = torch.empty(M, N, device=DEV, dtype=torch.bfloat16); cs = torch.ones(N, device=DEV)
+        ops.gemm(A, W, o, mode=L.EPI_MUL_AUX, aux=g, colsum=cs)
         assert_close(o, acc * g.float(), 2e-2, 3e-2, "mul_aux")
+        assert_close(cs, 1 + (acc * g.float()).sum(0), 1e-3, 5e-2, "fused colsum")
 
 
 # --------------------------------------------------------------------------------------------- attention
