@@ -24,6 +24,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line (rank 0): NCCL's banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 FLOPS_FWD_PER_PAIR = 48_427_376_640          # ViT-B/16 35.13 GF + BERT-base(77) 13.30 GF
 FLOPS_TRAIN_PER_PAIR = 3 * FLOPS_FWD_PER_PAIR
