@@ -222,7 +222,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const DropCtx dc = drop_ctx(p.drop);
   uint8_t* sPd = sP + (dc.on ? ps_bytes : 0);     // dropout: the dV MMA reads the MASKED probabilities from a second tile
   float* smask = reinterpret_cast<float*>(sPd + ps_bytes);        // [256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smask + 256);      // kv, qdo[0], qdo[1], s, dp, dq
+  float* sDp = smask + 256;                                       // [4][128] partial rowsum(dO o O) per column quarter
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDp + 512);        // kv, qdo[0], qdo[1], s, dp, dq
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
 
   if (tid == 0) {
@@ -278,23 +279,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_k(aQ + k * 32), desc_k(aK + k * 32), idesc, k > 0);
       umma_commit(&bars[3]);
     }
-    // D = rowsum(dO o O) and the row's LSE, straight from global memory while the MMA runs
-    float Dq = 0.f, lse2 = 0.f;
-    if (qvalid) {
-      const uint4* po = reinterpret_cast<const uint4*>(p.ctx_in + (long long)(b * p.L + q) * p.d + h * 64);
-      const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + (long long)(b * p.L + q) * p.d + h * 64);
+    // D = rowsum(dO o O): each column quarter takes 16 of the 64 head columns (no redundant global loads), partials meet in shared
+    // memory at the barrier between the two passes; the row's LSE comes straight from global memory while the MMA runs
+    float lse2 = 0.f;
+    {
+      float dpart = 0.f;
+      if (qvalid) {
+        const uint4* po = reinterpret_cast<const uint4*>(p.ctx_in + (long long)(b * p.L + q) * p.d + h * 64 + part * 16);
+        const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + (long long)(b * p.L + q) * p.d + h * 64 + part * 16);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint4 o = po[i], g = pd[i];
-        const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&o);
-        const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&g);
+        for (int i = 0; i < 2; ++i) {
+          uint4 o = po[i], g = pd[i];
+          const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&o);
+          const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&g);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 a = __bfloat1622float2(o2[j]), c = __bfloat1622float2(g2[j]);
-          Dq += a.x * c.x + a.y * c.y;
+          for (int j = 0; j < 4; ++j) {
+            float2 a = __bfloat1622float2(o2[j]), c = __bfloat1622float2(g2[j]);
+            dpart += a.x * c.x + a.y * c.y;
+          }
         }
+        lse2 = p.lse[((long long)b * p.H + h) * p.L + q] * LOG2E;
       }
-      lse2 = p.lse[((long long)b * p.H + h) * p.L + q] * LOG2E;
+      sDp[part * 128 + row] = dpart;
     }
     mbar_wait(&bars[3], ph);
     tc_fence_after();
@@ -346,6 +352,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(&bars[4], ph);
     tc_fence_after();
     // ---- pass 2: dS = scale * P o (dP - D)
+    const float Dq = sDp[row] + sDp[128 + row] + sDp[256 + row] + sDp[384 + row];
     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
       float dv[16];
       if (c0 < p.lk_pad) {
@@ -505,7 +512,7 @@ extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const
   if ((rc = make_tmap_2d_bf16(&tDO, dctx, (uint64_t)d, (uint64_t)B * L, (uint64_t)d, 64, 128))) return rc;
   const int k_bytes = p.lk_pad * 128;
   const int n_kt = p.lk_pad > 128 ? 2 : 1;
-  const int smem = 4 * 16384 + 2 * k_bytes + (n_kt * 2 * 16384) * (p.drop.on ? 2 : 1) + 1024 + 64 + 1024;
+  const int smem = 4 * 16384 + 2 * k_bytes + (n_kt * 2 * 16384) * (p.drop.on ? 2 : 1) + 1024 + 2048 + 64 + 1024;
   static int configured = 0;
   if (configured < smem) {
     CLIPK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

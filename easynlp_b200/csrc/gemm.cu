@@ -47,7 +47,18 @@ struct GemmSmem {
 // step, so every global access is a coalesced 128-B (fp32) / 64-B (bf16) segment.  All global LOADS of the chunk (residual, GELU
 // pre-activation) are issued before any store: `out` may alias `residual`, so the compiler cannot hoist them itself and a
 // load -> store -> load chain would expose one DRAM latency per row group.
-__device__ __forceinline__ void epi_chunk(const GemmParams& p, const float* slab, int row0, int col, int sub_r, int sub_c) {
+// bf16 multiplier tile (MUL_AUX) of one chunk: 8 row groups x 4 columns per lane.  Loaded one chunk AHEAD of its use (and the first chunk
+// before the accumulator is even complete) so the DRAM/L2 latency overlaps the previous chunk / the mainloop.
+__device__ __forceinline__ void epi_load_aux(const GemmParams& p, int row0, int col, int sub_r, uint2* zz) {
+  const clipk_epilogue_t& e = p.epi;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row0 + 4 * i + sub_r;
+    zz[i] = (row < p.M && col < p.N) ? *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(e.aux) + (size_t)row * e.ldaux + col) : make_uint2(0u, 0u);
+  }
+}
+
+__device__ __forceinline__ void epi_chunk(const GemmParams& p, const float* slab, int row0, int col, int sub_r, int sub_c, const uint2* zz) {
   const clipk_epilogue_t& e = p.epi;
   const bool col_ok = col < p.N;
   float4 v[8];
@@ -94,16 +105,11 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, const float* slab
     return;
   }
   if (e.mode == CLIPK_EPI_MUL_AUX) {
-    uint2 zz[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int row = row0 + 4 * i + sub_r;
-      zz[i] = (row < p.M) ? *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(e.aux) + (size_t)row * e.ldaux + col) : make_uint2(0u, 0u);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 z0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&zz[i].x));
-      const float2 z1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&zz[i].y));
+      uint2 z = zz[i];
+      const float2 z0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&z.x));
+      const float2 z1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&z.y));
       v[i].x *= z0.x; v[i].y *= z0.y; v[i].z *= z1.x; v[i].w *= z1.y;
     }
   }
@@ -277,6 +283,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (mn % p.n_tiles) * BN + half * (BN / 2);
       const int k_begin = ks * p.k_per_split;
       const bool has_k = k_begin < p.K;   // an empty split contributes nothing (host never creates one, but be safe)
+      const bool aux_mode = p.epi.mode == CLIPK_EPI_MUL_AUX;
+      uint2 zz[8], zn[8];
+      if (aux_mode) epi_load_aux(p, m0 + q * 32, n0 + sub_c, sub_r, zz);     // in flight while the MMAs of this tile finish
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
@@ -290,10 +299,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(slab + lane * 32 + ((j ^ (lane & 7)) << 2)) =
               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        if (c + 1 < CHUNKS) tmem_ld_x32(t_row + (c + 1) * 32, r);   // next chunk streams in while this one is written out
+        if (c + 1 < CHUNKS) {
+          tmem_ld_x32(t_row + (c + 1) * 32, r);   // next chunk streams in while this one is written out
+          if (aux_mode) epi_load_aux(p, m0 + q * 32, n0 + (c + 1) * 32 + sub_c, sub_r, zn);
+        }
         __syncwarp();
         // phase 2: 8 lanes per row, 4 rows per step -> coalesced global traffic
-        if (has_k) epi_chunk(p, slab, m0 + q * 32, n0 + c * 32 + sub_c, sub_r, sub_c);
+        if (has_k) epi_chunk(p, slab, m0 + q * 32, n0 + c * 32 + sub_c, sub_r, sub_c, zz);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zz[i] = zn[i];
         __syncwarp();
       }
       tc_fence_before();
@@ -466,6 +480,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n0 = (mn % p.n_tiles) * BN2 + half * (BN2 / 2);
       const int k_begin = ks * p.k_per_split;
       const bool has_k = k_begin < p.K;
+      const bool aux_mode = p.epi.mode == CLIPK_EPI_MUL_AUX;
+      uint2 zz[8], zn[8];
+      if (aux_mode) epi_load_aux(p, m0 + q * 32, n0 + sub_c, sub_r, zz);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN2 + half * (BN2 / 2);
@@ -478,9 +495,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(slab + lane * 32 + ((j ^ (lane & 7)) << 2)) =
               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        if (c + 1 < CHUNKS) tmem_ld_x32(t_row + (c + 1) * 32, r);
+        if (c + 1 < CHUNKS) {
+          tmem_ld_x32(t_row + (c + 1) * 32, r);
+          if (aux_mode) epi_load_aux(p, m0 + q * 32, n0 + (c + 1) * 32 + sub_c, sub_r, zn);
+        }
         __syncwarp();
-        if (has_k) epi_chunk(p, slab, m0 + q * 32, n0 + c * 32 + sub_c, sub_r, sub_c);
+        if (has_k) epi_chunk(p, slab, m0 + q * 32, n0 + c * 32 + sub_c, sub_r, sub_c, zz);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zz[i] = zn[i];
         __syncwarp();
       }
       tc_fence_before();
