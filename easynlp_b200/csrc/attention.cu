@@ -454,6 +454,182 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// ------------------------------------------------------------------------------------------------------ backward, L <= 128
+// One 128-query tile and one 128-key tile per (batch, head): the whole chain is latency bound, so this variant (a) needs only 256
+// TMEM columns and ~110 KB of shared memory so that TWO CTAs share an SM and overlap each other's waits, and (b) computes S and dP
+// side by side so that P and dS come out of ONE pass over the accumulators (no second TMEM sweep, no P re-read, 3 instead of 6
+// block-wide syncs).  TMEM map (256 columns): [0,128) S -> dQ(64) | dK(64) ; [128,256) dP -> dV(64).
+// 256 threads: TMEM lane quarter (w & 3) = one thread per query / key row, column half (w >> 2).
+constexpr int ATT_BWD_SMALL_THREADS = 256;
+
+__global__ void __launch_bounds__(ATT_BWD_SMALL_THREADS, 2)
+attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmDO,
+                      const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, half = warp >> 2;
+  const int k_bytes = p.lk_pad * 128;
+  uint8_t* sQ = smem;
+  uint8_t* sDO = smem + 16384;
+  uint8_t* sK = smem + 32768;
+  uint8_t* sV = sK + k_bytes;
+  uint8_t* sP = sV;                               // (masked) probabilities, over V once dP = dO V^T has completed
+  uint8_t* sDS = sP + 32768;
+  float* smask = reinterpret_cast<float*>(sDS + 32768);            // [128]
+  float* sDp = smask + 128;                                        // [2][128] partial rowsum(dO o O) per column half
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDp + 256);         // loads, s/dp, grads
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+  const DropCtx dc = drop_ctx(p.drop);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmDO);
+    for (int i = 0; i < 3; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_holder, 256);
+  if (tid < 128) smask[tid] = (tid < p.L) ? (p.mask ? p.mask[(long long)b * p.L + tid] * LOG2E : 0.f) : -INFINITY;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16);
+  const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sDS);
+  const float sc = p.scale * LOG2E;
+  const int ksteps = p.lk_pad >> 4;
+  const int row = q4 * 32 + lane;
+  const bool qvalid = row < p.L;
+  const uint32_t drow = (uint32_t)((b * p.H + h) * p.L + row);
+
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], 2 * k_bytes + 2 * 16384);
+    tma_load_2d(sK, &tmKV, &bars[0], p.d + h * 64, b * p.L);
+    tma_load_2d(sV, &tmKV, &bars[0], 2 * p.d + h * 64, b * p.L);
+    tma_load_2d(sQ, &tmQ, &bars[0], h * 64, b * p.L);
+    tma_load_2d(sDO, &tmDO, &bars[0], h * 64, b * p.L);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, p.lk_pad, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_k(aQ + k * 32), desc_k(aK + k * 32), idesc, k > 0);            // S = Q K^T
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem + 128, desc_k(aDO + k * 32), desc_k(aV + k * 32), idesc, k > 0);     // dP = dO V^T
+    umma_commit(&bars[1]);
+  }
+  // D = rowsum(dO o O): each column half takes 32 of the 64 head columns; the loads overlap the TMA + MMA latency
+  float lse2 = 0.f;
+  {
+    float dpart = 0.f;
+    if (qvalid) {
+      const uint4* po = reinterpret_cast<const uint4*>(p.ctx_in + (long long)(b * p.L + row) * p.d + h * 64 + half * 32);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + (long long)(b * p.L + row) * p.d + h * 64 + half * 32);
+      uint4 o[4], g[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { o[i] = po[i]; g[i] = pd[i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&o[i]);
+        const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&g[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 a = __bfloat1622float2(o2[j]), c = __bfloat1622float2(g2[j]);
+          dpart += a.x * c.x + a.y * c.y;
+        }
+      }
+      lse2 = p.lse[((long long)b * p.H + h) * p.L + row] * LOG2E;
+    }
+    sDp[half * 128 + row] = dpart;
+  }
+  __syncthreads();
+  const float Dq = sDp[row] + sDp[128 + row];
+  // key columns split between the two halves at a multiple of 16; the upper half also zero-fills [lk_pad, 128)
+  const int split = min(p.lk_pad, ((p.lk_pad >> 1) + 15) & ~15);
+  const int c_begin = half ? split : 0;
+  const int c_end = half ? 128 : split;
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  // ---- single pass: P = exp(S - lse) [o mask], dS = scale * P o (dP [o mask] - D)
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    float pv[16], dv[16];
+    if (c0 < p.lk_pad) {
+      uint32_t rs[16], rp[16];
+      tmem_ld_x16(t_row + c0, rs);
+      tmem_ld_x16(t_row + 128 + c0, rp);
+      float m[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(m + 4 * j) = *reinterpret_cast<const float4*>(smask + c0 + 4 * j);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pv[j] = qvalid ? exp2f(fmaf(__uint_as_float(rs[j]), sc, m[j] - lse2)) : 0.f;
+      if (dc.on) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 mm = drop_mult4(dc, drow, (c0 >> 2) + j4);
+          const float mk[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int j = 4 * j4 + t;
+            dv[j] = p.scale * pv[j] * (__uint_as_float(rp[j]) * mk[t] - Dq);     // dP = dP~ o mask
+            pv[j] *= mk[t];                                                       // P~ = P o mask feeds dV = P~^T dO
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dv[j] = p.scale * pv[j] * (__uint_as_float(rp[j]) - Dq);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { pv[j] = 0.f; dv[j] = 0.f; }
+    }
+    store_row8_sw128(sP, row, c0, pv);
+    store_row8_sw128(sP, row, c0 + 8, pv + 8);
+    store_row8_sw128(sDS, row, c0, dv);
+    store_row8_sw128(sDS, row, c0 + 8, dv + 8);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  // ---- dQ = dS K -> [0,64) ; dK = dS^T Q -> [64,128) ; dV = P~^T dO -> [128,192)
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);
+    for (int t = 0; t < ksteps; ++t)
+      umma_bf16(tmem, desc_k(aDS + (t >> 2) * 16384 + (t & 3) * 32), desc_mn(aK + t * 2048, 16384), idesc_dq, t > 0);
+    const uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) umma_bf16(tmem + 64, desc_mn(aDS + ks * 2048, 16384), desc_mn(aQ + ks * 2048, 16384), idesc_t, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) umma_bf16(tmem + 128, desc_mn(aP + ks * 2048, 16384), desc_mn(aDO + ks * 2048, 16384), idesc_t, ks > 0);
+    umma_commit(&bars[2]);
+  }
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  {   // rows are queries for dQ and keys for dK / dV; both ranges are [0, L).  tcgen05.ld is warp-collective: no divergence around it
+    bf16* dst = p.dqkv + (long long)(b * p.L + row) * (3 * p.d) + h * 64 + half * 32;
+#pragma unroll 1
+    for (int w = 0; w < 3; ++w) {
+      uint32_t r[32];
+      tmem_ld_x32(t_row + w * 64 + half * 32, r);
+      tmem_wait_ld();
+      if (qvalid) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(r[s4 * 8 + 0]), __uint_as_float(r[s4 * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(r[s4 * 8 + 2]), __uint_as_float(r[s4 * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(r[s4 * 8 + 4]), __uint_as_float(r[s4 * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(r[s4 * 8 + 6]), __uint_as_float(r[s4 * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + w * p.d + s4 * 8) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
 static int check_shapes(const char* who, int B, int L, int H, int d) {
   if (B <= 0 || L <= 0 || H <= 0 || d != H * 64) { set_error("%s: need d == 64*H (B=%d L=%d H=%d d=%d)", who, B, L, H, d); return CLIPK_ERR_ARG; }
   if (L > 256) { set_error("%s: sequence length %d > 256 is not supported by the one-shot kernel yet", who, L); return CLIPK_ERR_UNSUPPORTED; }
@@ -505,6 +681,22 @@ extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const
   p.mask = key_mask; p.lse = const_cast<float*>(lse);
   p.ctx_in = (const bf16*)ctx; p.dctx = (const bf16*)dctx; p.dqkv = (bf16*)dqkv;
   p.drop = make_drop_arg(drop);
+  if (L <= 128) {
+    CUtensorMap tQ, tKV, tDO;
+    if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, p.lk_pad))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tDO, dctx, (uint64_t)d, (uint64_t)B * L, (uint64_t)d, 64, 128))) return rc;
+    const int smem = 32768 + p.lk_pad * 128 + 65536 + 512 + 1024 + 64;
+    static int configured_small = 0;
+    if (configured_small < smem) {
+      CLIPK_CUDA(cudaFuncSetAttribute(attn_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured_small = smem;
+    }
+    attn_bwd_small_kernel<<<dim3(H, B), ATT_BWD_SMALL_THREADS, smem, stream>>>(tQ, tKV, tDO, p);
+    note_launch();
+    CLIPK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (p.drop.on && L > 128) { set_error("attention_bwd: attention dropout is implemented for L <= 128 (the text tower)"); return CLIPK_ERR_UNSUPPORTED; }
   CUtensorMap tQ, tKV, tDO;
   if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;

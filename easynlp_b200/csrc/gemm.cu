@@ -15,6 +15,7 @@
 // in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   warp 0: TMA producer   warp 1: MMA issuer + TMEM owner   warps 2-5: epilogue (TMEM -> registers -> global)
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "../../include/clipk.h"
 
@@ -34,11 +35,13 @@ struct GemmParams {
 
 template <int BN>
 struct GemmSmem {
+  static constexpr int NSTAGE = STAGES;
+  static constexpr int EPI_WARP_BYTES = 32 * 32 * 4;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;          // per epilogue warp: [32 rows x 32 floats] XOR-swizzled transpose staging
-  static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;
+  static constexpr int EPI_OFFSET = NSTAGE * STAGE_BYTES;          // per epilogue warp: staging (fp32 transpose slab / bf16 store tiles)
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
 };
@@ -169,17 +172,156 @@ __device__ __forceinline__ void epi_prefetch(const GemmParams& p, int tile, int 
   }
 }
 
-template <int BN, int A_MN, int B_MN>
+
+// column sums over the 32 rows (lanes) of a chunk held as 32 column values per lane: butterfly transpose-reduce, lane j ends with column j
+__device__ __forceinline__ float colsum32(const float* v, int lane) {
+  float w[16];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { const float send = up ? v[k] : v[k + 16]; const float keep = up ? v[k + 16] : v[k]; w[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+  }
+#pragma unroll
+  for (int h = 8; h >= 1; h >>= 1) {
+    const bool up = lane & h;
+#pragma unroll
+    for (int k = 0; k < h; ++k) { const float send = up ? w[k] : w[k + h]; const float keep = up ? w[k + h] : w[k]; w[k] = keep + __shfl_xor_sync(0xffffffffu, send, h); }
+  }
+  return w[0];
+}
+
+// bf16 multiplier row segment (MUL_AUX) for one lane = one accumulator row: 32 consecutive columns = 64 B
+__device__ __forceinline__ void epi_load_aux_row(const GemmParams& p, int row, int col, uint4* z) {
+  const clipk_epilogue_t& e = p.epi;
+  if (row < p.M && col < p.N) {
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.aux) + (size_t)row * e.ldaux + col);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = src[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// Epilogue of one warp's [32 rows x BN/2 cols] slice for bf16 outputs WITHOUT a residual input: the math runs directly on the
+// tcgen05.ld register layout (lane = row, 32 consecutive columns per chunk), the packed bf16 chunk goes to a 64B-swizzled
+// 32 x 32 staging tile (conflict-free STS.128) and ONE thread hands it to the TMA store unit, which also clips at the matrix edge.
+// Compared with the transpose-through-smem path this removes the LDS pass, the per-row address arithmetic and all global store
+// instructions from the warp.  MODE is a template parameter and the chunk loop is NOT unrolled: the fully unrolled runtime-mode
+// version was 7.4 k SASS instructions and stalled on instruction fetch (profiles/r01_gemm_epilogue_tma.md).
+// stage: NBUF x 2 KB per warp; seq: running count of committed bulk groups of this warp (GELU commits a pair of tiles per group).
+template <int BN, int NBUF, int MODE>
+__device__ __forceinline__ void epi_tile_tma(const GemmParams& p, const CUtensorMap* tmO, const CUtensorMap* tmO2, uint8_t* stage, uint32_t& seq,
+                                             uint64_t* full_bar, uint32_t full_phase, uint32_t t_row, int row0, int col0, int lane, bool has_k) {
+  constexpr int CHUNKS = BN / 64;
+  constexpr bool GELU = MODE == CLIPK_EPI_QUICK_GELU || MODE == CLIPK_EPI_ERF_GELU;
+  constexpr bool AUX = MODE == CLIPK_EPI_MUL_AUX;
+  const clipk_epilogue_t& e = p.epi;
+  const int row = row0 + lane;
+  const float al = e.alpha;
+  uint4 zc[4], zn[4];
+  uint32_t r[32];
+  if (AUX) epi_load_aux_row(p, row, col0, zc);              // in flight while the MMAs of this tile finish
+  mbar_wait(full_bar, full_phase);
+  tc_fence_after();
+  tmem_ld_x32(t_row, r);
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll 1
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col = col0 + c * 32;
+    const bool live = has_k && col < p.N;                   // warp-uniform (N % 32 == 0 on this path)
+    float4 b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = (e.bias && live) ? __ldg(reinterpret_cast<const float4*>(e.bias + col) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    tmem_wait_ld();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j] = fmaf(__uint_as_float(r[4 * j]), al, b[j].x); v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), al, b[j].y);
+      v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), al, b[j].z); v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), al, b[j].w);
+    }
+    if (c + 1 < CHUNKS) {
+      tmem_ld_x32(t_row + (c + 1) * 32, r);                 // next chunk streams in while this one is processed
+      if (AUX) epi_load_aux_row(p, row, col + 32, zn);
+    }
+    if (live) {
+      uint32_t o[16], o2[16];
+      if (GELU) {
+        // out2 = act(z) (the next GEMM's operand); out = act'(z), saved INSTEAD of z so that the backward epilogue is a plain multiply
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a0, a1, g0, g1;
+          if (MODE == CLIPK_EPI_QUICK_GELU) { quick_gelu_both(v[2 * j], a0, g0); quick_gelu_both(v[2 * j + 1], a1, g1); }
+          else                              { erf_gelu_both(v[2 * j], a0, g0);   erf_gelu_both(v[2 * j + 1], a1, g1); }
+          o[j] = pack_bf16x2(g0, g1); o2[j] = pack_bf16x2(a0, a1);
+        }
+      } else {
+        if (AUX) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t zw[4] = {zc[j].x, zc[j].y, zc[j].z, zc[j].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              v[8 * j + 2 * t] *= __uint_as_float(zw[t] << 16);             // bf16 -> fp32 is a shift / mask
+              v[8 * j + 2 * t + 1] *= __uint_as_float(zw[t] & 0xffff0000u);
+            }
+          }
+        }
+        if (e.colsum) {
+          if (row >= p.M) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          const float cs = colsum32(v, lane);
+          atomicAdd(e.colsum + col + lane, cs);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      }
+      uint8_t* bufO = stage + (GELU ? (seq % (NBUF / 2)) * 4096u : (seq % NBUF) * 2048u);
+      uint8_t* bufA = bufO + 2048;
+      if (lane == 0) { if (GELU) tma_store_wait_read<NBUF / 2 - 1>(); else tma_store_wait_read<NBUF - 1>(); }   // the tile(s) written now are released
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t off = (uint32_t)lane * 64u + ((((uint32_t)j) ^ sw) << 4);
+        *reinterpret_cast<uint4*>(bufO + off) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        if (GELU) *reinterpret_cast<uint4*>(bufA + off) = make_uint4(o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmO, bufO, col, row0);
+        if (GELU) tma_store_2d(tmO2, bufA, col, row0);
+        tma_store_commit();
+      }
+      ++seq;
+    }
+    if (AUX) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) zc[j] = zn[j];
+    }
+  }
+}
+
+// EPI: 0 = transpose-through-smem epilogue (any output type), 1 = TMA-store epilogue, 4-stage ring + 2 staging tiles per warp,
+//      2 = TMA-store epilogue, 3-stage ring + 8 staging tiles per warp
+template <int BN, int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                 const __grid_constant__ CUtensorMap tmO2, const GemmParams p) {
+  constexpr bool TMA_OUT = EPI != 0;
+  constexpr int NSTAGE = STAGES;
+  constexpr int NBUF = 2;                         // 2 KB bf16 store tiles per epilogue warp (EPI == 0: one 4 KB fp32 slab)
+  constexpr int MODE = EPI == 0 ? 0 : EPI - 1;
   using L = GemmSmem<BN>;
   // 1024-B aligned dynamic smem (SWIZZLE_128B atoms); indexing the __shared__ array directly keeps the address space known to
   // the compiler (LDS/STS instead of generic LD/ST)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + NSTAGE;
+  uint64_t* tmem_full = empty_bar + NSTAGE;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -191,7 +333,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
     fence_mbar_init();
   }
@@ -229,7 +371,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else {
             tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -260,7 +402,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             accumulate = 1;
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);      // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -272,6 +414,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = (warp - 2) >> 2;
     constexpr int CHUNKS = BN / 32 / 2;        // 32-column chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t store_seq = 0;
     float* slab = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + (warp - 2) * 32 * 32;
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
     if ((int)blockIdx.x < num_tiles) epi_prefetch<BN>(p, blockIdx.x, tiles_mn, q, half, lane);
@@ -283,6 +426,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (mn % p.n_tiles) * BN + half * (BN / 2);
       const int k_begin = ks * p.k_per_split;
       const bool has_k = k_begin < p.K;   // an empty split contributes nothing (host never creates one, but be safe)
+      if constexpr (TMA_OUT) {
+        epi_tile_tma<BN, NBUF, MODE>(p, &tmO, &tmO2, smem + L::EPI_OFFSET + (warp - 2) * (NBUF * 2048), store_seq, &tmem_full[acc], acc_phase,
+                         tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2), m0 + q * 32, n0, lane, has_k);
+      } else {
       const bool aux_mode = p.epi.mode == CLIPK_EPI_MUL_AUX;
       uint2 zz[8], zn[8];
       if (aux_mode) epi_load_aux(p, m0 + q * 32, n0 + sub_c, sub_r, zz);     // in flight while the MMAs of this tile finish
@@ -310,11 +457,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < 8; ++i) zz[i] = zn[i];
         __syncwarp();
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (TMA_OUT && lane == 0) tma_store_wait_read<0>();   // staging tiles must outlive the bulk stores reading them
   }
 
   tc_fence_before();
@@ -325,9 +474,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int A_MN, int B_MN>
-static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+template <int BN, int A_MN, int B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tO, const CUtensorMap& tO2, const GemmParams& p,
+                       cudaStream_t stream) {
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
   static bool configured = false;
   const int smem = GemmSmem<BN>::TOTAL;
   if (!configured) {
@@ -336,7 +486,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
   }
   const int tiles = p.m_tiles * p.n_tiles * p.splits;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(tA, tB, p);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(tA, tB, tO, tO2, p);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;
@@ -590,14 +740,49 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     return launch_gemm2<0, 0>(tA, tB, p, stream);
   }
 
-#define CLIPK_DISPATCH(BN_)                                                          \
-  if (a_mn_major) {                                                                  \
-    if (b_mn_major) return launch_gemm<BN_, 1, 1>(tA, tB, p, stream);                \
-    return launch_gemm<BN_, 1, 0>(tA, tB, p, stream);                                \
-  } else {                                                                           \
-    if (b_mn_major) return launch_gemm<BN_, 0, 1>(tA, tB, p, stream);                \
-    return launch_gemm<BN_, 0, 0>(tA, tB, p, stream);                                \
+  // bf16 results without a residual input leave through the TMA store unit (epi_tile_tma); fp32 / atomic / residual epilogues keep the
+  // transpose-through-smem path (CLIPK_GEMM_NO_TMA_OUT=1 forces it everywhere, for A/B measurements)
+  const clipk_epilogue_t& ee = p.epi;
+  const bool gelu = ee.mode == CLIPK_EPI_QUICK_GELU || ee.mode == CLIPK_EPI_ERF_GELU;
+  static int no_tma_out = -1;
+  if (no_tma_out < 0) { const char* ev = getenv("CLIPK_GEMM_NO_TMA_OUT"); no_tma_out = (ev && ev[0] == '1') ? 1 : 0; }
+  const bool tma_out = !no_tma_out && ee.out_dtype == CLIPK_BF16 && !ee.residual && ee.mode != CLIPK_EPI_ATOMIC_ADD && ee.mode != CLIPK_EPI_RESERVED4 &&
+                       (gelu ? ee.out2 != nullptr : ee.out2 == nullptr) && (N % 32 == 0) && (ee.ldo % 8 == 0) &&
+                       !(reinterpret_cast<uintptr_t>(ee.out) & 15) && (!gelu || (ee.ldo2 % 8 == 0 && !(reinterpret_cast<uintptr_t>(ee.out2) & 15))) &&
+                       (ee.mode != CLIPK_EPI_MUL_AUX || (ee.ldaux % 8 == 0 && !(reinterpret_cast<uintptr_t>(ee.aux) & 15))) &&
+                       (!ee.bias || !(reinterpret_cast<uintptr_t>(ee.bias) & 15));
+  const int variant = (tma_out && !a_mn_major) ? 1 : 0;   // 0 = transpose-through-smem epilogue, 1 = TMA-store epilogue
+  CUtensorMap tO = tA, tO2 = tA;
+  if (variant) {
+    rc = make_tmap_2d_bf16(&tO, ee.out, (uint64_t)N, (uint64_t)M, (uint64_t)ee.ldo, 32, 32, 64);
+    if (rc) return rc;
+    if (gelu) { rc = make_tmap_2d_bf16(&tO2, ee.out2, (uint64_t)N, (uint64_t)M, (uint64_t)ee.ldo2, 32, 32, 64); if (rc) return rc; }
   }
-  if (BN == 256) { CLIPK_DISPATCH(256) } else { CLIPK_DISPATCH(128) }
+  if (variant == 0) {
+#define CLIPK_DISPATCH(BN_)                                                          \
+    if (a_mn_major) {                                                                \
+      if (b_mn_major) return launch_gemm<BN_, 1, 1, 0>(tA, tB, tO, tO2, p, stream);  \
+      return launch_gemm<BN_, 1, 0, 0>(tA, tB, tO, tO2, p, stream);                  \
+    } else {                                                                         \
+      if (b_mn_major) return launch_gemm<BN_, 0, 1, 0>(tA, tB, tO, tO2, p, stream);  \
+      return launch_gemm<BN_, 0, 0, 0>(tA, tB, tO, tO2, p, stream);                  \
+    }
+    if (BN == 256) { CLIPK_DISPATCH(256) } else { CLIPK_DISPATCH(128) }
 #undef CLIPK_DISPATCH
+  }
+  const int epi_id = 1 + ee.mode;   // ee.mode in 0..3 on this path
+#define CLIPK_DISPATCH_E(BN_, E_)                                                    \
+  case E_:                                                                           \
+    if (b_mn_major) return launch_gemm<BN_, 0, 1, E_>(tA, tB, tO, tO2, p, stream);   \
+    return launch_gemm<BN_, 0, 0, E_>(tA, tB, tO, tO2, p, stream);
+#define CLIPK_DISPATCH_BN(BN_)                                                       \
+  switch (epi_id) {                                                                  \
+    CLIPK_DISPATCH_E(BN_, 1) CLIPK_DISPATCH_E(BN_, 2) CLIPK_DISPATCH_E(BN_, 3) CLIPK_DISPATCH_E(BN_, 4)      \
+    default: break;                                                                  \
+  }
+  if (BN == 256) { CLIPK_DISPATCH_BN(256) } else { CLIPK_DISPATCH_BN(128) }
+  set_error("clipk_gemm_bf16: internal dispatch error (epilogue id %d)", epi_id);
+  return CLIPK_ERR_ARG;
+#undef CLIPK_DISPATCH_E
+#undef CLIPK_DISPATCH_BN
 }

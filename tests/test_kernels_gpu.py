@@ -41,6 +41,34 @@ def test_gemm_variants(M, N, K, a_mn, b_mn):
     assert_close(out, ref, 1e-3, 1e-3 * math.sqrt(K), "gemm")
 
 
+@pytest.mark.parametrize("M,N,K", [(394, 96, 128), (100, 288, 64), (1000, 768, 192)])
+def test_gemm_bf16_store_path_slices_and_edges(M, N, K):
+    """bf16 results leave through the TMA store unit: ragged M (clipped boxes), N below / across the tile width, and an output
+    that is a column slice of a wider buffer (ldo > N) whose surroundings must stay untouched."""
+    A = rnd(M, K, seed=21).bfloat16(); W = rnd(N, K, seed=22, scale=0.2).bfloat16(); bias = rnd(N, seed=23)
+    acc = A.float() @ W.float().t() + bias
+    wide = torch.full((M + 3, N + 128), 7.0, device=DEV, dtype=torch.bfloat16)
+    out = wide[1:M + 1, 64:64 + N]
+    ops.gemm(A, W, out, bias=bias)
+    assert_close(out, acc, 1e-2, 2e-2, "slice")
+    chk = wide.clone(); chk[1:M + 1, 64:64 + N] = 7.0
+    assert torch.all(chk == 7.0)
+    # GELU pair + multiply-by-saved-derivative with the fused column sum, same slices
+    g = torch.full_like(wide, 5.0); a = torch.full_like(wide, 3.0)
+    gs, as_ = g[1:M + 1, 64:64 + N], a[1:M + 1, 64:64 + N]
+    ops.gemm(A, W, gs, bias=bias, mode=L.EPI_QUICK_GELU, out2=as_)
+    sg = torch.sigmoid(1.702 * acc)
+    assert_close(as_, acc * sg, 1e-2, 1e-2, "act")
+    assert_close(gs, sg * (1 + 1.702 * acc * (1 - sg)), 1e-2, 1e-2, "act'")
+    g2 = g.clone(); g2[1:M + 1, 64:64 + N] = 5.0
+    assert torch.all(g2 == 5.0)
+    o = torch.empty(M, N, device=DEV, dtype=torch.bfloat16); cs = torch.zeros(N, device=DEV)
+    ops.gemm(A, W, o, mode=L.EPI_MUL_AUX, aux=gs, colsum=cs)
+    want = (A.float() @ W.float().t()) * gs.float()
+    assert_close(o, want, 2e-2, 3e-2, "mul_aux")
+    assert_close(cs, want.sum(0), 1e-3, 5e-2, "fused colsum")
+
+
 def test_gemm_splitk_accumulates():
     M, N, K = 768, 3072, 1576
     A = rnd(M, K, seed=3).bfloat16(); B = rnd(N, K, seed=4).bfloat16()
