@@ -46,7 +46,7 @@ def _declare(L):
     L.clipk_gemm_bf16.argtypes = [vp, i, i, vp, i, i, i, i, i, C.POINTER(Epilogue), i, vp]
     dp = C.POINTER(Dropout)
     L.clipk_attention_fwd.argtypes = [vp, vp, vp, vp, i, i, i, i, dp, vp]
-    L.clipk_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, dp, vp]
+    L.clipk_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, dp, vp]
     L.clipk_dropout_mask.argtypes = [vp, i, i, dp, vp]
     L.clipk_layernorm_fwd.argtypes = [vp, ll, vp, ll, vp, vp, vp, f, vp, vp, vp, vp, i, i, dp, i, vp]
     L.clipk_layernorm_bwd.argtypes = [vp, i, vp, vp, ll, vp, vp, vp, vp, vp, ll, vp, vp, vp, vp, i, i, dp, i, vp]
@@ -60,6 +60,9 @@ def _declare(L):
     L.clipk_l2norm_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, vp]
     L.clipk_cast_bf16.argtypes = [vp, vp, ll, vp]
     L.clipk_axpy.argtypes = [vp, vp, f, ll, vp]
+    L.clipk_split_bf16x3.argtypes = [vp, vp, i, i, i, ll, vp]
+    L.clipk_ce_rows_fwd.argtypes = [vp, ll, vp, i, vp, vp, i, i, vp]
+    L.clipk_ce_rows_bwd.argtypes = [vp, ll, vp, vp, i, f, vp, ll, vp, i, i, vp]
     L.clipk_ce_strip_fwd.argtypes = [vp, vp, vp, i, vp, ll, i, vp, vp, i, i, i, vp]
     L.clipk_ce_strip_bwd.argtypes = [vp, vp, vp, vp, i, f, i, vp, i, vp, i, i, i, vp]
     L.clipk_reduce_sum.argtypes = [vp, i, f, vp, i, vp]

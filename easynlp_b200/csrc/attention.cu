@@ -31,6 +31,7 @@ struct AttnParams {
   const bf16* ctx_in;  // bwd in
   const bf16* dctx;    // bwd in  [B*L, d]
   bf16* dqkv;          // bwd out [B*L, 3d]
+  float* dqkv_colsum;  // bwd out (optional) [3d] += column sums of dqkv = gradient of the QKV projection bias
   DropArg drop;        // dropout on the attention probabilities (modeling_bert.py:238); element (b,h,q,j): row = (b*H+h)*L+q, quad = j/4
 };
 
@@ -223,7 +224,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sPd = sP + (dc.on ? ps_bytes : 0);     // dropout: the dV MMA reads the MASKED probabilities from a second tile
   float* smask = reinterpret_cast<float*>(sPd + ps_bytes);        // [256]
   float* sDp = smask + 256;                                       // [4][128] partial rowsum(dO o O) per column quarter
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDp + 512);        // kv, qdo[0], qdo[1], s, dp, dq
+  float* scol = sDp + 512;                                        // [3][64] column sums of this head's dQ | dK | dV
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scol + 192);       // kv, qdo[0], qdo[1], s, dp, dq
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
 
   if (tid == 0) {
@@ -234,6 +236,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0) tmem_alloc(tmem_holder, 512);
   for (int j = tid; j < 256; j += ATT_BWD_THREADS)
     smask[j] = (j < p.L) ? (p.mask ? p.mask[(long long)b * p.L + j] * LOG2E : 0.f) : -INFINITY;
+  if (tid < 192) scol[tid] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -410,6 +413,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t r[16];
       tmem_ld_x16(t_row + part * 16, r);
       tmem_wait_ld();
+      if (p.dqkv_colsum) {    // rows of invalid queries are exactly zero (their dS rows are)
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        const float cs = colsum16(v, lane);
+        if (!(lane & 1)) atomicAdd(&scol[part * 16 + (lane >> 1)], cs);
+      }
       if (qvalid) {
 #pragma unroll
         for (int s4 = 0; s4 < 2; ++s4) {
@@ -437,6 +447,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t r[32];
     tmem_ld_x32(t_row + tcol, r);
     tmem_wait_ld();
+    if (p.dqkv_colsum) {      // rows of invalid / padded keys are exactly zero (their P and dS columns are)
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      const float cs = colsum32(v, lane);
+      atomicAdd(&scol[(which == 0 ? 128 : 64) + ch * 32 + lane], cs);
+    }
     if (kvalid) {
 #pragma unroll
       for (int s4 = 0; s4 < 4; ++s4) {
@@ -451,6 +468,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dqkv_colsum && tid < 192) atomicAdd(p.dqkv_colsum + (tid >> 6) * p.d + h * 64 + (tid & 63), scol[tid]);
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
@@ -479,7 +497,8 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint8_t* sDS = sP + 32768;
   float* smask = reinterpret_cast<float*>(sDS + 32768);            // [128]
   float* sDp = smask + 128;                                        // [2][128] partial rowsum(dO o O) per column half
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDp + 256);         // loads, s/dp, grads
+  float* scol = sDp + 256;                                         // [3][64] column sums of this head's dQ | dK | dV
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scol + 192);        // loads, s/dp, grads
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
   const DropCtx dc = drop_ctx(p.drop);
 
@@ -490,6 +509,7 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
   if (warp == 0) tmem_alloc(tmem_holder, 256);
   if (tid < 128) smask[tid] = (tid < p.L) ? (p.mask ? p.mask[(long long)b * p.L + tid] * LOG2E : 0.f) : -INFINITY;
+  if (tid < 192) scol[tid] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -612,6 +632,13 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       uint32_t r[32];
       tmem_ld_x32(t_row + w * 64 + half * 32, r);
       tmem_wait_ld();
+      if (p.dqkv_colsum) {    // invalid query / key rows are exactly zero
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const float cs = colsum32(v, lane);
+        atomicAdd(&scol[w * 64 + half * 32 + lane], cs);
+      }
       if (qvalid) {
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) {
@@ -627,6 +654,7 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dqkv_colsum && tid < 192) atomicAdd(p.dqkv_colsum + (tid >> 6) * p.d + h * 64 + (tid & 63), scol[tid]);
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
@@ -670,7 +698,7 @@ extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void*
 }
 
 extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
-                                   int B, int L, int H, int d, const clipk_dropout_t* drop, cudaStream_t stream) {
+                                   float* dqkv_colsum, int B, int L, int H, int d, const clipk_dropout_t* drop, cudaStream_t stream) {
   int rc = check_shapes("attention_bwd", B, L, H, d);
   if (rc) return rc;
   AttnParams p{};
@@ -679,14 +707,14 @@ extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const
   p.q_tiles = (L + 127) / 128;
   p.scale = 0.125f;
   p.mask = key_mask; p.lse = const_cast<float*>(lse);
-  p.ctx_in = (const bf16*)ctx; p.dctx = (const bf16*)dctx; p.dqkv = (bf16*)dqkv;
+  p.ctx_in = (const bf16*)ctx; p.dctx = (const bf16*)dctx; p.dqkv = (bf16*)dqkv; p.dqkv_colsum = dqkv_colsum;
   p.drop = make_drop_arg(drop);
   if (L <= 128) {
     CUtensorMap tQ, tKV, tDO;
     if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;
     if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, p.lk_pad))) return rc;
     if ((rc = make_tmap_2d_bf16(&tDO, dctx, (uint64_t)d, (uint64_t)B * L, (uint64_t)d, 64, 128))) return rc;
-    const int smem = 32768 + p.lk_pad * 128 + 65536 + 512 + 1024 + 64;
+    const int smem = 32768 + p.lk_pad * 128 + 65536 + 512 + 1024 + 768 + 64;
     static int configured_small = 0;
     if (configured_small < smem) {
       CLIPK_CUDA(cudaFuncSetAttribute(attn_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -704,7 +732,7 @@ extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const
   if ((rc = make_tmap_2d_bf16(&tDO, dctx, (uint64_t)d, (uint64_t)B * L, (uint64_t)d, 64, 128))) return rc;
   const int k_bytes = p.lk_pad * 128;
   const int n_kt = p.lk_pad > 128 ? 2 : 1;
-  const int smem = 4 * 16384 + 2 * k_bytes + (n_kt * 2 * 16384) * (p.drop.on ? 2 : 1) + 1024 + 2048 + 64 + 1024;
+  const int smem = 4 * 16384 + 2 * k_bytes + (n_kt * 2 * 16384) * (p.drop.on ? 2 : 1) + 1024 + 2048 + 768 + 64 + 1024;
   static int configured = 0;
   if (configured < smem) {
     CLIPK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -303,6 +303,40 @@ __device__ __forceinline__ void erf_gelu_both(float x, float& act, float& grad) 
   act = x * cdf;
   grad = fmaf(x * 0.39894228040143268f, ex, cdf);
 }
+// column sums over the 32 rows (lanes) of a chunk held as 32 column values per lane: butterfly transpose-reduce, lane j ends with column j
+__device__ __forceinline__ float colsum32(const float* v, int lane) {
+  float w[16];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { const float send = up ? v[k] : v[k + 16]; const float keep = up ? v[k + 16] : v[k]; w[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+  }
+#pragma unroll
+  for (int h = 8; h >= 1; h >>= 1) {
+    const bool up = lane & h;
+#pragma unroll
+    for (int k = 0; k < h; ++k) { const float send = up ? w[k] : w[k + h]; const float keep = up ? w[k + h] : w[k]; w[k] = keep + __shfl_xor_sync(0xffffffffu, send, h); }
+  }
+  return w[0];
+}
+
+// the same for 16 column values per lane: lanes 2j and 2j+1 both end with column j
+__device__ __forceinline__ float colsum16(const float* v, int lane) {
+  float w[8];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float send = up ? v[k] : v[k + 8]; const float keep = up ? v[k + 8] : v[k]; w[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+  }
+#pragma unroll
+  for (int h = 4; h >= 1; h >>= 1) {
+    const bool up = lane & (2 * h);
+#pragma unroll
+    for (int k = 0; k < h; ++k) { const float send = up ? w[k] : w[k + h]; const float keep = up ? w[k + h] : w[k]; w[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * h); }
+  }
+  return w[0] + __shfl_xor_sync(0xffffffffu, w[0], 1);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

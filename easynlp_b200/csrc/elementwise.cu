@@ -1,6 +1,7 @@
 // HBM-bound kernels of the CLIP towers: LayerNorm fwd/bwd, patch im2col, ViT token assembly, BERT embedding
 // gather/scatter, column sums (bias grads), L2 normalisation.  One warp owns one row; a lane owns the float4
 // column groups {lane + 32 i}, so per-column reductions over rows (dgamma, dbeta, dbias) stay in registers.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/clipk.h"
 
@@ -117,6 +118,13 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const void* __res
     const float* xr = x + (long long)row * ldx;
     float4 xh[NV], dvv[NV];
     float s1 = 0.f, s2 = 0.f;
+    // the residual gradient added to dx is only needed after the row reduction; fetching it into L1 now keeps its DRAM round trip
+    // off the critical path without holding registers (the kernel is latency bound: ncu long_scoreboard.  Measured +6 % GB/s;
+    // loading it into registers here instead spills at 128 registers and gains nothing)
+    if (dx_add) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(dx_add + (long long)row * d + (lane + 32 * i) * 4));
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + 32 * i) * 4;
@@ -376,7 +384,11 @@ extern "C" int clipk_layernorm_bwd(const void* dy, int dy_is_f32, const float* d
   if (d % 128 || d > 128 * LN_MAXV || (ldx % 4) || (lddx % 4)) { set_error("layernorm_bwd: d=%d unsupported", d); return CLIPK_ERR_UNSUPPORTED; }
   const int nv = d / 128;
   int g = (rows + 7) / 8;
-  const int cap = sm_count() * 8;     // 2 CTAs / SM resident (<= 128 registers), 4 waves of row groups
+  // 2 CTAs / SM resident (<= 128 registers).  One wave by default: every CTA pays a fixed cost (zeroing / reducing its 72 KB of
+  // column partials, 3d atomics), so fewer, longer-lived CTAs win over finer load balancing (CLIPK_LN_BWD_WAVES for A/B runs)
+  static int waves = -1;
+  if (waves < 0) { const char* ev = getenv("CLIPK_LN_BWD_WAVES"); waves = ev ? atoi(ev) : 1; if (waves < 1) waves = 1; }
+  const int cap = sm_count() * 2 * waves;
   if (g > cap) g = cap;
   dim3 grid(g), block(256);
   const DropArg da = make_drop_arg(drop);

@@ -173,23 +173,6 @@ __device__ __forceinline__ void epi_prefetch(const GemmParams& p, int tile, int 
 }
 
 
-// column sums over the 32 rows (lanes) of a chunk held as 32 column values per lane: butterfly transpose-reduce, lane j ends with column j
-__device__ __forceinline__ float colsum32(const float* v, int lane) {
-  float w[16];
-  {
-    const bool up = lane & 16;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { const float send = up ? v[k] : v[k + 16]; const float keep = up ? v[k + 16] : v[k]; w[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
-  }
-#pragma unroll
-  for (int h = 8; h >= 1; h >>= 1) {
-    const bool up = lane & h;
-#pragma unroll
-    for (int k = 0; k < h; ++k) { const float send = up ? w[k] : w[k + h]; const float keep = up ? w[k + h] : w[k]; w[k] = keep + __shfl_xor_sync(0xffffffffu, send, h); }
-  }
-  return w[0];
-}
-
 // bf16 multiplier row segment (MUL_AUX) for one lane = one accumulator row: 32 consecutive columns = 64 B
 __device__ __forceinline__ void epi_load_aux_row(const GemmParams& p, int row, int col, uint4* z) {
   const clipk_epilogue_t& e = p.epi;

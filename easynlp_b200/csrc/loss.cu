@@ -226,6 +226,87 @@ static inline int ce_warps_for(int n_rows) {
   return 8;
 }
 
+
+// ====================================================================================================== tensor-core path
+// The strip kernels above stream the gallery through CUDA cores with 32 query rows per CTA: at B_local = 256 that is 8 CTAs on 148
+// SMs, and their time grows with the GLOBAL batch.  The training step therefore takes the logits from the tcgen05 GEMM instead,
+// without giving up fp32-level logits: each fp32 embedding is split x = hi + lo (two bf16) and
+//     <q, k>  ~=  <q_hi, k_hi> + <q_hi, k_lo> + <q_lo, k_hi>          (error ~2^-17 relative, the lo*lo term)
+// is ONE GEMM with K = 3E over the concatenations  Qs = [q_hi | q_hi | q_lo],  Ks = [k_hi | k_lo | k_hi].  The row kernels below
+// turn the raw dots into scaled logits + log-sum-exp + per-row loss, and into the bf16 dS operand of the two gradient GEMMs
+// (dOwn = dS Ks_hi, dGallery = dS^T Qs_hi; bf16 like every other backward operand).
+__global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ x, bf16* __restrict__ out, int rows, int cols, int pattern,
+                                                           long long ld_out) {
+  const long long n4 = (long long)rows * (cols / 4);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / (cols / 4)), c = (int)(t % (cols / 4)) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + (long long)r * cols + c);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    float hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { hi[j] = __bfloat162float(__float2bfloat16_rn(f[j])); lo[j] = f[j] - hi[j]; }
+    uint2 h, l;
+    h.x = pack_bf16x2(hi[0], hi[1]); h.y = pack_bf16x2(hi[2], hi[3]);
+    l.x = pack_bf16x2(lo[0], lo[1]); l.y = pack_bf16x2(lo[2], lo[3]);
+    bf16* o = out + (long long)r * ld_out + c;
+    *reinterpret_cast<uint2*>(o) = h;                                   // pattern 0: [hi | hi | lo]   pattern 1: [hi | lo | hi]
+    *reinterpret_cast<uint2*>(o + cols) = pattern ? l : h;
+    *reinterpret_cast<uint2*>(o + 2 * cols) = pattern ? h : l;
+  }
+}
+
+// one warp per row: S (raw dots) -> scaled logits in place, lse, loss_rows = lse - logit[label]
+__global__ void __launch_bounds__(256) ce_rows_fwd_kernel(float* __restrict__ S, long long lds, const float* __restrict__ logit_scale_log,
+                                                          int label_offset, float* __restrict__ lse_out, float* __restrict__ loss_rows, int nq,
+                                                          int nk) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= nq) return;
+  const float scale = __expf(*logit_scale_log);
+  float* s = S + (long long)row * lds;
+  float mx = -INFINITY;
+  for (int j = lane; j < nk; j += 32) { const float v = s[j] * scale; s[j] = v; mx = fmaxf(mx, v); }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < nk; j += 32) sum += __expf(s[j] - mx);     // own writes: same lane, same addresses
+  sum = warp_sum(sum);
+  if (lane == 0) {
+    const float lse = mx + __logf(sum);
+    const int lab = label_offset + row;
+    lse_out[row] = lse;
+    loss_rows[row] = lse - ((lab >= 0 && lab < nk) ? s[lab] : 0.f);
+  }
+}
+
+// one warp per row: dS' = scale * coef * (exp(s - lse) - [j == label]) as bf16 (columns [nk, ldds) zero-filled);
+// dscale_log += sum_j coef * (p - onehot) * s
+__global__ void __launch_bounds__(256) ce_rows_bwd_kernel(const float* __restrict__ S, long long lds, const float* __restrict__ logit_scale_log,
+                                                          const float* __restrict__ lse, int label_offset, float coef, bf16* __restrict__ dS,
+                                                          long long ldds, float* __restrict__ dscale_log, int nq, int nk) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= nq) return;
+  const float scale = __expf(*logit_scale_log);
+  const float* s = S + (long long)row * lds;
+  bf16* o = dS + (long long)row * ldds;
+  const float l = lse[row];
+  const int lab = label_offset + row;
+  float acc = 0.f;
+  for (int j = lane; j < (int)ldds; j += 32) {
+    float g = 0.f;
+    if (j < nk) {
+      const float v = s[j];
+      g = coef * (__expf(v - l) - (j == lab ? 1.f : 0.f));
+      acc += g * v;
+    }
+    o[j] = __float2bfloat16_rn(g * scale);
+  }
+  if (dscale_log) {
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(dscale_log, acc);
+  }
+}
+
 }  // namespace clipk
 
 using namespace clipk;
@@ -303,6 +384,37 @@ extern "C" int clipk_retrieval_rank(const float* Q, const float* K, int label_of
   }
   CE_DISPATCH(nv, LAUNCH)
 #undef LAUNCH
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_split_bf16x3(const float* x, void* out_bf16, int rows, int cols, int pattern, long long ld_out, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if ((cols % 4) || (ld_out % 4) || ld_out < 3LL * cols) { set_error("split_bf16x3: cols=%d ld_out=%lld unsupported", cols, ld_out); return CLIPK_ERR_ARG; }
+  const long long n4 = (long long)rows * (cols / 4);
+  long long g = (n4 + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  split_bf16x3_kernel<<<(int)g, 256, 0, stream>>>(x, (bf16*)out_bf16, rows, cols, pattern ? 1 : 0, ld_out);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_ce_rows_fwd(float* S, long long lds, const float* logit_scale_log, int label_offset, float* lse, float* loss_rows, int nq,
+                                 int nk, cudaStream_t stream) {
+  if (nq <= 0 || nk <= 0) return 0;
+  ce_rows_fwd_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(S, lds, logit_scale_log, label_offset, lse, loss_rows, nq, nk);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_ce_rows_bwd(const float* S, long long lds, const float* logit_scale_log, const float* lse, int label_offset, float coef,
+                                 void* dS_bf16, long long ldds, float* dscale_log, int nq, int nk, cudaStream_t stream) {
+  if (nq <= 0 || nk <= 0) return 0;
+  if (ldds < nk) { set_error("ce_rows_bwd: ldds=%lld < nk=%d", ldds, nk); return CLIPK_ERR_ARG; }
+  ce_rows_bwd_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(S, lds, logit_scale_log, lse, label_offset, coef, (bf16*)dS_bf16, ldds, dscale_log, nq, nk);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

@@ -72,6 +72,15 @@ class ClipEngine:
             self._buf[key] = t
         return t
 
+    def zbuf(self, name, shape, dtype):
+        """like buf, but zero-filled when first created (for operands whose padding rows must stay zero)"""
+        key = (name, tuple(shape), dtype)
+        t = self._buf.get(key)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=self.dev)
+            self._buf[key] = t
+        return t
+
     def bf(self, name, *shape):
         return self.buf(name, shape, torch.bfloat16)
 
@@ -177,8 +186,7 @@ class ClipEngine:
             ops.gemm(dX1b, ly["ctx"], P_.g(p + "attn.out_proj.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
                      splits=_splits_for(W, W, M))
             ops.gemm(dX1b, P_.w(p + "attn.out_proj.weight"), dctx, b_mn_major=1)
-            ops.attention_bwd(ly["qkv"], None, ly["ctx"], ly["lse"], dctx, dqkv, B, Lv, Hh)
-            ops.colsum(dqkv, P_.g(p + "attn.in_proj_bias"), M, 3 * W)
+            ops.attention_bwd(ly["qkv"], None, ly["ctx"], ly["lse"], dctx, dqkv, B, Lv, Hh, dqkv_colsum=P_.g(p + "attn.in_proj_bias"))
             ops.gemm(dqkv, ly["h"], P_.g(p + "attn.in_proj_weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
                      splits=_splits_for(3 * W, W, M))
             ops.gemm(dqkv, P_.w(p + "attn.in_proj_weight"), dh, b_mn_major=1)
@@ -290,8 +298,8 @@ class ClipEngine:
             ops.gemm(ds1b, ly["ctx"], P_.g(p + "attention.output.dense.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
                      splits=_splits_for(H, H, M))
             ops.gemm(ds1b, P_.w(p + "attention.output.dense.weight"), dctx, b_mn_major=1)
-            ops.attention_bwd(ly["qkv"], st["mask"], ly["ctx"], ly["lse"], dctx, dqkv, B, Lt, Hh, drop=self._drop(train, self.p_attn, 16 * (i + 1)))
-            ops.colsum(dqkv, P_.g(p + "attention.self.query.bias", (3 * H,)), M, 3 * H)
+            ops.attention_bwd(ly["qkv"], st["mask"], ly["ctx"], ly["lse"], dctx, dqkv, B, Lt, Hh, drop=self._drop(train, self.p_attn, 16 * (i + 1)),
+                              dqkv_colsum=P_.g(p + "attention.self.query.bias", (3 * H,)))   # query|key|value biases are adjacent (params.py)
             ops.gemm(dqkv, ly["xb_in"], P_.g(p + "attention.self.query.weight", (3 * H, H)), a_mn_major=1, b_mn_major=1,
                      mode=L.EPI_ATOMIC_ADD, splits=_splits_for(3 * H, H, M))
             ops.gemm(dqkv, P_.w(p + "attention.self.query.weight", (3 * H, H)), dxp, b_mn_major=1)
@@ -308,41 +316,54 @@ class ClipEngine:
 
     # ------------------------------------------------------------------ contrastive head
     def loss_forward(self, text_embeds, image_embeds, gallery_image=None, gallery_text=None, label_offset=0, want_logits=True):
-        """Two CE strips: local texts vs the image gallery, local images vs the text gallery.  With no gallery given the
-        local batch is the gallery (world size 1: identical to the reference's [B,B] loss)."""
+        """Two CE strips: local texts vs the image gallery, local images vs the text gallery (appzoo/clip/model.py:148-164).  With no
+        gallery given the local batch is the gallery (world size 1: identical to the reference's [B,B] loss).
+        The dots come from the tcgen05 GEMM on bf16 hi/lo splits of the fp32 embeddings (K = 3E, fp32-level logits; loss.cu)."""
         gi = image_embeds if gallery_image is None else gallery_image
         gt = text_embeds if gallery_text is None else gallery_text
-        B = text_embeds.shape[0]; G = gi.shape[0]
+        B = text_embeds.shape[0]; G = gi.shape[0]; E = self.E
+        Gp = (G + 7) // 8 * 8                                   # GEMM N / leading dimensions are multiples of 8; padding rows stay zero
         ls = self.params.p("logit_scale")
-        st = {"T": text_embeds, "I": image_embeds, "GI": gi, "GT": gt, "off": label_offset, "G": G}
+        Ts = self.bf("l.Ts", B, 3 * E); Is = self.bf("l.Is", B, 3 * E)
+        GIs = self.zbuf("l.GIs", (Gp, 3 * E), torch.bfloat16); GTs = self.zbuf("l.GTs", (Gp, 3 * E), torch.bfloat16)
+        ops.split_bf16x3(text_embeds, Ts, 0); ops.split_bf16x3(image_embeds, Is, 0)
+        ops.split_bf16x3(gi, GIs, 1); ops.split_bf16x3(gt, GTs, 1)
+        S_t = self.f32("l.S_t", B, Gp); S_i = self.f32("l.S_i", B, Gp)
+        ops.gemm(Ts, GIs, S_t); ops.gemm(Is, GTs, S_i)
+        st = {"T": text_embeds, "I": image_embeds, "off": label_offset, "G": G, "Gp": Gp, "Ts": Ts, "Is": Is, "GIs": GIs, "GTs": GTs,
+              "S_t": S_t, "S_i": S_i}
         st["lse_t"] = self.f32("l.lse_t", B); st["lse_i"] = self.f32("l.lse_i", B)
         rows_t = self.f32("l.rows_t", B); rows_i = self.f32("l.rows_i", B)
-        logits = self.f32("l.logits", B, G) if want_logits else None
-        ops.ce_strip_fwd(text_embeds, gi, ls, label_offset, st["lse_t"], rows_t, S_out=logits, lds=G)
-        ops.ce_strip_fwd(image_embeds, gt, ls, label_offset, st["lse_i"], rows_i)
+        ops.ce_rows_fwd(S_t, ls, label_offset, st["lse_t"], rows_t, B, G)     # S_* now hold the scaled logits
+        ops.ce_rows_fwd(S_i, ls, label_offset, st["lse_i"], rows_i, B, G)
         st["loss_sum"] = self.f32("l.loss", 1)       # sum over LOCAL rows of both directions / (2 G)
         ops.reduce_sum(rows_t, B, 1.0 / (2 * G), st["loss_sum"], False)
         ops.reduce_sum(rows_i, B, 1.0 / (2 * G), st["loss_sum"], True)
-        st["logits"] = logits
+        st["logits"] = S_t[:, :G] if want_logits else None
         return st
 
     def loss_backward(self, st, grad_scale: float = 1.0, local_gallery: bool = True):
         """d(grad_scale * loss) w.r.t. the local embeddings.  With local_gallery (world size 1) the gallery IS the local batch and
         its gradient accumulates straight onto dI / dT; otherwise the gallery gradients (all G rows) are returned separately so
         the distributed wrapper can reduce-scatter them to their owners."""
-        B = st["T"].shape[0]; G = st["G"]; E = self.E
+        B = st["T"].shape[0]; G = st["G"]; Gp = st["Gp"]; E = self.E
         coef = grad_scale / (2.0 * G)
         ls = self.params.p("logit_scale"); dls = self.params.g("logit_scale").view(1)
+        dS_t = self.bf("l.dS_t", B, Gp); dS_i = self.bf("l.dS_i", B, Gp)
+        ops.ce_rows_bwd(st["S_t"], ls, st["lse_t"], st["off"], coef, dS_t, B, G, dscale_log=dls)
+        ops.ce_rows_bwd(st["S_i"], ls, st["lse_i"], st["off"], coef, dS_i, B, G, dscale_log=dls)
+        hi = lambda t: t[:, :E]                                  # the bf16 "hi" block of a split operand
         dT = self.f32("l.dT", B, E); dI = self.f32("l.dI", B, E)
-        ops.ce_strip_bwd(st["T"], st["GI"], ls, st["lse_t"], st["off"], coef, True, dT, False, dls)
-        ops.ce_strip_bwd(st["I"], st["GT"], ls, st["lse_i"], st["off"], coef, True, dI, False, dls)
+        ops.gemm(dS_t, hi(st["GIs"]), dT, b_mn_major=1)          # own rows as queries: dT = dS_t GI, dI = dS_i GT
+        ops.gemm(dS_i, hi(st["GTs"]), dI, b_mn_major=1)
         if local_gallery:
-            ops.ce_strip_bwd(st["GI"], st["T"], ls, st["lse_t"], st["off"], coef, False, dI, True)
-            ops.ce_strip_bwd(st["GT"], st["I"], ls, st["lse_i"], st["off"], coef, False, dT, True)
+            # gallery rows: dGI = dS_t^T T (+= onto dI), dGT = dS_i^T I (+= onto dT)
+            ops.gemm(dS_t[:, :G], hi(st["Ts"]), dI, a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
+            ops.gemm(dS_i[:, :G], hi(st["Is"]), dT, a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
             return dT, dI, None, None
         dGI = self.f32("l.dGI", G, E); dGT = self.f32("l.dGT", G, E)
-        ops.ce_strip_bwd(st["GI"], st["T"], ls, st["lse_t"], st["off"], coef, False, dGI, False)
-        ops.ce_strip_bwd(st["GT"], st["I"], ls, st["lse_i"], st["off"], coef, False, dGT, False)
+        ops.gemm(dS_t[:, :G], hi(st["Ts"]), dGI, a_mn_major=1, b_mn_major=1)
+        ops.gemm(dS_i[:, :G], hi(st["Is"]), dGT, a_mn_major=1, b_mn_major=1)
         return dT, dI, dGI, dGT
 
     # ------------------------------------------------------------------ public steps

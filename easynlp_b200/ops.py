@@ -130,12 +130,14 @@ def attention_fwd(qkv, key_mask, ctx, lse, B, L, H, drop=None):
 
 
 @_op
-def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H, drop=None):
+def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H, drop=None, dqkv_colsum=None):
+    """dqkv_colsum: optional f32 [3d], += column sums of dqkv (the QKV projection's bias gradient), fused into the kernel"""
     d = H * 64
     assert dqkv.shape == (B * L, 3 * d) and dqkv.is_contiguous() and dctx.shape == (B * L, d) and dctx.is_contiguous()
+    assert dqkv_colsum is None or (dqkv_colsum.numel() == 3 * d and dqkv_colsum.is_contiguous())
     with _traced(f"attention_bwd|L{L}", 10.0 * B * H * L * L * 64):
-        L_.check(L_.lib().clipk_attention_bwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), _b16(dctx), _b16(dqkv), B, L, H, d,
-                                              _dp(drop), _stream()), "attention_bwd")
+        L_.check(L_.lib().clipk_attention_bwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), _b16(dctx), _b16(dqkv), _f32(dqkv_colsum),
+                                              B, L, H, d, _dp(drop), _stream()), "attention_bwd")
 
 
 @_op
@@ -230,6 +232,28 @@ def ce_strip_bwd(own, streamed, logit_scale_log, lse, label_offset, coef, own_is
     L_.check(L_.lib().clipk_ce_strip_bwd(_f32(own), _f32(streamed), _f32(logit_scale_log), _f32(lse), label_offset, coef,
                                          int(own_is_query), _f32(out), int(accumulate), _f32(dscale_log), n_own,
                                          streamed.shape[0], E, _stream()), "ce_strip_bwd")
+
+
+@_op
+def split_bf16x3(x, out, pattern):
+    """x f32 [rows, E] -> out bf16 [rows(+pad), 3E]: [hi|hi|lo] (pattern 0, query side) or [hi|lo|hi] (pattern 1, gallery side)"""
+    rows, E = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.shape[1] == 3 * E and out.shape[0] >= rows
+    L_.check(L_.lib().clipk_split_bf16x3(_f32(x), _b16(out), rows, E, int(pattern), out.stride(0), _stream()), "split_bf16x3")
+
+
+@_op
+def ce_rows_fwd(S, logit_scale_log, label_offset, lse, loss_rows, nq, nk):
+    assert S.dtype == torch.float32 and S.stride(1) == 1
+    L_.check(L_.lib().clipk_ce_rows_fwd(_f32(S), S.stride(0), _f32(logit_scale_log), label_offset, _f32(lse), _f32(loss_rows), nq, nk,
+                                        _stream()), "ce_rows_fwd")
+
+
+@_op
+def ce_rows_bwd(S, logit_scale_log, lse, label_offset, coef, dS, nq, nk, dscale_log=None):
+    assert S.dtype == torch.float32 and S.stride(1) == 1 and dS.dtype == torch.bfloat16 and dS.stride(1) == 1
+    L_.check(L_.lib().clipk_ce_rows_bwd(_f32(S), S.stride(0), _f32(logit_scale_log), _f32(lse), label_offset, coef, _b16(dS), dS.stride(0),
+                                        _f32(dscale_log), nq, nk, _stream()), "ce_rows_bwd")
 
 
 @_op

@@ -96,10 +96,12 @@ int clipk_dropout_mask(float* out, int rows, int cols, const clipk_dropout_t* dr
 int clipk_attention_fwd(const void* qkv, const float* key_mask, void* ctx, float* lse, int B, int L, int H, int d,
                         const clipk_dropout_t* drop /* optional: dropout on the probabilities, row = (b*H+h)*L+q, col = key */,
                         cudaStream_t stream);
-/* dqkv[B*L, 3d] (bf16) from dctx[B*L, d] (bf16); ctx / lse are the forward outputs.                             */
+/* dqkv[B*L, 3d] (bf16) from dctx[B*L, d] (bf16); ctx / lse are the forward outputs.
+ * dqkv_colsum: optional f32 [3d], += column sums of dqkv taken on the fp32 accumulators = the gradient of the fused
+ * query/key/value projection bias (in_proj_bias, modeling_chineseclip.py:188; query/key/value.bias, modeling_bert.py:145-147). */
 int clipk_attention_bwd(const void* qkv, const float* key_mask, const void* ctx, const float* lse, const void* dctx,
-                        void* dqkv, int B, int L, int H, int d, const clipk_dropout_t* drop /* same as forward; L <= 128 */,
-                        cudaStream_t stream);
+                        void* dqkv, float* dqkv_colsum, int B, int L, int H, int d,
+                        const clipk_dropout_t* drop /* same as forward; L <= 128 */, cudaStream_t stream);
 
 /* -------------------------------------------------------------------------------------------- LayerNorm
  * y = (x - mean) * rstd * gamma + beta over the last dim d (d % 128 == 0, d <= 1024), fp32 statistics
@@ -160,6 +162,17 @@ int clipk_ce_strip_fwd(const float* Q, const float* K, const float* logit_scale_
 int clipk_ce_strip_bwd(const float* own, const float* streamed, const float* logit_scale_log, const float* lse,
                        int label_offset, float coef, int own_is_query, float* out, int accumulate, float* dscale_log,
                        int n_own, int n_streamed, int E, cudaStream_t stream);
+/* Tensor-core form of the same strips (what the training step uses: the strip kernels above occupy nq/32 CTAs and their time
+ * grows with the GLOBAL batch).  fp32 rows are split into bf16 hi + lo and concatenated so that ONE clipk_gemm_bf16 with K = 3E
+ * gives <q,k> ~= <qh,kh> + <qh,kl> + <ql,kh> (fp32-level logits): pattern 0 = [hi|hi|lo] (query side), 1 = [hi|lo|hi] (gallery). */
+int clipk_split_bf16x3(const float* x, void* out_bf16, int rows, int cols, int pattern, long long ld_out, cudaStream_t stream);
+/* S[nq, nk] (ld lds): raw dots in, scaled logits exp(logit_scale_log) * S out (in place); lse[i]; loss_rows[i] = lse_i - S[i,label] */
+int clipk_ce_rows_fwd(float* S, long long lds, const float* logit_scale_log, int label_offset, float* lse, float* loss_rows,
+                      int nq, int nk, cudaStream_t stream);
+/* dS[nq, ldds] (bf16, columns >= nk zero-filled) = exp(logit_scale_log) * coef * (exp(S - lse) - onehot(label)) from the scaled
+ * logits: the A operand of dOwn = dS * gallery_hi and (MN-major) of dGallery = dS^T * own_hi;  dscale_log += sum coef (p - 1hot) S */
+int clipk_ce_rows_bwd(const float* S, long long lds, const float* logit_scale_log, const float* lse, int label_offset, float coef,
+                      void* dS_bf16, long long ldds, float* dscale_log, int nq, int nk, cudaStream_t stream);
 int clipk_reduce_sum(const float* x, int n, float scale, float* out, int accumulate, cudaStream_t stream);
 /* Retrieval: rank_out[i] = #{gallery j : <Q_i,K_j> > <Q_i,K_label(i)>} (int32); hit@K <=> rank < K.  Replaces
  * CLIPEvaluator's N x N matrix + per-row torch.sort (appzoo/clip/evaluator.py:47-61).                          */

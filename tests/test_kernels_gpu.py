@@ -139,10 +139,13 @@ def test_attention_fwd_bwd(B, L, H, masked):
     dctx = rnd(B * L, d, seed=12).bfloat16()
     o_ref.backward(dctx.float())
     dqkv = torch.zeros(B * L, 3 * d, device=DEV, dtype=torch.bfloat16)
-    ops.attention_bwd(qkv, mask, ctx, lse, dctx, dqkv, B, L, H)
+    dbias = torch.full((3 * d,), 0.5, device=DEV)                        # accumulated into (+=), like every gradient buffer
+    ops.attention_bwd(qkv, mask, ctx, lse, dctx, dqkv, B, L, H, dqkv_colsum=dbias)
     ref = qf.grad
     scale = ref.abs().max().item()
     assert_close(dqkv, ref, 3e-2, 2e-2 * scale, "dqkv")
+    cref = ref.sum(0)
+    assert_close(dbias - 0.5, cref, 1e-2, 5e-3 * cref.abs().max().item() + 1e-3 * scale * math.sqrt(B * L), "fused QKV bias gradient")
 
 
 # --------------------------------------------------------------------------------------------- LayerNorm
@@ -268,6 +271,43 @@ def test_ce_strip(nq, nk, E, off):
     tot = torch.zeros(1, device=DEV)
     ops.reduce_sum(rows, nq, 0.5, tot)
     assert_close(tot, per.sum().view(1) * 0.5, 1e-5, 1e-5, "reduce")
+
+
+@pytest.mark.parametrize("nq,nk,E,off,scale", [(8, 8, 512, 0, 1 / 0.07), (50, 200, 128, 100, 1 / 0.07), (256, 256, 512, 0, 100.0), (33, 70, 768, 7, 30.0),
+                                               (256, 2048, 512, 512, 100.0)])
+def test_ce_tensor_core_path(nq, nk, E, off, scale):
+    """what the training step runs: dots from ONE K = 3E GEMM over bf16 hi/lo splits (fp32-level logits), row kernels for
+    lse / loss / dS, gradient GEMMs in bf16 -- against the fp32 torch loss"""
+    Q = torch.nn.functional.normalize(rnd(nq, E, seed=71), dim=-1)
+    K = torch.nn.functional.normalize(rnd(nk, E, seed=72), dim=-1)
+    ls = torch.tensor(math.log(scale), device=DEV)
+    nkp = (nk + 7) // 8 * 8
+    Qs = torch.empty(nq, 3 * E, device=DEV, dtype=torch.bfloat16); Ks = torch.zeros(nkp, 3 * E, device=DEV, dtype=torch.bfloat16)
+    ops.split_bf16x3(Q, Qs, 0); ops.split_bf16x3(K, Ks, 1)
+    S = torch.empty(nq, nkp, device=DEV)
+    ops.gemm(Qs, Ks, S)
+    assert_close(S[:, :nk], Q @ K.t(), 0.0, 3e-6, "hi/lo split dots")          # bf16 x 3 ~ 2^-17 relative on |q||k| = 1
+    lse = torch.empty(nq, device=DEV); rows = torch.empty(nq, device=DEV)
+    ops.ce_rows_fwd(S, ls, off, lse, rows, nq, nk)
+    Qr = Q.clone().requires_grad_(True); Kr = K.clone().requires_grad_(True); lr = ls.clone().requires_grad_(True)
+    Sr = (Qr @ Kr.t()) * lr.exp()
+    lab = off + torch.arange(nq, device=DEV)
+    per = torch.nn.functional.cross_entropy(Sr, lab, reduction="none")
+    assert_close(S[:, :nk], Sr, 1e-5, 3e-6 * scale, "scaled logits")
+    assert_close(lse, torch.logsumexp(Sr, -1), 1e-5, 3e-6 * scale, "lse")
+    assert_close(rows, per, 1e-4, 1e-5 * scale, "per-row CE")
+    coef = 0.37
+    (per.sum() * coef).backward()
+    dS = torch.full((nq, nkp), 9.0, device=DEV, dtype=torch.bfloat16); dls = torch.zeros(1, device=DEV)
+    ops.ce_rows_bwd(S, ls, lse, off, coef, dS, nq, nk, dscale_log=dls)
+    assert torch.all(dS[:, nk:] == 0)
+    dQ = torch.empty(nq, E, device=DEV); dK = torch.empty(nk, E, device=DEV)
+    ops.gemm(dS, Ks[:, :E], dQ, b_mn_major=1)
+    ops.gemm(dS[:, :nk], Qs[:, :E], dK, a_mn_major=1, b_mn_major=1)
+    gq = Qr.grad.abs().max().item(); gk = Kr.grad.abs().max().item()
+    assert_close(dQ, Qr.grad, 2e-2, 1e-2 * gq, "dQ (bf16 operands)")
+    assert_close(dK, Kr.grad, 2e-2, 1e-2 * gk, "dK (bf16 operands)")
+    assert_close(dls, lr.grad.view(1), 2e-3, 1e-3 * abs(lr.grad.item()) + 1e-4, "dscale")
 
 
 # --------------------------------------------------------------------------------------------- optimizer
