@@ -108,10 +108,12 @@ class Trainer(object):
         captured CUDA graph (ClipEngine.train_step); otherwise through model(batch) / compute_loss / loss.backward()."""
         args = self.args
         label_ids = batch.pop("label_ids", None)
-        if args.gradient_accumulation_steps == 1 and self.use_graph:
+        if args.gradient_accumulation_steps == 1:
+            # one fused step: a replayed CUDA graph on one GPU; eager launches with the gradient all-reduce overlapped with the
+            # backward pass when the step contains collectives (use_cuda_graph=False)
             out = self.engine.train_step(batch["pixel_values"], batch["input_ids"], lr=args.learning_rate, weight_decay=args.weight_decay,
                                          max_grad_norm=args.max_grad_norm, warmup_steps=self._warmup_steps, t_total=self._t_total,
-                                         distributed=getattr(self.model_module, "distributed_loss", False), use_graph=True)
+                                         distributed=getattr(self.model_module, "distributed_loss", False), use_graph=self.use_graph)
             self._sched_step += 1
             return out["loss"].item()
         forward_outputs = self._model(batch)

@@ -30,6 +30,7 @@ constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, wa
 struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles, splits, k_per_split;  // k_per_split multiple of BK
+  int* tile_counter;                          // {next tile, CTAs done}: dynamic tile scheduler of the 1-CTA kernel (self re-arming)
   clipk_epilogue_t epi;
 };
 
@@ -306,7 +307,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + NSTAGE;
   uint64_t* tmem_full = empty_bar + NSTAGE;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* sched_full = tmem_empty + 2;          // dynamic tile scheduler: 2-deep queue of tile ids, producer -> MMA + epilogue warps
+  uint64_t* sched_empty = sched_full + 2;
+  int* sched_tile = reinterpret_cast<int*>(sched_empty + 2);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(sched_tile + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -318,6 +322,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sched_full[s], 1); mbar_init(&sched_empty[s], 1 + EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, 2 * BN);
@@ -330,7 +335,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================================================ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int slot = 0; uint32_t sphase = 0;
+      while (true) {
+        // tiles come from a global counter, not from blockIdx: a CTA that starts late (its SM was busy with a concurrent kernel, e.g.
+        // an NCCL all-reduce overlapping the backward pass) finds the counter exhausted instead of holding the whole GEMM back
+        int tile = atomicAdd(p.tile_counter, 1);
+        if (tile >= num_tiles) tile = -1;
+        mbar_wait(&sched_empty[slot], sphase ^ 1);
+        sched_tile[slot] = tile;
+        mbar_arrive(&sched_full[slot]);
+        if (++slot == 2) { slot = 0; sphase ^= 1; }
+        if (tile < 0) break;
         const int ks = tile / tiles_mn;
         const int mn = tile - ks * tiles_mn;
         const int m0 = (mn / p.n_tiles) * BM;
@@ -357,6 +372,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
+      // the last CTA to run dry re-arms the counters for the next launch that uses this slot (every CTA's final fetch precedes its
+      // arrival here, so nobody reads the counter afterwards)
+      if (atomicAdd(p.tile_counter + 1, 1) == (int)gridDim.x - 1) { p.tile_counter[0] = 0; p.tile_counter[1] = 0; __threadfence(); }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one thread)
@@ -364,7 +382,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int slot = 0; uint32_t sphase = 0;
+      while (true) {
+        mbar_wait(&sched_full[slot], sphase);
+        const int tile = sched_tile[slot];
+        mbar_arrive(&sched_empty[slot]);
+        if (++slot == 2) { slot = 0; sphase ^= 1; }
+        if (tile < 0) break;
         const int ks = tile / tiles_mn;
         const int k_begin = ks * p.k_per_split;
         const int k_end = min(p.K, k_begin + p.k_per_split);
@@ -400,9 +424,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t store_seq = 0;
     float* slab = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + (warp - 2) * 32 * 32;
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-    if ((int)blockIdx.x < num_tiles) epi_prefetch<BN>(p, blockIdx.x, tiles_mn, q, half, lane);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      if (tile + (int)gridDim.x < num_tiles) epi_prefetch<BN>(p, tile + gridDim.x, tiles_mn, q, half, lane);
+    int slot = 0; uint32_t sphase = 0;
+    while (true) {
+      mbar_wait(&sched_full[slot], sphase);
+      const int tile = sched_tile[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sched_empty[slot]);
+      if (++slot == 2) { slot = 0; sphase ^= 1; }
+      if (tile < 0) break;
+      epi_prefetch<BN>(p, tile, tiles_mn, q, half, lane);    // the id arrives >= 1 tile ahead of the accumulator: L2 prefetch of the epilogue inputs
       const int ks = tile / tiles_mn;
       const int mn = tile - ks * tiles_mn;
       const int m0 = (mn / p.n_tiles) * BM;
@@ -705,6 +735,20 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   p.k_per_split = kb_per * BK;
   p.epi = *epi;
   if (p.epi.alpha == 0.0f) p.epi.alpha = 1.0f;
+  {
+    // pool of self-re-arming scheduler counters; consecutive launches rotate through it so that back-to-back GEMMs never share one
+    constexpr int POOL = 64;
+    static int* pool = nullptr;
+    static unsigned next = 0;
+    if (!pool) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(stream, &cs);
+      if (cs != cudaStreamCaptureStatusNone) { set_error("clipk_gemm_bf16: first call (allocates the scheduler counters) must not happen during stream capture"); return CLIPK_ERR_CUDA; }
+      CLIPK_CUDA(cudaMalloc(&pool, POOL * 2 * sizeof(int)));
+      CLIPK_CUDA(cudaMemset(pool, 0, POOL * 2 * sizeof(int)));
+    }
+    p.tile_counter = pool + 2 * (next++ % POOL);
+  }
 
   CUtensorMap tA, tB;
   int rc;

@@ -76,3 +76,42 @@ def allreduce_sum_(flat: torch.Tensor) -> torch.Tensor:
 def barrier():
     if world_size() > 1:
         dist.barrier()
+
+
+class OverlappedGradReducer:
+    """SUM all-reduce of a flat gradient buffer issued in pieces WHILE the backward pass is still running (what DDP's bucketing does
+    for the reference, core/trainer.py:103-108).  `ready(ranges)` launches an asynchronous all-reduce of slices whose gradients are
+    final (the collective runs on the backend's own stream, ordered after the kernels launched so far); `finish()` sends whatever
+    was never announced and makes the current stream wait for everything.  Each element is reduced exactly once."""
+
+    def __init__(self, flat: torch.Tensor, n: int):
+        self.flat = flat
+        self.n = int(n)
+        self.done = []      # (start, end) already sent
+        self.works = []
+
+    def _launch(self, a: int, b: int):
+        if b > a:
+            self.works.append(dist.all_reduce(self.flat[a:b], async_op=True))
+            self.done.append((a, b))
+
+    def ready(self, ranges):
+        if world_size() == 1:
+            return
+        for a, b in ranges:
+            a, b = max(0, int(a)), min(self.n, int(b))
+            for c, d in self.done:                     # never send an element twice
+                if a < d and c < b:
+                    raise RuntimeError(f"gradient range [{a},{b}) overlaps an already reduced range [{c},{d})")
+            self._launch(a, b)
+
+    def finish(self):
+        if world_size() > 1:
+            pos = 0
+            for a, b in sorted(self.done):
+                self._launch(pos, a)
+                pos = max(pos, b)
+            self._launch(pos, self.n)
+            for w in self.works:
+                w.wait()
+        self.done, self.works = [], []

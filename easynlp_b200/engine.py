@@ -17,6 +17,8 @@ Dropout probabilities are taken as 0 by this engine ("dropout").
 import math
 from typing import Dict, Optional
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -52,6 +54,7 @@ class ClipEngine:
         self.params = ParamStore(cfg, device, with_optimizer_state)
         self._buf: Dict[tuple, torch.Tensor] = {}
         self._saved = None
+        self._reducer = None      # OverlappedGradReducer while an eager multi-GPU backward is running
         self.norm_and_coef = torch.zeros(2, device=self.dev)
         self._norm_ws = torch.zeros(1024, dtype=torch.float64, device=self.dev)
         # device-resident optimizer step counter (also the per-step dropout offset) and {lr, step size}
@@ -193,6 +196,7 @@ class ClipEngine:
             bias_prev = P_.g(f"visual.transformer.resblocks.{i - 1}.mlp.c_proj.bias") if i > 0 else None
             ops.layernorm_bwd(dh, ly["x_in"], P_.p(p + "ln_1.weight"), ly["m1"], ly["r1"], dx_add=dX1, dx_f32=dX, dx_bf16=dXb,
                               dgamma=P_.g(p + "ln_1.weight"), dbeta=P_.g(p + "ln_1.bias"), dbias=bias_prev)
+            self._grads_ready(p)
         # ln_pre, token assembly, patch embedding
         dx0 = self.f32("v.dx0", M, W)
         ops.layernorm_bwd(dX, self.f32("v.x0", M, W), P_.p("visual.ln_pre.weight"), st["mean0"], st["rstd0"], dx_f32=dx0,
@@ -306,6 +310,7 @@ class ClipEngine:
             # d(layer input) = dxp (bf16) + ds1 (f32): consumed by the LayerNorm backward of the layer below, which writes ds2
             # (a different buffer) before ds1 is overwritten again
             dy, dy_add = dxp, ds1
+            self._grads_ready(p)
         de = self.f32("t.de", M, H)
         ops.layernorm_bwd(dy, st["e"], P_.p("bert.embeddings.LayerNorm.weight"), st["me"], st["re"], dy_add=dy_add, dx_f32=de,
                           dgamma=P_.g("bert.embeddings.LayerNorm.weight"), dbeta=P_.g("bert.embeddings.LayerNorm.bias"),
@@ -313,6 +318,7 @@ class ClipEngine:
         ops.bert_embed_bwd(st["ids"].view(-1), de, P_.g("bert.embeddings.word_embeddings.weight"), M, H, self.cfg["vocab_size"])
         ops.colsum(de, P_.g("bert.embeddings.position_embeddings.weight").view(-1)[:Lt * H], B, Lt * H)
         ops.colsum(de, P_.g("bert.embeddings.token_type_embeddings.weight")[0], M, H)
+        self._grads_ready("bert.embeddings.")
 
     # ------------------------------------------------------------------ contrastive head
     def loss_forward(self, text_embeds, image_embeds, gallery_image=None, gallery_text=None, label_offset=0, want_logits=True):
@@ -422,6 +428,11 @@ class ClipEngine:
         from . import distributed as D
         D.allreduce_sum_(self.params.grad)
 
+    def _grads_ready(self, prefix: str):
+        """backward hook: every gradient under `prefix` is final -> hand its slices to the overlapped all-reduce (if one is active)"""
+        if self._reducer is not None:
+            self._reducer.ready(self.params.ranges_for(prefix))
+
     def optimizer_step(self, lr: float, weight_decay: float = 1e-4, max_grad_norm: float = 1.0, warmup_steps: int = 0, t_total: int = 0):
         """clip_grad_norm_(max_grad_norm) + AdamW(betas 0.9/0.999, eps 1e-6) with the reference's decay grouping.
         The step counter and {lr, bias-corrected step size} live on the device (clipk_adam_schedule), so the same launches can be
@@ -444,9 +455,19 @@ class ClipEngine:
     def _step_body(self, pixels, ids, hp):
         self.zero_grad()
         out = self.forward(pixels, ids, save=True, want_logits=hp["want_logits"], distributed=hp["distributed"])
-        self.backward(hp["grad_scale"])
-        if hp["allreduce"]:
-            self.allreduce_grads()
+        if hp["allreduce"] and hp.get("overlap", False):
+            # eager multi-GPU step: per-layer gradient slices are all-reduced while the rest of the backward pass runs
+            from . import distributed as D
+            self._reducer = D.OverlappedGradReducer(self.params.grad, self.params.n_trainable)
+            try:
+                self.backward(hp["grad_scale"])
+                self._reducer.finish()
+            finally:
+                self._reducer = None
+        else:
+            self.backward(hp["grad_scale"])
+            if hp["allreduce"]:
+                self.allreduce_grads()
         self.optimizer_step(hp["lr"], hp["weight_decay"], hp["max_grad_norm"], hp["warmup_steps"], hp["t_total"])
         return out
 
@@ -473,7 +494,8 @@ class ClipEngine:
         st["pixels"].copy_(pixels, non_blocking=True)
         st["ids"].copy_(ids, non_blocking=True)
         hp = {"lr": lr, "weight_decay": weight_decay, "max_grad_norm": max_grad_norm, "warmup_steps": warmup_steps, "t_total": t_total,
-              "distributed": distributed, "want_logits": want_logits, "grad_scale": grad_scale, "allreduce": allreduce}
+              "distributed": distributed, "want_logits": want_logits, "grad_scale": grad_scale, "allreduce": allreduce,
+              "overlap": bool(allreduce) and not use_graph and os.environ.get("CLIPK_NO_OVERLAP", "0") != "1"}
         if not use_graph or st["calls"] < 2:
             st["calls"] += 1
             return self._step_body(st["pixels"], st["ids"], hp)

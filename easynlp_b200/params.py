@@ -127,6 +127,20 @@ class ParamStore:
     def trainable_names(self) -> List[str]:
         return [n for n in self.schema if n not in NO_GRAD]
 
+    def ranges_for(self, prefix: str) -> List[Tuple[int, int]]:
+        """Contiguous [start, end) element ranges of the flat gradient covering every trainable tensor whose name starts with
+        `prefix` (padding up to the next tensor included).  One layer's tensors are adjacent inside each decay group, so a layer is
+        at most two ranges -- what the overlapped gradient all-reduce sends as soon as that layer's backward has run."""
+        spans = sorted((self.offsets[n], self.offsets[n] + _pad(max(1, _numel(self.schema[n])))) for n in self.trainable_names()
+                       if n.startswith(prefix))
+        out: List[Tuple[int, int]] = []
+        for a, b in spans:
+            if out and out[-1][1] == a:
+                out[-1] = (out[-1][0], b)
+            else:
+                out.append((a, b))
+        return out
+
     # ---- checkpoint I/O (reference key names; `chinese_clip.` prefix handled by the caller)
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = False):
         missing = []

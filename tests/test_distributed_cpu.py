@@ -56,6 +56,21 @@ def _worker(rank, world, port, b, E, q):
     flat = torch.full((8,), float(rank + 1))
     D.allreduce_sum_(flat)
     ok = ok and bool((flat == sum(range(1, world + 1))).all())
+    # overlapped gradient all-reduce: slices announced out of order + the never-announced remainder, each element exactly once
+    n = 1000
+    flat = torch.arange(n + 24, dtype=torch.float32) * (rank + 1)       # [n, n+24) lies outside the trainable range: untouched
+    red = D.OverlappedGradReducer(flat, n)
+    red.ready([(640, 768), (128, 256)])
+    red.ready([(0, 64)])
+    try:
+        red.ready([(700, 800)])
+        ok = False                                                      # overlapping an already sent range must raise
+    except RuntimeError:
+        pass
+    red.finish()
+    want = torch.arange(n + 24, dtype=torch.float32) * sum(range(1, world + 1))
+    want[n:] = torch.arange(n, n + 24, dtype=torch.float32) * (rank + 1)
+    ok = ok and torch.equal(flat, want) and red.done == [] and red.works == []
     D.barrier()
     q.put((rank, ok, total.item(), ref.item()))
     dist.destroy_process_group()
@@ -82,3 +97,30 @@ def test_single_process_helpers_are_identity():
     x = torch.randn(4, 8)
     assert D.world_size() == 1 and D.get_rank() == 0
     assert D.gather_rows(x) is x and D.reduce_scatter_rows(x) is x and D.allreduce_sum_(x) is x
+    flat = torch.ones(16)
+    red = D.OverlappedGradReducer(flat, 16)
+    red.ready([(0, 8)]); red.finish()
+    assert torch.equal(flat, torch.ones(16))
+
+
+def test_layer_gradient_ranges_cover_each_parameter_once():
+    """the overlapped all-reduce sends, per finished layer, the contiguous slices ParamStore.ranges_for names: per-layer prefixes +
+    the remainder must tile the trainable range without overlap"""
+    from easynlp_b200.params import ParamStore
+    cfg = O.tiny_config()
+    st = ParamStore(cfg, device="cpu", with_optimizer_state=False)
+    seen = torch.zeros(st.n_trainable, dtype=torch.int32)
+    prefixes = [f"visual.transformer.resblocks.{i}." for i in range(cfg["vision_layers"])] + \
+               [f"bert.encoder.layer.{i}." for i in range(cfg["text_num_hidden_layers"])] + ["bert.embeddings."]
+    for pre in prefixes:
+        rs = st.ranges_for(pre)
+        assert 1 <= len(rs) <= 2, (pre, rs)                             # decay group + no-decay group
+        for a, b in rs:
+            seen[a:b] += 1
+        names = [n for n in st.trainable_names() if n.startswith(pre)]
+        assert sum(b - a for a, b in rs) >= sum(st.p(n).numel() for n in names)
+        for n in names:
+            o = st.offsets[n]
+            assert any(a <= o and o + st.p(n).numel() <= b for a, b in rs)
+    assert int(seen.max()) == 1                                         # no element announced twice
+    assert st.ranges_for("bert.pooler.") == []                           # never receives a gradient: outside the reduced range
