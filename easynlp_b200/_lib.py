@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libclipk.so")
 
-EPI_LINEAR, EPI_QUICK_GELU, EPI_ERF_GELU, EPI_MUL_AUX, _EPI_RESERVED4, EPI_ATOMIC_ADD = range(6)
+EPI_LINEAR, EPI_QUICK_GELU, EPI_ERF_GELU, EPI_MUL_AUX, EPI_RANK_COUNT, EPI_ATOMIC_ADD = range(6)
 BF16, F32 = 0, 1
 
 
@@ -21,7 +21,8 @@ class Dropout(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [("mode", C.c_int), ("out_dtype", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int),
                 ("out2", C.c_void_p), ("ldo2", C.c_int), ("bias", C.c_void_p), ("residual", C.c_void_p),
-                ("ldr", C.c_int), ("aux", C.c_void_p), ("ldaux", C.c_int), ("alpha", C.c_float), ("colsum", C.c_void_p)]
+                ("ldr", C.c_int), ("aux", C.c_void_p), ("ldaux", C.c_int), ("alpha", C.c_float), ("colsum", C.c_void_p),
+                ("label_offset", C.c_int)]
 
 
 _lib = None
@@ -60,6 +61,9 @@ def _declare(L):
     L.clipk_l2norm_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, vp]
     L.clipk_cast_bf16.argtypes = [vp, vp, ll, vp]
     L.clipk_axpy.argtypes = [vp, vp, f, ll, vp]
+    L.clipk_retrieval_rank_tc_workspace.argtypes = [i, i, i]
+    L.clipk_retrieval_rank_tc_workspace.restype = C.c_size_t
+    L.clipk_retrieval_rank_tc.argtypes = [vp, vp, i, vp, i, i, i, vp, C.c_size_t, vp]
     L.clipk_split_bf16x3.argtypes = [vp, vp, i, i, i, ll, vp]
     L.clipk_ce_rows_fwd.argtypes = [vp, ll, vp, i, vp, vp, i, i, vp]
     L.clipk_ce_rows_bwd.argtypes = [vp, ll, vp, vp, i, f, vp, ll, vp, i, i, vp]

@@ -1,8 +1,10 @@
 """CLIPEvaluator -- drop-in for easynlp/appzoo/clip/evaluator.py:27-72.
 
 Same protocol (encode the whole validation set, text->image recall@1/5/10, return [("mean_recall", fraction)]) but the
-N x N agreement matrix and the per-row torch.sort loop are replaced by clipk_retrieval_rank, which streams the gallery and
-counts, per query, the gallery items scoring above the match: hit@K <=> rank < K."""
+N x N agreement matrix and the per-row torch.sort loop are replaced by clipk_retrieval_rank_tc: a tcgen05 GEMM over bf16 hi/lo
+splits of the embeddings (fp32-level scores) whose epilogue counts, per query, the gallery items scoring above the match --
+hit@K <=> rank < K, and the matrix is never materialised (the fp32 CUDA-core kernel clipk_retrieval_rank remains as
+the exact-arithmetic cross-check, `exact=True`)."""
 import time
 
 import torch
@@ -11,10 +13,11 @@ from ...core.evaluator import Evaluator
 from ... import ops
 
 
-def recall_from_embeddings(text_embeds: torch.Tensor, image_embeds: torch.Tensor, ks=(1, 5, 10)):
+def recall_from_embeddings(text_embeds: torch.Tensor, image_embeds: torch.Tensor, ks=(1, 5, 10), exact: bool = False):
     n = text_embeds.shape[0]
     ranks = torch.empty(n, dtype=torch.int32, device=text_embeds.device)
-    ops.retrieval_rank(text_embeds.float().contiguous(), image_embeds.float().contiguous(), ranks)
+    fn = ops.retrieval_rank if (exact or text_embeds.shape[1] % 8) else ops.retrieval_rank_tc
+    fn(text_embeds.float().contiguous(), image_embeds.float().contiguous(), ranks)
     r = ranks.cpu()
     return {k: int((r < k).sum()) for k in ks}
 

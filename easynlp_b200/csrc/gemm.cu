@@ -31,8 +31,23 @@ struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles, splits, k_per_split;  // k_per_split multiple of BK
   int* tile_counter;                          // {next tile, CTAs done}: dynamic tile scheduler of the 1-CTA kernel (self re-arming)
+  int group_m;                                // tile rasterisation: consecutive tile ids walk down group_m row tiles before the next column tile
   clipk_epilogue_t epi;
 };
+
+// Tile id -> (row tile, column tile).  group_m == 1: column tiles fastest (the CTAs running together share a few A row tiles and all
+// of a small B).  group_m > 1 (B far larger than L2, e.g. the retrieval gallery): ids sweep a [group_m x n_tiles] band column by
+// column, so every B tile is fetched from HBM once per band instead of once per row tile.
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int mn, int& mi, int& ni) {
+  if (p.group_m <= 1) { mi = mn / p.n_tiles; ni = mn - mi * p.n_tiles; return; }
+  const int band = p.group_m * p.n_tiles;
+  const int g = mn / band;
+  const int first = g * p.group_m;
+  const int gm = min(p.group_m, p.m_tiles - first);
+  const int rem = mn - g * band;
+  ni = rem / gm;
+  mi = first + (rem - ni * gm);
+}
 
 template <int BN>
 struct GemmSmem {
@@ -158,8 +173,10 @@ __device__ __forceinline__ void epi_prefetch(const GemmParams& p, int tile, int 
   const clipk_epilogue_t& e = p.epi;
   if (!e.residual && !e.aux) return;
   const int mn = tile % tiles_mn;
-  const int row = (mn / p.n_tiles) * BM + q * 32 + lane;
-  const int col = (mn % p.n_tiles) * BN + half * (BN / 2);
+  int mi, ni;
+  tile_coords(p, mn, mi, ni);
+  const int row = mi * BM + q * 32 + lane;
+  const int col = ni * BN + half * (BN / 2);
   if (row >= p.M || col >= p.N) return;
   if (e.residual) {
     const char* ptr = reinterpret_cast<const char*>(e.residual + (size_t)row * e.ldr + col);
@@ -288,16 +305,50 @@ __device__ __forceinline__ void epi_tile_tma(const GemmParams& p, const CUtensor
   }
 }
 
-// EPI: 0 = transpose-through-smem epilogue (any output type), 1 = TMA-store epilogue, 4-stage ring + 2 staging tiles per warp,
-//      2 = TMA-store epilogue, 3-stage ring + 8 staging tiles per warp
+// Epilogue of CLIPK_EPI_RANK_COUNT: nothing is stored -- every accumulator of the warp's [32 rows x BN/2 cols] slice is compared with the
+// row's threshold (the score of the query's own match) and the number of larger ones goes to rank[row] with one atomic per row and tile.
+template <int BN>
+__device__ __forceinline__ void epi_tile_rank(const GemmParams& p, uint64_t* full_bar, uint32_t full_phase, uint32_t t_row, int row0, int col0,
+                                              int lane, bool has_k) {
+  constexpr int CHUNKS = BN / 64;
+  const clipk_epilogue_t& e = p.epi;
+  const int row = row0 + lane;
+  const float thr = (row < p.M) ? reinterpret_cast<const float*>(e.aux)[row] : INFINITY;
+  const int lab = e.label_offset + row;
+  const float al = e.alpha;
+  uint32_t r[32];
+  int cnt = 0;
+  mbar_wait(full_bar, full_phase);
+  tc_fence_after();
+  tmem_ld_x32(t_row, r);
+#pragma unroll 1
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col = col0 + c * 32;
+    tmem_wait_ld();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * al;
+    if (c + 1 < CHUNKS) tmem_ld_x32(t_row + (c + 1) * 32, r);
+    if (has_k && col < p.N) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) cnt += (col + j < p.N && col + j != lab && v[j] > thr) ? 1 : 0;
+    }
+  }
+  if (row < p.M && cnt) atomicAdd(reinterpret_cast<int*>(e.out) + row, cnt);
+}
+
+// EPI: 0 = transpose-through-smem epilogue (any output type / mode, chosen at run time);
+//      1 + mode = TMA-store epilogue of that mode (LINEAR / QUICK_GELU / ERF_GELU / MUL_AUX), 2 staging tiles per warp
+//                 (a 3-stage ring + 4 staging tiles per warp was measured too: no gain at K = 768, -7 % at K = 3072);
+//      5 = CLIPK_EPI_RANK_COUNT (compare + count, no output matrix).
 template <int BN, int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                  const __grid_constant__ CUtensorMap tmO2, const GemmParams p) {
-  constexpr bool TMA_OUT = EPI != 0;
+  constexpr bool TMA_OUT = EPI >= 1 && EPI <= 4;
   constexpr int NSTAGE = STAGES;
   constexpr int NBUF = 2;                         // 2 KB bf16 store tiles per epilogue warp (EPI == 0: one 4 KB fp32 slab)
-  constexpr int MODE = EPI == 0 ? 0 : EPI - 1;
+  constexpr int MODE = TMA_OUT ? EPI - 1 : 0;
   using L = GemmSmem<BN>;
   // 1024-B aligned dynamic smem (SWIZZLE_128B atoms); indexing the __shared__ array directly keeps the address space known to
   // the compiler (LDS/STS instead of generic LD/ST)
@@ -348,8 +399,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (tile < 0) break;
         const int ks = tile / tiles_mn;
         const int mn = tile - ks * tiles_mn;
-        const int m0 = (mn / p.n_tiles) * BM;
-        const int n0 = (mn % p.n_tiles) * BN;
+        int mi, ni;
+        tile_coords(p, mn, mi, ni);
+        const int m0 = mi * BM;
+        const int n0 = ni * BN;
         const int k_begin = ks * p.k_per_split;
         const int k_end = min(p.K, k_begin + p.k_per_split);
         for (int k0 = k_begin; k0 < k_end; k0 += BK) {
@@ -435,11 +488,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       epi_prefetch<BN>(p, tile, tiles_mn, q, half, lane);    // the id arrives >= 1 tile ahead of the accumulator: L2 prefetch of the epilogue inputs
       const int ks = tile / tiles_mn;
       const int mn = tile - ks * tiles_mn;
-      const int m0 = (mn / p.n_tiles) * BM;
-      const int n0 = (mn % p.n_tiles) * BN + half * (BN / 2);
+      int mi, ni;
+      tile_coords(p, mn, mi, ni);
+      const int m0 = mi * BM;
+      const int n0 = ni * BN + half * (BN / 2);
       const int k_begin = ks * p.k_per_split;
       const bool has_k = k_begin < p.K;   // an empty split contributes nothing (host never creates one, but be safe)
-      if constexpr (TMA_OUT) {
+      if constexpr (EPI == 5) {
+        epi_tile_rank<BN>(p, &tmem_full[acc], acc_phase, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2), m0 + q * 32, n0,
+                          lane, has_k);
+      } else if constexpr (TMA_OUT) {
         epi_tile_tma<BN, NBUF, MODE>(p, &tmO, &tmO2, smem + L::EPI_OFFSET + (warp - 2) * (NBUF * 2048), store_seq, &tmem_full[acc], acc_phase,
                          tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2), m0 + q * 32, n0, lane, has_k);
       } else {
@@ -708,7 +766,8 @@ using namespace clipk;
 extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N,
                                int K, const clipk_epilogue_t* epi, int splits, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) { set_error("clipk_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K); return CLIPK_ERR_ARG; }
-  if ((lda % 8) || (ldb % 8) || (N % 8)) { set_error("clipk_gemm_bf16: lda/ldb/N must be multiples of 8 (lda=%d ldb=%d N=%d)", lda, ldb, N); return CLIPK_ERR_ARG; }
+  const bool rank_mode = epi && epi->mode == CLIPK_EPI_RANK_COUNT;
+  if ((lda % 8) || (ldb % 8) || ((N % 8) && !rank_mode)) { set_error("clipk_gemm_bf16: lda/ldb/N must be multiples of 8 (lda=%d ldb=%d N=%d)", lda, ldb, N); return CLIPK_ERR_ARG; }
   if (!epi || !epi->out) { set_error("clipk_gemm_bf16: epilogue output missing"); return CLIPK_ERR_ARG; }
   if (splits < 1) splits = 1;
   if (splits > 1 && epi->mode != CLIPK_EPI_ATOMIC_ADD) { set_error("clipk_gemm_bf16: split-K requires CLIPK_EPI_ATOMIC_ADD"); return CLIPK_ERR_ARG; }
@@ -716,13 +775,14 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   if ((epi->mode == CLIPK_EPI_QUICK_GELU || epi->mode == CLIPK_EPI_ERF_GELU) && !epi->out2) { set_error("clipk_gemm_bf16: GELU epilogue needs out2"); return CLIPK_ERR_ARG; }
   if (epi->colsum && (N % 32)) { set_error("clipk_gemm_bf16: the fused column sum needs N %% 32 == 0"); return CLIPK_ERR_ARG; }
   if (epi->mode == CLIPK_EPI_MUL_AUX && !epi->aux) { set_error("clipk_gemm_bf16: MUL_AUX epilogue needs aux"); return CLIPK_ERR_ARG; }
+  if (rank_mode && (!epi->aux || a_mn_major || splits > 1)) { set_error("clipk_gemm_bf16: RANK_COUNT needs aux (f32 thresholds), a K-major A and no split-K"); return CLIPK_ERR_ARG; }
   if (epi->mode < 0 || epi->mode > CLIPK_EPI_ATOMIC_ADD) { set_error("clipk_gemm_bf16: unknown epilogue mode %d", epi->mode); return CLIPK_ERR_ARG; }
 
   const int BN = (N % 256 == 0 || N > 512) ? 256 : 128;
   static int use_pair = -1;
   // experimental: correct (tests pass) but measured at half the 1-CTA rate on B200 (profiles/r01_gemm_2cta_note.md) -> opt-in only
   if (use_pair < 0) { const char* ev = getenv("CLIPK_GEMM_2CTA"); use_pair = (ev && ev[0] == '1') ? 1 : 0; }
-  const bool pair = use_pair && BN == 256 && M >= 256;
+  const bool pair = use_pair && BN == 256 && M >= 256 && !rank_mode;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = pair ? (M + 255) / 256 : (M + BM - 1) / BM;
@@ -735,6 +795,8 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   p.k_per_split = kb_per * BK;
   p.epi = *epi;
   if (p.epi.alpha == 0.0f) p.epi.alpha = 1.0f;
+  // many column tiles AND a B operand that cannot stay in the 126 MB L2 (the retrieval gallery): band rasterisation (tile_coords)
+  p.group_m = (!pair && p.n_tiles > 64 && (size_t)N * (size_t)K * 2 > ((size_t)48 << 20)) ? 16 : 1;
   {
     // pool of self-re-arming scheduler counters; consecutive launches rotate through it so that back-to-back GEMMs never share one
     constexpr int POOL = 64;
@@ -773,7 +835,7 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   const bool gelu = ee.mode == CLIPK_EPI_QUICK_GELU || ee.mode == CLIPK_EPI_ERF_GELU;
   static int no_tma_out = -1;
   if (no_tma_out < 0) { const char* ev = getenv("CLIPK_GEMM_NO_TMA_OUT"); no_tma_out = (ev && ev[0] == '1') ? 1 : 0; }
-  const bool tma_out = !no_tma_out && ee.out_dtype == CLIPK_BF16 && !ee.residual && ee.mode != CLIPK_EPI_ATOMIC_ADD && ee.mode != CLIPK_EPI_RESERVED4 &&
+  const bool tma_out = !no_tma_out && ee.out_dtype == CLIPK_BF16 && !ee.residual && ee.mode != CLIPK_EPI_ATOMIC_ADD && ee.mode != CLIPK_EPI_RANK_COUNT &&
                        (gelu ? ee.out2 != nullptr : ee.out2 == nullptr) && (N % 32 == 0) && (ee.ldo % 8 == 0) &&
                        !(reinterpret_cast<uintptr_t>(ee.out) & 15) && (!gelu || (ee.ldo2 % 8 == 0 && !(reinterpret_cast<uintptr_t>(ee.out2) & 15))) &&
                        (ee.mode != CLIPK_EPI_MUL_AUX || (ee.ldaux % 8 == 0 && !(reinterpret_cast<uintptr_t>(ee.aux) & 15))) &&
@@ -784,6 +846,11 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     rc = make_tmap_2d_bf16(&tO, ee.out, (uint64_t)N, (uint64_t)M, (uint64_t)ee.ldo, 32, 32, 64);
     if (rc) return rc;
     if (gelu) { rc = make_tmap_2d_bf16(&tO2, ee.out2, (uint64_t)N, (uint64_t)M, (uint64_t)ee.ldo2, 32, 32, 64); if (rc) return rc; }
+  }
+  if (rank_mode) {
+    if (BN == 256) { if (b_mn_major) return launch_gemm<256, 0, 1, 5>(tA, tB, tO, tO2, p, stream); return launch_gemm<256, 0, 0, 5>(tA, tB, tO, tO2, p, stream); }
+    if (b_mn_major) return launch_gemm<128, 0, 1, 5>(tA, tB, tO, tO2, p, stream);
+    return launch_gemm<128, 0, 0, 5>(tA, tB, tO, tO2, p, stream);
   }
   if (variant == 0) {
 #define CLIPK_DISPATCH(BN_)                                                          \

@@ -307,6 +307,21 @@ __global__ void __launch_bounds__(256) ce_rows_bwd_kernel(const float* __restric
   }
 }
 
+
+// thr[i] = <Q_i, K_{label_offset + i}> (fp32): the score of query i's own match, the threshold of the rank-count GEMM epilogue
+__global__ void __launch_bounds__(256) match_score_kernel(const float* __restrict__ Q, const float* __restrict__ K, int label_offset,
+                                                          float* __restrict__ thr, int nq, int nk, int E) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= nq) return;
+  const int lab = label_offset + row;
+  float acc = 0.f;
+  if (lab >= 0 && lab < nk)
+    for (int c = lane * 4; c < E; c += 128) acc += dot4(*reinterpret_cast<const float4*>(Q + (long long)row * E + c), *reinterpret_cast<const float4*>(K + (long long)lab * E + c));
+  acc = warp_sum(acc);
+  if (lane == 0) thr[row] = (lab >= 0 && lab < nk) ? acc : INFINITY;     // no match in the gallery: nothing ranks above it
+}
+
 }  // namespace clipk
 
 using namespace clipk;
@@ -418,4 +433,34 @@ extern "C" int clipk_ce_rows_bwd(const float* S, long long lds, const float* log
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;
+}
+
+static size_t rank_tc_align(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" size_t clipk_retrieval_rank_tc_workspace(int nq, int nk, int E) {
+  return rank_tc_align((size_t)nq * 3 * E * 2) + rank_tc_align((size_t)nk * 3 * E * 2) + rank_tc_align((size_t)nq * 4);
+}
+
+extern "C" int clipk_retrieval_rank_tc(const float* Q, const float* K, int label_offset, int* rank_out, int nq, int nk, int E, void* workspace,
+                                       size_t workspace_bytes, cudaStream_t stream) {
+  if (nq <= 0 || nk <= 0) return 0;
+  if (E % 8) { set_error("retrieval_rank_tc: E %% 8 != 0"); return CLIPK_ERR_UNSUPPORTED; }
+  if (!workspace || workspace_bytes < clipk_retrieval_rank_tc_workspace(nq, nk, E) || (reinterpret_cast<uintptr_t>(workspace) & 15)) {
+    set_error("retrieval_rank_tc: workspace of %zu bytes (16-byte aligned) required", clipk_retrieval_rank_tc_workspace(nq, nk, E));
+    return CLIPK_ERR_ARG;
+  }
+  char* w = reinterpret_cast<char*>(workspace);
+  void* Qs = w; w += rank_tc_align((size_t)nq * 3 * E * 2);
+  void* Ks = w; w += rank_tc_align((size_t)nk * 3 * E * 2);
+  float* thr = reinterpret_cast<float*>(w);
+  int rc;
+  if ((rc = clipk_split_bf16x3(Q, Qs, nq, E, 0, 3LL * E, stream))) return rc;
+  if ((rc = clipk_split_bf16x3(K, Ks, nk, E, 1, 3LL * E, stream))) return rc;
+  match_score_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(Q, K, label_offset, thr, nq, nk, E);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  CLIPK_CUDA(cudaMemsetAsync(rank_out, 0, (size_t)nq * sizeof(int), stream));
+  clipk_epilogue_t e{};
+  e.mode = CLIPK_EPI_RANK_COUNT; e.out_dtype = CLIPK_F32; e.out = rank_out; e.aux = thr; e.alpha = 1.0f; e.label_offset = label_offset;
+  return clipk_gemm_bf16(Qs, 3 * E, 0, Ks, 3 * E, 0, nq, nk, 3 * E, &e, 1, stream);
 }

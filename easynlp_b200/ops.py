@@ -295,5 +295,18 @@ def retrieval_rank(Q, K, rank_out, label_offset=0):
 
 
 @_op
+def retrieval_rank_tc(Q, K, rank_out, label_offset=0):
+    """ranks on the tensor cores: hi/lo-split K = 3E GEMM with the compare-and-count epilogue (no N x N matrix); see clipk.h"""
+    nq, E = Q.shape
+    nk = K.shape[0]
+    assert rank_out.dtype == torch.int32 and rank_out.numel() == nq and Q.is_contiguous() and K.is_contiguous()
+    nbytes = L_.lib().clipk_retrieval_rank_tc_workspace(nq, nk, E)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=Q.device)
+    with _traced(f"retrieval_rank_tc|{nq}x{nk}x{E}", 2.0 * nq * nk * 3 * E):
+        L_.check(L_.lib().clipk_retrieval_rank_tc(_f32(Q), _f32(K), label_offset, _ptr(rank_out), nq, nk, E, _ptr(ws), nbytes, _stream()),
+                 "retrieval_rank_tc")
+
+
+@_op
 def dropout_mask(out, rows, cols, drop):
     L_.check(L_.lib().clipk_dropout_mask(_f32(out), rows, cols, _dp(drop), _stream()), "dropout_mask")

@@ -47,7 +47,7 @@ int64_t clipk_launch_count(void);
                                     (modeling_chineseclip.py:179-181)                                                     */
 #define CLIPK_EPI_ERF_GELU 2     /* same with gelu_erf (modelzoo/activations.py:45-48): out2 = act(z), out = act'(z)              */
 #define CLIPK_EPI_MUL_AUX 3      /* out = (alpha*acc + bias) * aux (+ residual): backward of modes 1/2 with aux = act'(z)          */
-#define CLIPK_EPI_RESERVED4 4    /* unused                                                                                  */
+#define CLIPK_EPI_RANK_COUNT 4   /* no matrix output: out (int32 [M]) += #{j != label_offset + i : alpha*acc_ij > aux_f32[i]}       */
 #define CLIPK_EPI_ATOMIC_ADD 5   /* out(f32) += acc  via red.add -- split-K weight gradients                                */
 
 typedef struct {
@@ -64,13 +64,14 @@ typedef struct {
   int ldaux;
   float alpha;           /* 0 is read as 1 */
   float* colsum;         /* optional f32 [N]: += column sums of the stored output (bias gradient of the producing layer) */
+  int label_offset;      /* CLIPK_EPI_RANK_COUNT: column label_offset + i is row i's own match and is not counted; aux = f32 [M] thresholds */
 } clipk_epilogue_t;
 
 /* D[M,N] = epilogue(op(A) x op(B)), bf16 operands, fp32 accumulation in TMEM (tcgen05).
  *   a_mn_major = 0: A is [M,K] row-major;  1: A is [K,M] row-major (A^T is the logical operand)
  *   b_mn_major = 0: B is [N,K] row-major (nn.Linear weight);  1: B is [K,N] row-major
  *   splits > 1: split-K, requires CLIPK_EPI_ATOMIC_ADD into a pre-zeroed/accumulating fp32 output.
- * lda, ldb, N multiples of 8; base pointers 16-byte aligned.                                          */
+ * lda, ldb, N multiples of 8 (N: any value for CLIPK_EPI_RANK_COUNT); base pointers 16-byte aligned.   */
 int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N, int K,
                     const clipk_epilogue_t* epi, int splits, cudaStream_t stream);
 
@@ -178,6 +179,13 @@ int clipk_reduce_sum(const float* x, int n, float scale, float* out, int accumul
  * CLIPEvaluator's N x N matrix + per-row torch.sort (appzoo/clip/evaluator.py:47-61).                          */
 int clipk_retrieval_rank(const float* Q, const float* K, int label_offset, int* rank_out, int nq, int nk, int E,
                          cudaStream_t stream);
+/* The same ranks from the tensor cores (blocked retrieval, SURVEY 8f.1 / the 1 M x 1 M configuration): bf16 hi/lo splits of both
+ * sides (fp32-level dots, K = 3E), the match score thr_i = <Q_i, K_label(i)> per query, then ONE GEMM whose epilogue
+ * (CLIPK_EPI_RANK_COUNT) compares every accumulator with thr_i and adds the count to rank_out[i] -- the N x N matrix never exists.
+ * workspace: caller-owned device memory of clipk_retrieval_rank_tc_workspace(nq, nk, E) bytes.                                   */
+size_t clipk_retrieval_rank_tc_workspace(int nq, int nk, int E);
+int clipk_retrieval_rank_tc(const float* Q, const float* K, int label_offset, int* rank_out, int nq, int nk, int E,
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* -------------------------------------------------------------------------------------------- optimizer
  * Global-norm clip (core/trainer.py:325) + the reference AdamW (core/optimizers.py:437-462) over a flat buffer.

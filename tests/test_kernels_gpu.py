@@ -310,6 +310,29 @@ def test_ce_tensor_core_path(nq, nk, E, off, scale):
     assert_close(dls, lr.grad.view(1), 2e-3, 1e-3 * abs(lr.grad.item()) + 1e-4, "dscale")
 
 
+@pytest.mark.parametrize("nq,nk,E,off", [(24, 24, 128, 0), (100, 1000, 512, 300), (513, 2049, 512, 0), (64, 40, 768, -8)])
+def test_retrieval_rank_tensor_core(nq, nk, E, off):
+    """rank-count GEMM epilogue (no N x N matrix) == brute-force fp32 ranks; ragged nq / nk, labels partly outside the gallery"""
+    Q = torch.nn.functional.normalize(rnd(nq, E, seed=91), dim=-1)
+    K = torch.nn.functional.normalize(rnd(nk, E, seed=92), dim=-1)
+    lab = off + torch.arange(nq, device=DEV)
+    ok = (lab >= 0) & (lab < nk)
+    K[lab[ok]] = torch.nn.functional.normalize(K[lab[ok]] + 0.35 * Q[ok], dim=-1)        # matches rank high but not always first
+    S = (Q.double() @ K.double().t())
+    thr = torch.where(ok, S[torch.arange(nq, device=DEV), lab.clamp(0, nk - 1)], torch.full((nq,), float("inf"), device=DEV, dtype=torch.float64))
+    want = ((S > thr[:, None]) & (torch.arange(nk, device=DEV)[None, :] != lab[:, None])).sum(1).int()
+    margin = (S - thr[:, None]).abs()
+    margin[torch.arange(nq, device=DEV)[ok], lab[ok]] = 1.0
+    assert margin.min().item() > 1e-5                                       # no near-ties in this fixture: the ranks are well defined
+    got = torch.full((nq,), -1, device=DEV, dtype=torch.int32)
+    ops.retrieval_rank_tc(Q, K, got, label_offset=off)
+    assert torch.equal(got, want), (got[:8], want[:8])
+    ref = torch.empty(nq, device=DEV, dtype=torch.int32)
+    if off >= 0 and off + nq <= nk:
+        ops.retrieval_rank(Q, K, ref, label_offset=off)                     # the fp32 CUDA-core kernel agrees
+        assert torch.equal(ref, want)
+
+
 # --------------------------------------------------------------------------------------------- optimizer
 def test_adamw_and_gradnorm():
     from oracle import clip_oracle as O
