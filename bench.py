@@ -254,7 +254,8 @@ def run_native(args):
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
         roofline = {"bound": "tensor", "kernel": "clipk::gemm_bf16_kernel (tcgen05, all 3 operand-major variants)",
                     "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak, "peak_kind": peak_kind + " sustained cuBLAS bf16",
-                    "traffic": None, "launches_per_step": g[0], "gflop_per_launch": g[1] / max(1, g[0]) / 1e9,
+                    "traffic": _ncu_gemm_traffic(), "traffic_source": "profiles/r01_launches.json: mean dram__bytes_read+write per GEMM launch, ncu pass over one step of this command (--no-graph)",
+                    "launches_per_step": g[0], "gflop_per_launch": g[1] / max(1, g[0]) / 1e9,
                     "avg_launch_ms": g[2] / max(1, g[0]),
                     "step_breakdown_ms": {k: round(v[2], 3) for k, v in agg.items()} | {"step_total": round(ms_per_step, 3)},
                     "gemm_shapes_MxNxK|majors|mode": gemm_shapes,
@@ -282,6 +283,15 @@ def run_native(args):
         print(json.dumps(line), flush=True)
     if dist_on:
         torch.distributed.destroy_process_group()
+
+
+def _ncu_gemm_traffic():
+    """DRAM bytes per GEMM launch from the committed ncu launch list of this command (tools/launch_summary.py); None if absent"""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_launches.json")) as f:
+            return json.load(f)["gemm"]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def main():
