@@ -92,12 +92,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
-def oracle_cpu_throughput(batch, seq_len, steps, warmup):
+def oracle_cpu_throughput(batch, seq_len, steps, warmup, budget_s=60.0):
     """The reference algorithm on the host cores: oracle port (plain PyTorch fp32 restatement of the reference modules,
-    pinned against the reference in tests/golden) -- forward + loss + backward + clip + the reference's AdamW."""
+    pinned against the reference in tests/golden) -- forward + loss + backward + clip + the reference's AdamW.
+    Threads: min(logical CPUs, 32) -- at 8 pairs per step more intra-op threads are SLOWER (measured on the 128-thread GPU box:
+    0.15-0.5 pairs/s with all threads); CLIPK_CPU_THREADS overrides.  Timed steps stop early once `budget_s` is spent (>= 1 step)."""
     import torch
     from oracle import clip_oracle as O
-    cores = os.cpu_count() or 1
+    ncpu = os.cpu_count() or 1
+    cores = max(1, min(ncpu, int(os.environ.get("CLIPK_CPU_THREADS", "32"))))
     torch.set_num_threads(cores)
     cfg = b16_config()      # the oracle's dropout is the identity (no RNG work on the CPU arm)
     sd = O.init_state_dict(cfg, seed=1234)
@@ -106,10 +109,14 @@ def oracle_cpu_throughput(batch, seq_len, steps, warmup):
     for _ in range(warmup):
         O.train_step(sd, cfg, pixels, ids, st, lr=1e-5)
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
         O.train_step(sd, cfg, pixels, ids, st, lr=1e-5)
-    dt = (time.perf_counter() - t0) / max(1, steps)
-    return batch / dt, dt, cores
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / max(1, done)
+    return batch / dt, dt, cores, done, ncpu
 
 
 def run_reference(args):
@@ -118,14 +125,14 @@ def run_reference(args):
         return
     b = 8
     steps = max(1, min(args.steps, 8)); warmup = max(1, min(args.warmup, 1))
-    v, dt, cores = oracle_cpu_throughput(b, args.seq_len, steps, warmup)
+    v, dt, cores, steps, ncpu = oracle_cpu_throughput(b, args.seq_len, steps, warmup, budget_s=120.0)
     line = {"impl": "reference", "metric": "train_pairs_per_sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "CLIP ViT-B/16 + BERT-base contrastive training step, seq 77 (BASELINE configs[1])",
                        "sample": f"batch {b} pairs per step on the host CPU (bounded sample of the batch-256 workload)"},
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} steps x {b} pairs, fwd+loss+bwd+clip+AdamW, torch fp32, {cores} threads"},
+                             "sample": f"{steps} steps x {b} pairs, fwd+loss+bwd+clip+AdamW, torch fp32, {cores} threads of {ncpu} logical CPUs"},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -265,9 +272,9 @@ def run_native(args):
     # ---- CPU baseline: the oracle port on the host cores (rank 0, N = 1 only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, cores = oracle_cpu_throughput(8, Lt, 3, 1)
+        v, dt, cores, nst, ncpu = oracle_cpu_throughput(8, Lt, 3, 1, budget_s=30.0)
         cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-               "sample": f"3 steps x 8 pairs (of the 256-pair batch), fwd+loss+bwd+clip+AdamW, torch fp32, {cores} threads"}
+               "sample": f"{nst} steps x 8 pairs (of the 256-pair batch), fwd+loss+bwd+clip+AdamW, torch fp32, {cores} threads of {ncpu} logical CPUs"}
 
     if rank == 0:
         line = {"metric": "train_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
