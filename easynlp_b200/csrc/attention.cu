@@ -225,12 +225,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* smask = reinterpret_cast<float*>(sPd + ps_bytes);        // [256]
   float* sDp = smask + 256;                                       // [4][128] partial rowsum(dO o O) per column quarter
   float* scol = sDp + 512;                                        // [3][64] column sums of this head's dQ | dK | dV
-  uint64_t* bars = reinterpret_cast<uint64_t*>(scol + 192);       // kv, qdo[0], qdo[1], s, dp, dq
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scol + 192);       // kv, qdo[0], qdo[1], s, dp, dq, dk
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 7);
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmDO);
-    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_holder, 512);
@@ -269,7 +269,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t drow = (uint32_t)((b * p.H + h) * p.L + q);
     // ---- loads + S = Q K^T
     if (tid == 0) {
-      if (qt + 1 < p.q_tiles) {   // prefetch the next query tile into the other buffer (its last readers finished with tile qt-1)
+      if (qt + 1 < p.q_tiles) {   // prefetch the next query tile into the other buffer (its last reader was tile qt-1's dK MMA)
+        if (qt >= 1) mbar_wait(&bars[6], (qt - 1) & 1);
         mbar_expect_tx(&bars[1 + (buf ^ 1)], 2 * 16384);
         tma_load_2d(sQ0 + (buf ^ 1) * 16384, &tmQ, &bars[1 + (buf ^ 1)], h * 64, b * p.L + (qt + 1) * 128);
         tma_load_2d(sDO0 + (buf ^ 1) * 16384, &tmDO, &bars[1 + (buf ^ 1)], h * 64, b * p.L + (qt + 1) * 128);
@@ -398,13 +399,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);
       for (int t = 0; t < ksteps; ++t)
         umma_bf16(tmem, desc_k(aDS + (t >> 2) * 16384 + (t & 3) * 32), desc_mn(aK + t * 2048, 16384), idesc_dq, t > 0);
+      umma_commit(&bars[5]);     // dQ only: the threads read it out while the dK MMAs below still run
       const uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);
       for (int mt = 0; mt < n_kt; ++mt)
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
           umma_bf16(tmem + 384 + mt * 64, desc_mn(aDS + mt * 32768 + ks * 2048, 16384), desc_mn(aQ + ks * 2048, 16384), idesc_t,
                     (qt > 0 || ks > 0) ? 1u : 0u);
-      umma_commit(&bars[5]);
+      // dK reads the dS and Q tiles: the next query tile overwrites them only after ITS S = Q K^T has completed (pass 1), and MMAs of
+      // one thread complete in issue order, so that wait covers this one too; the epilogue waits on bars[6] explicitly
+      umma_commit(&bars[6]);
     }
     mbar_wait(&bars[5], ph);
     tc_fence_after();
@@ -438,6 +442,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 
   // ---- epilogue: dK, dV rows (one thread per key; quarters 0,1 write the two 32-column halves of dV, quarters 2,3 of dK)
+  mbar_wait(&bars[6], (p.q_tiles - 1) & 1);
+  tc_fence_after();
   for (int mt = 0; mt < n_kt; ++mt) {
     const int key = mt * 128 + q4 * 32 + lane;
     const bool kvalid = key < p.L;

@@ -798,18 +798,21 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   // many column tiles AND a B operand that cannot stay in the 126 MB L2 (the retrieval gallery): band rasterisation (tile_coords)
   p.group_m = (!pair && p.n_tiles > 64 && (size_t)N * (size_t)K * 2 > ((size_t)48 << 20)) ? 16 : 1;
   {
-    // pool of self-re-arming scheduler counters; consecutive launches rotate through it so that back-to-back GEMMs never share one
-    constexpr int POOL = 64;
-    static int* pool = nullptr;
+    // per-device pool of self-re-arming scheduler counters; consecutive launches rotate through it so that back-to-back GEMMs never share one
+    constexpr int POOL = 64, MAX_DEV = 64;
+    static int* pools[MAX_DEV] = {nullptr};
     static unsigned next = 0;
-    if (!pool) {
+    int dev = 0;
+    CLIPK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) { set_error("clipk_gemm_bf16: device ordinal %d out of range", dev); return CLIPK_ERR_ARG; }
+    if (!pools[dev]) {
       cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
       cudaStreamIsCapturing(stream, &cs);
-      if (cs != cudaStreamCaptureStatusNone) { set_error("clipk_gemm_bf16: first call (allocates the scheduler counters) must not happen during stream capture"); return CLIPK_ERR_CUDA; }
-      CLIPK_CUDA(cudaMalloc(&pool, POOL * 2 * sizeof(int)));
-      CLIPK_CUDA(cudaMemset(pool, 0, POOL * 2 * sizeof(int)));
+      if (cs != cudaStreamCaptureStatusNone) { set_error("clipk_gemm_bf16: the first call on a device (allocates the scheduler counters) must not happen during stream capture"); return CLIPK_ERR_CUDA; }
+      CLIPK_CUDA(cudaMalloc(&pools[dev], POOL * 2 * sizeof(int)));
+      CLIPK_CUDA(cudaMemset(pools[dev], 0, POOL * 2 * sizeof(int)));
     }
-    p.tile_counter = pool + 2 * (next++ % POOL);
+    p.tile_counter = pools[dev] + 2 * (next++ % POOL);
   }
 
   CUtensorMap tA, tB;
