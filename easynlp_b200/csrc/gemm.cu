@@ -305,6 +305,80 @@ __device__ __forceinline__ void epi_tile_tma(const GemmParams& p, const CUtensor
   }
 }
 
+// 16-epilogue-warp form of epi_tile_tma (EPI 6..9, opt-in: CLIPK_GEMM_EPI16=1): four warps per scheduler cover the TMEM / L2 / bulk-store
+// latencies by thread-level parallelism instead of software pipelining.  A warp owns [32 rows x BN/4 cols]; 576 threads leave 112
+// registers per thread, so there is no accumulator / multiplier prefetch, and ONE 2 KB staging tile per warp (GELU stores its two
+// tiles one after the other).
+template <int BN, int MODE>
+__device__ __forceinline__ void epi_tile_tma16(const GemmParams& p, const CUtensorMap* tmO, const CUtensorMap* tmO2, uint8_t* tile,
+                                               uint64_t* full_bar, uint32_t full_phase, uint32_t t_row, int row0, int col0, int lane, bool has_k) {
+  constexpr int CHUNKS = BN / 128;
+  constexpr bool GELU = MODE == CLIPK_EPI_QUICK_GELU || MODE == CLIPK_EPI_ERF_GELU;
+  constexpr bool AUX = MODE == CLIPK_EPI_MUL_AUX;
+  const clipk_epilogue_t& e = p.epi;
+  const int row = row0 + lane;
+  const float al = e.alpha;
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+  uint4 zc[4];
+  if (AUX) epi_load_aux_row(p, row, col0, zc);
+  mbar_wait(full_bar, full_phase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col = col0 + c * 32;
+    const bool live = has_k && col < p.N;                   // warp-uniform (N % 32 == 0 on this path)
+    uint32_t r[32];
+    tmem_ld_x32(t_row + c * 32, r);
+    if (AUX && c > 0) epi_load_aux_row(p, row, col, zc);
+    tmem_wait_ld();
+    if (!live) continue;
+    uint32_t o[16], o2[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + col) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float v0 = fmaf(__uint_as_float(r[4 * j]), al, b.x), v1 = fmaf(__uint_as_float(r[4 * j + 1]), al, b.y);
+      float v2 = fmaf(__uint_as_float(r[4 * j + 2]), al, b.z), v3 = fmaf(__uint_as_float(r[4 * j + 3]), al, b.w);
+      if (GELU) {
+        float a0, a1, a2, a3, g0, g1, g2, g3;
+        if (MODE == CLIPK_EPI_QUICK_GELU) { quick_gelu_both(v0, a0, g0); quick_gelu_both(v1, a1, g1); quick_gelu_both(v2, a2, g2); quick_gelu_both(v3, a3, g3); }
+        else                              { erf_gelu_both(v0, a0, g0);   erf_gelu_both(v1, a1, g1);   erf_gelu_both(v2, a2, g2);   erf_gelu_both(v3, a3, g3); }
+        o[2 * j] = pack_bf16x2(g0, g1); o[2 * j + 1] = pack_bf16x2(g2, g3);
+        o2[2 * j] = pack_bf16x2(a0, a1); o2[2 * j + 1] = pack_bf16x2(a2, a3);
+      } else {
+        if (AUX) {
+          const uint4 z = zc[j >> 1];
+          const uint32_t w0 = (j & 1) ? z.z : z.x, w1 = (j & 1) ? z.w : z.y;
+          v0 *= __uint_as_float(w0 << 16); v1 *= __uint_as_float(w0 & 0xffff0000u);
+          v2 *= __uint_as_float(w1 << 16); v3 *= __uint_as_float(w1 & 0xffff0000u);
+        }
+        r[4 * j] = __float_as_uint(v0); r[4 * j + 1] = __float_as_uint(v1); r[4 * j + 2] = __float_as_uint(v2); r[4 * j + 3] = __float_as_uint(v3);
+        o[2 * j] = pack_bf16x2(v0, v1); o[2 * j + 1] = pack_bf16x2(v2, v3);
+      }
+    }
+    if (!GELU && e.colsum) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (row < p.M) ? __uint_as_float(r[j]) : 0.f;
+      const float cs = colsum32(v, lane);
+      atomicAdd(e.colsum + col + lane, cs);
+    }
+#pragma unroll
+    for (int pass = 0; pass < (GELU ? 2 : 1); ++pass) {
+      if (lane == 0) tma_store_wait_read<0>();               // the tile is no longer being read by the previous bulk store
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t off = (uint32_t)lane * 64u + ((((uint32_t)j) ^ sw) << 4);
+        *reinterpret_cast<uint4*>(tile + off) = pass ? make_uint4(o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3])
+                                                     : make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_2d(pass ? tmO2 : tmO, tile, col, row0); tma_store_commit(); }
+    }
+  }
+}
+
 // Epilogue of CLIPK_EPI_RANK_COUNT: nothing is stored -- every accumulator of the warp's [32 rows x BN/2 cols] slice is compared with the
 // row's threshold (the score of the query's own match) and the number of larger ones goes to rank[row] with one atomic per row and tile.
 template <int BN>
@@ -342,13 +416,14 @@ __device__ __forceinline__ void epi_tile_rank(const GemmParams& p, uint64_t* ful
 //                 (a 3-stage ring + 4 staging tiles per warp was measured too: no gain at K = 768, -7 % at K = 3072);
 //      5 = CLIPK_EPI_RANK_COUNT (compare + count, no output matrix).
 template <int BN, int A_MN, int B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(EPI >= 6 ? 64 + 32 * 16 : GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                  const __grid_constant__ CUtensorMap tmO2, const GemmParams p) {
-  constexpr bool TMA_OUT = EPI >= 1 && EPI <= 4;
+  constexpr bool TMA_OUT = (EPI >= 1 && EPI <= 4) || EPI >= 6;
+  constexpr int EPW = EPI >= 6 ? 16 : EPI_WARPS;       // epilogue warps
   constexpr int NSTAGE = STAGES;
   constexpr int NBUF = 2;                         // 2 KB bf16 store tiles per epilogue warp (EPI == 0: one 4 KB fp32 slab)
-  constexpr int MODE = TMA_OUT ? EPI - 1 : 0;
+  constexpr int MODE = EPI >= 6 ? EPI - 6 : (TMA_OUT ? EPI - 1 : 0);
   using L = GemmSmem<BN>;
   // 1024-B aligned dynamic smem (SWIZZLE_128B atoms); indexing the __shared__ array directly keeps the address space known to
   // the compiler (LDS/STS instead of generic LD/ST)
@@ -372,8 +447,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sched_full[s], 1); mbar_init(&sched_empty[s], 1 + EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPW); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sched_full[s], 1); mbar_init(&sched_empty[s], 1 + EPW); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, 2 * BN);
@@ -471,8 +546,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ================================================================ epilogue warps: TMEM lane quarter = warp % 4, column half = (warp-2)/4
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int CHUNKS = BN / 32 / 2;        // 32-column chunks per warp
+    const int half = (warp - 2) >> 2;          // column half (8 epilogue warps) / column quarter (16)
+    constexpr int CHUNKS = BN / 32 / 2;        // 32-column chunks per warp (8-warp forms)
+    constexpr int WCOLS = BN / (EPW / 4);      // columns per epilogue warp
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t store_seq = 0;
     float* slab = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + (warp - 2) * 32 * 32;
@@ -485,16 +561,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&sched_empty[slot]);
       if (++slot == 2) { slot = 0; sphase ^= 1; }
       if (tile < 0) break;
-      epi_prefetch<BN>(p, tile, tiles_mn, q, half, lane);    // the id arrives >= 1 tile ahead of the accumulator: L2 prefetch of the epilogue inputs
+      if constexpr (EPI < 6) epi_prefetch<BN>(p, tile, tiles_mn, q, half, lane);    // the id arrives >= 1 tile ahead of the accumulator: L2 prefetch of the epilogue inputs
       const int ks = tile / tiles_mn;
       const int mn = tile - ks * tiles_mn;
       int mi, ni;
       tile_coords(p, mn, mi, ni);
       const int m0 = mi * BM;
-      const int n0 = ni * BN + half * (BN / 2);
+      const int n0 = ni * BN + half * WCOLS;
       const int k_begin = ks * p.k_per_split;
       const bool has_k = k_begin < p.K;   // an empty split contributes nothing (host never creates one, but be safe)
-      if constexpr (EPI == 5) {
+      if constexpr (EPI >= 6) {
+        epi_tile_tma16<BN, MODE>(p, &tmO, &tmO2, smem + L::EPI_OFFSET + (warp - 2) * 2048, &tmem_full[acc], acc_phase,
+                                 tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * WCOLS, m0 + q * 32, n0, lane, has_k);
+      } else if constexpr (EPI == 5) {
         epi_tile_rank<BN>(p, &tmem_full[acc], acc_phase, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2), m0 + q * 32, n0,
                           lane, has_k);
       } else if constexpr (TMA_OUT) {
@@ -557,7 +636,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   }
   const int tiles = p.m_tiles * p.n_tiles * p.splits;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(tA, tB, tO, tO2, p);
+  kern<<<grid, EPI >= 6 ? 64 + 32 * 16 : GEMM_THREADS, smem, stream>>>(tA, tB, tO, tO2, p);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;
@@ -867,7 +946,9 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     if (BN == 256) { CLIPK_DISPATCH(256) } else { CLIPK_DISPATCH(128) }
 #undef CLIPK_DISPATCH
   }
-  const int epi_id = 1 + ee.mode;   // ee.mode in 0..3 on this path
+  static int epi16 = -1;   // opt-in: 16 epilogue warps (CLIPK_GEMM_EPI16=1)
+  if (epi16 < 0) { const char* ev = getenv("CLIPK_GEMM_EPI16"); epi16 = (ev && ev[0] == '1') ? 1 : 0; }
+  const int epi_id = (epi16 ? 6 : 1) + ee.mode;   // ee.mode in 0..3 on this path
 #define CLIPK_DISPATCH_E(BN_, E_)                                                    \
   case E_:                                                                           \
     if (b_mn_major) return launch_gemm<BN_, 0, 1, E_>(tA, tB, tO, tO2, p, stream);   \
@@ -875,6 +956,7 @@ extern "C" int clipk_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
 #define CLIPK_DISPATCH_BN(BN_)                                                       \
   switch (epi_id) {                                                                  \
     CLIPK_DISPATCH_E(BN_, 1) CLIPK_DISPATCH_E(BN_, 2) CLIPK_DISPATCH_E(BN_, 3) CLIPK_DISPATCH_E(BN_, 4)      \
+    CLIPK_DISPATCH_E(BN_, 6) CLIPK_DISPATCH_E(BN_, 7) CLIPK_DISPATCH_E(BN_, 8) CLIPK_DISPATCH_E(BN_, 9)      \
     default: break;                                                                  \
   }
   if (BN == 256) { CLIPK_DISPATCH_BN(256) } else { CLIPK_DISPATCH_BN(128) }

@@ -1,5 +1,5 @@
 """A/B of the bf16 GEMM epilogue store path on the K = 768 shapes of the step (diagnostic, not a test).
-   run with CLIPK_GEMM_STORE=tma|lsu, CLIPK_GEMM_NO_TMA_OUT=1 for the transpose-through-smem path"""
+   run with CLIPK_GEMM_EPI16=1 for the 16-epilogue-warp variants, CLIPK_GEMM_NO_TMA_OUT=1 for the transpose-through-smem path"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,7 +12,7 @@ from gemm_bench import timeit
 def main():
     dev = "cuda"
     torch.manual_seed(0)
-    tag = os.environ.get("CLIPK_GEMM_STORE", "auto") + ("/old" if os.environ.get("CLIPK_GEMM_NO_TMA_OUT") == "1" else "")
+    tag = ("epi16" if os.environ.get("CLIPK_GEMM_EPI16") == "1" else "epi8") + ("/old" if os.environ.get("CLIPK_GEMM_NO_TMA_OUT") == "1" else "")
     for M in (50432, 19712):
         for N, K, b_mn, mode in ((2304, 768, 0, 0), (768, 768, 0, 0), (768, 768, 1, 0), (3072, 768, 0, 1), (3072, 768, 0, 2), (3072, 768, 1, 3), (768, 3072, 0, 0)):
             A = torch.randn(M, K, device=dev).bfloat16()
