@@ -1,6 +1,10 @@
 """CLIPPredictor -- drop-in for easynlp/appzoo/clip/predictor.py:32-153: rows with a text column (`first_sequence`) or a
 base64 image column (`second_sequence`) -> one modality's embedding per row, formatted as tab-joined floats under
-'text_feat' / 'image_feat'.  As in the reference, a row carrying both encodes only the text (predict() overwrites)."""
+'text_feat' / 'image_feat'.  As in the reference, a row carrying both encodes only the text (predict() overwrites).
+
+`feature_format` (new): "text" (default) is the reference's `'\t'.join(str(x))` (predictor.py:140-153, ~10 bytes and a
+float->str conversion per value: GBs of text at 1 M vectors); "numpy" hands back float32 arrays under the same keys, which
+SimplePredictorManager writes as ONE [rows, E] .npy file when the output file ends in .npy."""
 import json
 import os
 
@@ -27,6 +31,9 @@ class CLIPPredictor(Predictor):
         self.first_sequence = kwargs.pop("first_sequence", "first_sequence")
         self.second_sequence = kwargs.pop("second_sequence", "second_sequence")
         self.sequence_length = kwargs.pop("sequence_length", 128)
+        self.feature_format = kwargs.pop("feature_format", "text")
+        if self.feature_format not in ("text", "numpy"):
+            raise ValueError(f"feature_format must be 'text' or 'numpy', got {self.feature_format!r}")
 
     def preprocess(self, in_data):
         if not in_data:
@@ -61,8 +68,11 @@ class CLIPPredictor(Predictor):
             return self.multi_modal(output, feat=True)
 
     def postprocess(self, result):
-        if result["image_embeds"] is not None:
-            return [{"image_feat": "\t".join(str(x) for x in emb)} for emb in result["image_embeds"].detach().cpu().numpy()]
-        if result["text_embeds"] is not None:
-            return [{"text_feat": "\t".join(str(x) for x in emb)} for emb in result["text_embeds"].detach().cpu().numpy()]
+        fmt = getattr(self, "feature_format", "text")
+        for key, col in (("image_embeds", "image_feat"), ("text_embeds", "text_feat")):
+            if result.get(key) is not None:
+                embs = result[key].detach().float().cpu().numpy()
+                if fmt == "numpy":
+                    return [{col: emb} for emb in embs]
+                return [{col: "\t".join(str(x) for x in emb)} for emb in embs]
         return []

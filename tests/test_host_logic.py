@@ -73,3 +73,38 @@ def test_synthetic_batch_layout():
     sd = random_state_dict(cfg, seed=1)
     assert set(sd) == set(param_schema(cfg))
     assert float(sd["bert.embeddings.word_embeddings.weight"][0].abs().max()) == 0.0
+
+
+def test_predictor_feature_formats_and_npy_sink(tmp_path):
+    """postprocess contract (reference predictor.py:140-153) + the binary sink behind it; no GPU: the encoder is stubbed"""
+    from easynlp_b200.appzoo.clip.predictor import CLIPPredictor
+    from easynlp_b200.core.predictor import Predictor, SimplePredictorManager
+    emb = torch.arange(12, dtype=torch.float32).view(3, 4) / 7.0
+    p = CLIPPredictor.__new__(CLIPPredictor)                       # no checkpoint / GPU: only postprocess is exercised
+    p.feature_format = "text"
+    out = p.postprocess({"image_embeds": None, "text_embeds": emb})
+    assert [list(o) for o in out] == [["text_feat"]] * 3
+    assert out[1]["text_feat"] == "\t".join(str(x) for x in emb[1].numpy())         # byte-identical to the reference formatting
+    p.feature_format = "numpy"
+    out = p.postprocess({"image_embeds": emb, "text_embeds": emb * 2})
+    assert list(out[0]) == ["image_feat"] and out[2]["image_feat"].dtype == np.float32 and np.array_equal(out[2]["image_feat"], emb[2].numpy())
+
+    class Stub(Predictor):                                          # rows -> vectors that depend on the row, in batches of 2
+        def __init__(self, fmt): self.fmt = fmt
+        def run(self, rows):
+            vs = [np.full(4, float(r["idx"]), np.float32) for r in rows]
+            return [{"text_feat": v if self.fmt == "numpy" else "\t".join(str(x) for x in v)} for v in vs]
+
+    src = tmp_path / "in.tsv"
+    src.write_text("".join(f"{i}\ttext {i}\n" for i in range(5)))
+    dst = str(tmp_path / "feat.npy")
+    SimplePredictorManager(Stub("numpy"), str(src), "idx:str:1,first_sequence:str:1", dst, "text_feat", "idx", batch_size=2).run()
+    arr = np.load(dst)
+    assert arr.shape == (5, 4) and arr.dtype == np.float32 and np.array_equal(arr[:, 0], np.arange(5, dtype=np.float32))
+    assert open(dst + ".tsv").read().split() == [str(i) for i in range(5)]
+    with pytest.raises(TypeError):
+        SimplePredictorManager(Stub("text"), str(src), "idx:str:1,first_sequence:str:1", dst, "text_feat", "", batch_size=2).run()
+    txt = str(tmp_path / "feat.tsv")
+    SimplePredictorManager(Stub("text"), str(src), "idx:str:1,first_sequence:str:1", txt, "text_feat", "idx", batch_size=2).run()
+    lines = open(txt).read().splitlines()
+    assert len(lines) == 5 and lines[3].split("\t") == ["3.0"] * 4 + ["3"]
