@@ -8,7 +8,10 @@
  * Conventions
  *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless named host_*.
  *   - the caller owns every buffer (workspace included); no hidden allocation, no global state except
- *     a per-process error string and cached device attributes.
+ *     a per-process error string, cached device attributes and ONE 512-byte per-device pool of GEMM tile-scheduler
+ *     counters (allocated by the first clipk_gemm_bf16 call on a device, which therefore must not be inside a stream capture).
+ *   - one host thread per process drives the library (one process per GPU, as torch.distributed.launch does for the
+ *     reference); kernels are re-entrant per stream.
  *   - every function is asynchronous on `stream` and returns 0 on success or a negative CLIPK_ERR_*;
  *     clipk_last_error() then describes the failure.
  *   - bf16 = IEEE bfloat16 storage; "ld*" = leading dimension in ELEMENTS.
