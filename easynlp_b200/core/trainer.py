@@ -75,7 +75,7 @@ class Trainer(object):
         P = self.engine.params
         if "exp_avg" in opt:
             P.exp_avg.copy_(opt["exp_avg"].to(P.exp_avg.device)); P.exp_avg_sq.copy_(opt["exp_avg_sq"].to(P.exp_avg.device))
-            P.step = int(opt.get("step", 0))
+            self.engine.set_step(int(opt.get("step", 0)))      # host AND device step counters (Adam bias correction, schedule, dropout stream)
         self._start_epoch = int(meta.get("epoch", 0))
         self._global_step = int(meta.get("global_step", 0)) + 1
         self._sched_step = self._global_step // max(1, args.gradient_accumulation_steps)   # unlike the reference (quirk A.4-6) the schedule survives a resume

@@ -433,6 +433,12 @@ class ClipEngine:
         if self._reducer is not None:
             self._reducer.ready(self.params.ranges_for(prefix))
 
+    def set_step(self, n: int):
+        """Number of optimizer steps already taken (checkpoint resume): the host counter AND the device-resident one that feeds Adam's
+        bias correction, the on-device learning-rate schedule and the dropout stream."""
+        self.params.step = int(n)
+        self._dev_step.fill_(int(n))
+
     def optimizer_step(self, lr: float, weight_decay: float = 1e-4, max_grad_norm: float = 1.0, warmup_steps: int = 0, t_total: int = 0):
         """clip_grad_norm_(max_grad_norm) + AdamW(betas 0.9/0.999, eps 1e-6) with the reference's decay grouping.
         The step counter and {lr, bias-corrected step size} live on the device (clipk_adam_schedule), so the same launches can be

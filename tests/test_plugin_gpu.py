@@ -142,3 +142,37 @@ def test_evaluator_trainer_checkpoint_predictor(ckpt, tmp_path):
     # the tiny config uses 64x64 inputs while the dataset transform yields 224x224 -> only check the row contract on text here;
     # image rows are exercised by the ViT-B/16-sized predictor test below when memory allows
     assert abs(sum(float(x) ** 2 for x in rows[0]["text_feat"].split("\t")) - 1.0) < 1e-3
+
+
+def test_trainer_resume_restores_optimizer_state_and_step_counters(ckpt, tmp_path):
+    """--resume_from_checkpoint (trainer.py:139-156): weights, Adam moments, the optimizer step count on the host AND on the device (bias
+    correction / on-device schedule / dropout stream) and the data position come back"""
+    from easynlp_b200.appzoo import get_application_model
+    from easynlp_b200.core import Trainer
+    from easynlp_b200.utils import parse_args, set_args
+    d, cfg, sd = ckpt
+    out_dir = str(tmp_path / "out")
+    flags = ["--micro_batch_size", "8", "--epoch_num", "2", "--learning_rate", "1e-3", "--checkpoint_dir", out_dir, "--logging_steps", "1",
+             "--sequence_length", "16", "--pretrained_model_name_or_path", d, "--data_threads", "0", "--save_checkpoint_steps", "3",
+             "--save_all_checkpoints"]
+    args = set_args(parse_args(flags))
+    train = SynthDataset(cfg, 32, 16, seed=9)
+    model = get_application_model("clip", d, user_defined_parameters={"app_parameters": {}})
+    tr = Trainer(model=model, train_dataset=train, evaluator=None, args=args)
+    tr.train()                                                            # 8 steps; a step-numbered checkpoint every 3
+    eng = model.engine
+    assert eng.params.step == 8 and int(eng._dev_step.item()) == 8
+    prefix = os.path.join(out_dir, "pytorch_model_step_6")
+    assert os.path.exists(prefix + ".bin") and os.path.exists(prefix + ".meta.bin")
+    meta = torch.load(prefix + ".meta.bin", map_location="cpu")
+    assert meta["optimizer"]["step"] == 6 and meta["global_step"] == 5
+    args2 = set_args(parse_args(flags + ["--resume_from_checkpoint", prefix]))
+    model2 = get_application_model("clip", d, user_defined_parameters={"app_parameters": {}})
+    tr2 = Trainer(model=model2, train_dataset=train, evaluator=None, args=args2)
+    e2 = model2.engine
+    assert e2.params.step == 6 and int(e2._dev_step.item()) == 6 and tr2._global_step == 6 and tr2._sched_step == 6
+    assert torch.equal(e2.params.exp_avg.cpu(), meta["optimizer"]["exp_avg"]) and torch.equal(e2.params.exp_avg_sq.cpu(), meta["optimizer"]["exp_avg_sq"])
+    saved = torch.load(prefix + ".bin", map_location="cpu")
+    assert torch.equal(model2.state_dict()["chinese_clip.visual.proj"].cpu(), saved["chinese_clip.visual.proj"])
+    tr2.train()                                                           # the remaining 2 steps of epoch 1
+    assert e2.params.step == 8 and int(e2._dev_step.item()) == 8 and len(tr2._log) == 2
