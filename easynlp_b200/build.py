@@ -25,7 +25,8 @@ def _sources():
 
 def _digest():
     h = hashlib.sha256()
-    for f in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(PKG, "..", "include", "clipk.h")]:
+    for f in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(CSRC, "*.h"))) + \
+            [os.path.join(PKG, "..", "include", "clipk.h")]:
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
+#include "gemm_tiles.h"
 #include "../../include/clipk.h"
 
 namespace clipk {
@@ -35,18 +36,9 @@ struct GemmParams {
   clipk_epilogue_t epi;
 };
 
-// Tile id -> (row tile, column tile).  group_m == 1: column tiles fastest (the CTAs running together share a few A row tiles and all
-// of a small B).  group_m > 1 (B far larger than L2, e.g. the retrieval gallery): ids sweep a [group_m x n_tiles] band column by
-// column, so every B tile is fetched from HBM once per band instead of once per row tile.
+// tile id -> (row tile, column tile): gemm_tiles.h (also compiled for the host by tests/test_tile_coords_host.py)
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int mn, int& mi, int& ni) {
-  if (p.group_m <= 1) { mi = mn / p.n_tiles; ni = mn - mi * p.n_tiles; return; }
-  const int band = p.group_m * p.n_tiles;
-  const int g = mn / band;
-  const int first = g * p.group_m;
-  const int gm = min(p.group_m, p.m_tiles - first);
-  const int rem = mn - g * band;
-  ni = rem / gm;
-  mi = first + (rem - ni * gm);
+  tile_coords_raw(p.m_tiles, p.n_tiles, p.group_m, mn, mi, ni);
 }
 
 template <int BN>
