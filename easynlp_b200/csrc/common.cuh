@@ -229,11 +229,17 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t chunk16) {
 // ------------------------------------------------------------------------------------------ dropout (Philox4x32-10)
 // Counter-based RNG: the keep/drop decision of an element depends only on (seed, per-step device offset, site, element index), so
 // the backward kernels regenerate the forward masks instead of storing them.  One call yields 4 independent 32-bit draws.
-__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+// (__host__ too: tests/test_philox_host.py runs the Random123 known-answer vectors through this very function on the CPU)
+__host__ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+    const uint32_t hi0 = (uint32_t)(((uint64_t)0xD2511F53u * c0) >> 32), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = (uint32_t)(((uint64_t)0xCD9E8D57u * c2) >> 32), lo1 = 0xCD9E8D57u * c2;
+#endif
     c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
