@@ -2,18 +2,28 @@
 //
 //   D[M,N] = epilogue( A (*) B )      fp32 accumulation in TMEM
 //
+// What it replaces in the reference (all of them ATen/cuBLAS calls plus separate elementwise kernels there):
+//   * nn.Linear / F.linear of the ViT blocks -- in_proj + out_proj inside nn.MultiheadAttention and mlp.c_fc / c_proj
+//     (easynlp/modelzoo/models/clip/modeling_chineseclip.py:188-204), the patch nn.Conv2d as a GEMM over im2col rows (:224,237),
+//     `x @ self.proj` (:251) and `@ self.text_projection` (:349);
+//   * BERT's query/key/value/dense Linears (easynlp/modelzoo/models/bert/modeling_bert.py:145-147,264-268,329-346);
+//   * the activations fused as epilogues: QuickGELU x*sigmoid(1.702x) (modeling_chineseclip.py:179-181), erf-GELU
+//     (easynlp/modelzoo/activations.py:45-48), bias adds, and in backward the multiply by the saved derivative + bias-gradient sums;
+//   * autograd's dgrad / wgrad GEMMs of all of the above (no transposes materialised: see operand storage below);
+//   * the contrastive logits `logit_scale * text @ image.t()` (easynlp/appzoo/clip/model.py:148-149) through bf16 hi/lo splits, and
+//     CLIPEvaluator's N x N similarity + per-row sort (easynlp/appzoo/clip/evaluator.py:47-61) through the RANK_COUNT epilogue.
+//
 // Operand storage (both bf16, leading dimension in elements, multiple of 8):
 //   A K-major  : A[M, K] row-major (the activation in y = x W^T)           a_mn_major = 0
 //   A MN-major : A[K, M] row-major (dY in dW = dY^T X, contraction on rows) a_mn_major = 1
 //   B K-major  : B[N, K] row-major (an nn.Linear weight [out, in])          b_mn_major = 0
 //   B MN-major : B[K, N] row-major (W in dX = dY W, X in dW = dY^T X)       b_mn_major = 1
-// This covers every GEMM of the CLIP towers (reference ops K1, K3, K4, K8-K10 of SURVEY.md 2.3 and their
-// autograd counterparts) without materialising a transpose.
 //
-// Structure: grid = #SMs, static tile scheduler, 128 x BN output tile, BK = 64, 4-stage TMA->smem ring
-// (SWIZZLE_128B), one MMA-issuing thread (tcgen05.mma cta_group::1, M=128, N=BN, K=16), accumulators double-buffered
-// in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   warp 0: TMA producer   warp 1: MMA issuer + TMEM owner   warps 2-5: epilogue (TMEM -> registers -> global)
+// Structure: grid = #SMs, DYNAMIC tile scheduler (global atomic counter -> 2-deep smem queue), 128 x BN output tile, BK = 64,
+// 4-stage TMA->smem ring (SWIZZLE_128B), one MMA-issuing thread (tcgen05.mma cta_group::1, M=128, N=BN, K=16), accumulators
+// double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp 0: TMA producer + scheduler   warp 1: MMA issuer + TMEM owner   warps 2-9 (2-17 with CLIPK_GEMM_EPI16): epilogue
+//   epilogue variants: see the EPI template parameter below and profiles/r01_gemm_epilogue_tma.md
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
