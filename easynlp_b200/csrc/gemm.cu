@@ -5,7 +5,7 @@
 // What it replaces in the reference (all of them ATen/cuBLAS calls plus separate elementwise kernels there):
 //   * nn.Linear / F.linear of the ViT blocks -- in_proj + out_proj inside nn.MultiheadAttention and mlp.c_fc / c_proj
 //     (easynlp/modelzoo/models/clip/modeling_chineseclip.py:188-204), the patch nn.Conv2d as a GEMM over im2col rows (:224,237),
-//     `x @ self.proj` (:251) and `@ self.text_projection` (:349);
+//     `x @ self.proj` (:251) and `x[:, 0, :] @ self.text_projection` (:350);
 //   * BERT's query/key/value/dense Linears (easynlp/modelzoo/models/bert/modeling_bert.py:145-147,264-268,329-346);
 //   * the activations fused as epilogues: QuickGELU x*sigmoid(1.702x) (modeling_chineseclip.py:179-181), erf-GELU
 //     (easynlp/modelzoo/activations.py:45-48), bias adds, and in backward the multiply by the saved derivative + bias-gradient sums;
