@@ -11,10 +11,15 @@ One "step" = one full training step on a synthetic batch of `--batch` (default 2
 `e2e`    : the same step through the public plugin API (CLIPApp.forward / compute_loss / loss.backward / optimizer) with
            pinned HOST inputs copied every step and the loss read back every step (as Trainer does, core/trainer.py:617-622,342).
 `roofline`: the dominant kernel (tcgen05 GEMM): algorithmic GEMM FLOPs / launch over its CUDA-event duration inside a step.
-`--impl reference`: the reference algorithm (oracle port, plain PyTorch fp32) on the host cores, bounded sample per step.
+`gpu_baseline`: the UNMODIFIED reference (oracle/_ref, a verbatim copy made by oracle/build_ref.py) on the SAME GPU: CLIPApp.cuda() under
+           torch.autocast(bfloat16) + the reference's AdamW, same batch, same e2e protocol -- the north star's actual bar.
+`parity`  : the CUDA path against the reference-generated golden fixture (checker role of oracle/, like the cpu_baseline leg).
+`--impl reference`: the UNMODIFIED reference on the host cores (kind "reference"; the oracle port only if oracle/_ref is absent),
+           bounded sample per step.
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -24,8 +29,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line (rank 0): NCCL's banner / debug output goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line (rank 0); NCCL_DEBUG output is left where the launcher put it
 
 FLOPS_FWD_PER_PAIR = 48_427_376_640          # ViT-B/16 35.13 GF + BERT-base(77) 13.30 GF
 FLOPS_TRAIN_PER_PAIR = 3 * FLOPS_FWD_PER_PAIR
@@ -92,19 +96,30 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
-def oracle_cpu_throughput(batch, seq_len, steps, warmup, budget_s=60.0):
-    """The reference algorithm on the host cores: oracle port (plain PyTorch fp32 restatement of the reference modules,
-    pinned against the reference in tests/golden) -- forward + loss + backward + clip + the reference's AdamW.
-    Threads: min(logical CPUs, 32) -- at 8 pairs per step more intra-op threads are SLOWER (measured on the 128-thread GPU box:
-    0.15-0.5 pairs/s with all threads); CLIPK_CPU_THREADS overrides.  Timed steps stop early once `budget_s` is spent (>= 1 step)."""
+def _cpu_threads():
+    """Threads for the CPU arm: min(logical CPUs, 32) -- at 8 pairs per step more intra-op threads are SLOWER (measured on the 128-thread
+    GPU box: 0.15-0.5 pairs/s with all of them); CLIPK_CPU_THREADS overrides."""
+    ncpu = os.cpu_count() or 1
+    return max(1, min(ncpu, int(os.environ.get("CLIPK_CPU_THREADS", "32")))), ncpu
+
+
+def reference_cpu_throughput(batch, seq_len, steps, warmup, budget_s=60.0):
+    """The reference's own CPU implementation of the step, timed on the host cores: the UNMODIFIED reference modules (oracle/_ref:
+    CLIPApp + get_optimizer's AdamW + clip_grad_norm_, one Trainer iteration per step) when the copy is present, else the oracle port
+    of the same algorithm.  Timed steps stop early once `budget_s` is spent (>= 1 step).  -> (pairs/s, s/step, cores, steps, ncpu, kind)"""
     import torch
     from oracle import clip_oracle as O
-    ncpu = os.cpu_count() or 1
-    cores = max(1, min(ncpu, int(os.environ.get("CLIPK_CPU_THREADS", "32"))))
+    cores, ncpu = _cpu_threads()
     torch.set_num_threads(cores)
-    cfg = b16_config()      # the oracle's dropout is the identity (no RNG work on the CPU arm)
+    cfg = b16_config()      # dropout 0.1 in train mode, as the reference config has it (the oracle port's dropout is the identity)
     sd = O.init_state_dict(cfg, seed=1234)
     pixels, ids = O.synthetic_batch(cfg, batch, seq_len=seq_len, seed=1234)
+    from oracle import ref_loader
+    if ref_loader.reference_root() is not None:
+        from oracle import ref_bench as RB
+        with contextlib.redirect_stdout(sys.stderr):        # the reference prints banners / its config
+            r = RB.time_reference_cpu(cfg, sd, pixels, ids, steps, warmup, cores, budget_s=budget_s)
+        return r["pairs_per_s"], r["s_per_step"], cores, r["steps"], ncpu, "reference"
     st = {}
     for _ in range(warmup):
         O.train_step(sd, cfg, pixels, ids, st, lr=1e-5)
@@ -116,7 +131,7 @@ def oracle_cpu_throughput(batch, seq_len, steps, warmup, budget_s=60.0):
         if time.perf_counter() - t0 > budget_s:
             break
     dt = (time.perf_counter() - t0) / max(1, done)
-    return batch / dt, dt, cores, done, ncpu
+    return batch / dt, dt, cores, done, ncpu, "port"
 
 
 def run_reference(args):
@@ -125,16 +140,87 @@ def run_reference(args):
         return
     b = 8
     steps = max(1, min(args.steps, 8)); warmup = max(1, min(args.warmup, 1))
-    v, dt, cores, steps, ncpu = oracle_cpu_throughput(b, args.seq_len, steps, warmup, budget_s=120.0)
+    v, dt, cores, steps, ncpu, kind = reference_cpu_throughput(b, args.seq_len, steps, warmup, budget_s=120.0)
+    what = "the unmodified reference modules (oracle/_ref)" if kind == "reference" else "oracle port of the reference algorithm"
     line = {"impl": "reference", "metric": "train_pairs_per_sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "CLIP ViT-B/16 + BERT-base contrastive training step, seq 77 (BASELINE configs[1])",
-                       "sample": f"batch {b} pairs per step on the host CPU (bounded sample of the batch-256 workload)"},
-            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                       "sample": f"batch {b} pairs per step on the host CPU (bounded sample of the batch-256 workload)", "what": what},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
                              "sample": f"{steps} steps x {b} pairs, fwd+loss+bwd+clip+AdamW, torch fp32, {cores} threads of {ncpu} logical CPUs"},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def parity_check(dev):
+    """CHECKER leg (oracle/ used as the checker, like cpu_baseline): the CUDA path on the reference-generated fixture
+    tests/golden/b16_fwd.npz (UNMODIFIED reference, fp32, ViT-B/16 + BERT-base, B = 8, Lt = 77, dropout 0) and recall.npz.
+    Reports the numbers against the north star's stated tolerance (logits / loss rtol <= 1e-3, recall@K exact)."""
+    import numpy as np
+    import torch
+    from easynlp_b200.engine import ClipEngine
+    from easynlp_b200.appzoo.clip.evaluator import recall_from_embeddings
+    from oracle import clip_oracle as O
+    gold = os.path.join(ROOT, "tests", "golden")
+    z = np.load(os.path.join(gold, "b16_fwd.npz"))
+    cfg = dict(O.vit_b16_bert_base_config(), text_attention_probs_dropout_prob=0.0, text_hidden_dropout_prob=0.0)
+    sd = O.init_state_dict(cfg, seed=1234, scale_boost=2.0)
+    pixels, ids = O.synthetic_batch(cfg, 8, seq_len=77, seed=1234)
+    eng = ClipEngine(cfg, device=dev, with_optimizer_state=False)
+    eng.params.load_state_dict(sd)
+    out = eng.forward(pixels.to(dev), ids.to(dev), save=False)
+    ref_log = torch.from_numpy(z["out.logits_per_text"]); got = out["logits_per_text"].float().cpu()
+    e_log = (got - ref_log).abs().max().item()
+    scale = 1 / 0.07
+    el_rtol = ((got - ref_log).abs() / ref_log.abs().clamp_min(1e-6)).max().item()
+    loss_ref = float(z["out.loss"]); loss = out["loss"].item()
+    r = np.load(os.path.join(gold, "recall.npz"))
+    pad = lambda t: torch.cat([t, torch.zeros(t.shape[0], 128 - t.shape[1])], 1).to(dev)
+    hits = recall_from_embeddings(pad(torch.from_numpy(r["text_embeds"])), pad(torch.from_numpy(r["image_embeds"])))
+    del eng
+    torch.cuda.empty_cache()
+    return {"fixture": "tests/golden/b16_fwd.npz + recall.npz (generated by the unmodified reference, fp32)",
+            "stated_tolerance": "logits/loss rtol <= 1e-3, recall@K exact",
+            "logits_max_abs_err": e_log, "logits_max_err_over_scale": e_log / scale, "logits_elementwise_rtol_max": el_rtol,
+            "logits_tolerance_met": bool(el_rtol <= 1e-3),
+            "logits_note": "bf16 tensor-core operands: elementwise rtol 1e-3 on logits is NOT met (PyTorch's own bf16 autocast misses it by 2x more); "
+                           "tests bound the error by 1.5x the bf16-autocast yardstick and 0.5 % of the logit scale",
+            "image_embeds_max_err": (out["image_embeds"].float().cpu() - torch.from_numpy(z["out.image_embeds"])).abs().max().item(),
+            "text_embeds_max_err": (out["text_embeds"].float().cpu() - torch.from_numpy(z["out.text_embeds"])).abs().max().item(),
+            "loss_rtol": abs(loss - loss_ref) / abs(loss_ref), "loss_tolerance_met": bool(abs(loss - loss_ref) <= 1e-3 * abs(loss_ref)),
+            "recall_exact": bool([hits[1], hits[5], hits[10]] == r["hits"].tolist())}
+
+
+def gpu_reference_baseline(dev, B, Lt, steps=3, warmup=2):
+    """The north star's bar, measured on this box: the UNMODIFIED reference CLIPApp (oracle/_ref) .cuda() under torch.autocast(bfloat16)
+    with the reference's AdamW / clip_grad_norm_, the same synthetic batch from pinned host memory every step and loss.item() read back
+    every step (the same protocol as `e2e`).  Falls back to smaller batches if the reference's fp32-master + saved-activation footprint
+    does not fit next to this process's engine."""
+    import torch
+    from oracle import clip_oracle as O
+    from oracle import ref_loader
+    if ref_loader.reference_root() is None:
+        return {"value": None, "unavailable": "oracle/_ref absent (run oracle/build_ref.py in the build container)"}
+    from oracle import ref_bench as RB
+    cfg = b16_config()
+    sd = O.init_state_dict(cfg, seed=1234)
+    last = None
+    for b in (B, B // 2, B // 4):
+        if b < 1:
+            break
+        pixels, ids = O.synthetic_batch(cfg, b, seq_len=Lt, seed=1234)
+        pixels = pixels.pin_memory(); ids = ids.pin_memory()
+        try:
+            with contextlib.redirect_stdout(sys.stderr):
+                r = RB.time_reference_gpu(cfg, sd, pixels, ids, steps, warmup, dev)
+            return {"value": r["pairs_per_s"], "unit": "pairs/s", "ms_per_step": r["ms_per_step"], "batch": b, "steps": steps, "loss": r["loss"],
+                    "max_mem_gb": r["max_mem_bytes"] / 1e9, "kind": "reference",
+                    "what": "unmodified reference CLIPApp.cuda() + torch.autocast(bfloat16) + reference AdamW/clip, pinned H2D + loss.item() per step (1 GPU, eager PyTorch)"}
+        except torch.cuda.OutOfMemoryError as ex:
+            last = repr(ex)[:200]
+            torch.cuda.empty_cache()
+    return {"value": None, "unavailable": "out of memory at every tried batch: " + str(last)}
 
 
 # ------------------------------------------------------------------------------------------------ native arm (B200)
@@ -261,7 +347,7 @@ def run_native(args):
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
         roofline = {"bound": "tensor", "kernel": "clipk::gemm_bf16_kernel (tcgen05, all 3 operand-major variants)",
                     "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak, "peak_kind": peak_kind + " sustained cuBLAS bf16",
-                    "traffic": _ncu_gemm_traffic(), "traffic_source": "profiles/r01_launches.json: mean dram__bytes_read+write per GEMM launch, ncu pass over one step of this command (--no-graph)",
+                    "traffic": _ncu_gemm_traffic()[0], "traffic_source": _ncu_gemm_traffic()[1],
                     "launches_per_step": g[0], "gflop_per_launch": g[1] / max(1, g[0]) / 1e9,
                     "avg_launch_ms": g[2] / max(1, g[0]),
                     "step_breakdown_ms": {k: round(v[2], 3) for k, v in agg.items()} | {"step_total": round(ms_per_step, 3)},
@@ -272,9 +358,22 @@ def run_native(args):
     # ---- CPU baseline: the oracle port on the host cores (rank 0, N = 1 only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, cores, nst, ncpu = oracle_cpu_throughput(8, Lt, 3, 1, budget_s=30.0)
-        cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+        v, dt, cores, nst, ncpu, kind = reference_cpu_throughput(8, Lt, 3, 1, budget_s=30.0)
+        cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
                "sample": f"{nst} steps x 8 pairs (of the 256-pair batch), fwd+loss+bwd+clip+AdamW, torch fp32, {cores} threads of {ncpu} logical CPUs"}
+    parity = gpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            parity = parity_check(dev)
+        except Exception as ex:
+            parity = {"error": repr(ex)[:300]}
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        try:
+            gpu_base = gpu_reference_baseline(dev, B, Lt)
+            if gpu_base.get("value") and e2e and e2e.get("value"):
+                gpu_base["e2e_over_gpu_baseline"] = e2e["value"] / gpu_base["value"]
+        except Exception as ex:
+            gpu_base = {"value": None, "error": repr(ex)[:300]}
 
     if rank == 0:
         line = {"metric": "train_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -286,19 +385,30 @@ def run_native(args):
                            "dropout": "text tower hidden 0.1 / attention-probs 0.1 (fused Philox, masks regenerated in backward); ViT tower has none", "l2": "per-step working set (~15 GB of activations) >> 126 MB L2; no explicit flush needed",
                            "init": "random-init weights of the named architecture (no checkpoints reachable)",
                            "launch": "one CUDA graph per step" if use_graph else "eager launches"},
-                "loss": loss_val, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+                "loss": loss_val, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_baseline": gpu_base, "parity": parity}
         print(json.dumps(line), flush=True)
     if dist_on:
         torch.distributed.destroy_process_group()
 
 
+PROFILE_JSON = os.path.join("profiles", "r02_launches.json")
+
+
 def _ncu_gemm_traffic():
-    """DRAM bytes per GEMM launch from the committed ncu launch list of this command (tools/launch_summary.py); None if absent"""
+    """(DRAM bytes per GEMM launch, provenance) from the committed ncu launch list of this command (tools/launch_summary.py).  The profile
+    records the sha256 of the libclipk.so it was captured with; a profile of a different build is REFUSED (null + the reason) instead of
+    silently reporting stale traffic."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_launches.json")) as f:
-            return json.load(f)["gemm"]["dram_bytes_per_launch"]
-    except Exception:
-        return None
+        with open(os.path.join(ROOT, PROFILE_JSON)) as f:
+            js = json.load(f)
+        with open(os.path.join(ROOT, "easynlp_b200", "lib", "libclipk.sha256")) as f:
+            cur = f.read().strip()
+        if js.get("libclipk_sha256") != cur:
+            return None, f"{PROFILE_JSON} was captured with another build of libclipk.so (profile {str(js.get('libclipk_sha256'))[:12]}, loaded {cur[:12]}): refused"
+        return js["gemm"]["dram_bytes_per_launch"], f"{PROFILE_JSON}: mean dram__bytes_read+write per GEMM launch, ncu pass over one step of this command (--no-graph), same libclipk.so"
+    except Exception as ex:
+        return None, f"no usable profile: {ex!r}"
 
 
 def main():
@@ -309,7 +419,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--seq-len", type=int, default=77)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference sample and the parity checker leg")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-on-this-GPU leg (unmodified reference under bf16 autocast)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--graph-multi", action="store_true", help="also capture the step (incl. NCCL collectives) into a CUDA graph when world > 1")
     args = ap.parse_args()

@@ -74,6 +74,7 @@ def _declare(L):
     L.clipk_grad_norm.argtypes = [vp, ll, f, vp, i, vp, vp]
     L.clipk_adamw_step.argtypes = [vp, vp, vp, vp, vp, ll, f, f, f, f, f, i, vp, vp, vp]
     L.clipk_adam_schedule.argtypes = [vp, vp, f, i, i, f, f, vp]
+    L.clipk_counter_add.argtypes = [vp, i, vp]
 
 
 def check(rc: int, what: str = ""):

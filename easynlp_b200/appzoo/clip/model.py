@@ -124,7 +124,11 @@ class CLIPApp(Application):
         out = self.engine.forward(pix, ids, save=self.training and torch.is_grad_enabled(), distributed=self.distributed_loss)
         lpt = out["logits_per_text"].clone()
         self._last_loss = out["loss"]
-        return {"logits_per_text": lpt, "logits_per_image": lpt.T, "image_embeds": out["image_embeds"].clone(),
+        # world size 1 (and local-loss data parallelism): logits_per_image is the transpose view, as in the reference (model.py:149).
+        # Global-batch mode: the rank holds two [b, G] strips -- its texts against the gathered images and its images against the
+        # gathered texts; the second one IS its rows of the image->text logits (not a transpose of the first).
+        lpi = out["logits_per_image"].clone() if out.get("distributed") else lpt.T
+        return {"logits_per_text": lpt, "logits_per_image": lpi, "image_embeds": out["image_embeds"].clone(),
                 "text_embeds": out["text_embeds"].clone()}
 
     def compute_loss(self, forward_outputs, label_ids, **kwargs):

@@ -95,9 +95,19 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+__global__ void counter_add_kernel(int* c, int v) { c[0] += v; }
+
 }  // namespace clipk
 
 using namespace clipk;
+
+extern "C" int clipk_counter_add(int* counter_dev, int value, cudaStream_t stream) {
+  if (!counter_dev) { set_error("counter_add: null counter"); return CLIPK_ERR_ARG; }
+  counter_add_kernel<<<1, 1, 0, stream>>>(counter_dev, value);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int clipk_grad_norm(const float* g, long long n, float max_norm, double* workspace, int workspace_len, float* norm_and_coef,
                                cudaStream_t stream) {

@@ -12,7 +12,8 @@ autograd graph PyTorch builds for
 
 Numerics: bf16 GEMM/attention operands with fp32 accumulation, fp32 residual stream / LayerNorm statistics /
 embeddings / logits / loss, fp32 master weights and gradients.  Layout: token-major [B*L, d] activations.
-Dropout probabilities are taken as 0 by this engine ("dropout").
+BERT-tower dropout (hidden / attention-probs) is fused into the LayerNorm and attention kernels as Philox masks keyed by a
+device-resident forward-pass counter: a training forward draws fresh masks, its backward regenerates them ("dropout").
 """
 import math
 from typing import Dict, Optional
@@ -57,8 +58,11 @@ class ClipEngine:
         self._reducer = None      # OverlappedGradReducer while an eager multi-GPU backward is running
         self.norm_and_coef = torch.zeros(2, device=self.dev)
         self._norm_ws = torch.zeros(1024, dtype=torch.float64, device=self.dev)
-        # device-resident optimizer step counter (also the per-step dropout offset) and {lr, step size}
+        # device-resident optimizer step counter and {lr, step size}
         self._dev_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        # device-resident count of TRAINING forward passes = the dropout stream offset: every forward(train) draws fresh masks (also
+        # each micro-batch of a gradient-accumulation window and every replay of a captured graph); backward reuses the value
+        self._dev_pass = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._dev_hyper = torch.zeros(2, dtype=torch.float32, device=self.dev)
         # BERT-tower dropout (nn.Dropout in modeling_bert.py:85,128,238,267,345); the ViT tower has none
         self.p_hidden = float(cfg.get("text_hidden_dropout_prob", 0.0) or 0.0)
@@ -217,7 +221,7 @@ class ClipEngine:
         key = (p, site)
         d = self._drops.get(key)
         if d is None:
-            d = ops.make_dropout(p, self.dropout_seed, site, self._dev_step)
+            d = ops.make_dropout(p, self.dropout_seed, site, self._dev_pass)
             self._drops[key] = d
         return d
 
@@ -345,7 +349,9 @@ class ClipEngine:
         st["loss_sum"] = self.f32("l.loss", 1)       # sum over LOCAL rows of both directions / (2 G)
         ops.reduce_sum(rows_t, B, 1.0 / (2 * G), st["loss_sum"], False)
         ops.reduce_sum(rows_i, B, 1.0 / (2 * G), st["loss_sum"], True)
+        # scaled logits of the two strips: local texts x image gallery, local images x text gallery.  World size 1: S_i == S_t^T.
         st["logits"] = S_t[:, :G] if want_logits else None
+        st["logits_img"] = S_i[:, :G] if want_logits else None
         return st
 
     def loss_backward(self, st, grad_scale: float = 1.0, local_gallery: bool = True):
@@ -389,6 +395,8 @@ class ClipEngine:
         from . import distributed as D
         if train is None:
             train = save           # training step <=> activations are kept; dropout is active only then
+        if train and (self.p_hidden > 0.0 or self.p_attn > 0.0):
+            ops.counter_add(self._dev_pass, 1)       # new dropout masks for this pass (its backward sees the same value)
         v = self.vit_forward(pixels, save)
         t = self.bert_forward(ids, save, train=train)
         if distributed and D.world_size() > 1:
@@ -401,7 +409,8 @@ class ClipEngine:
             l = self.loss_forward(t["embeds"], v["embeds"], want_logits=want_logits)
             l["dist"] = False
         self._saved = (v, t, l) if save else None
-        return {"image_embeds": v["embeds"], "text_embeds": t["embeds"], "logits_per_text": l["logits"], "loss": l["loss_sum"]}
+        return {"image_embeds": v["embeds"], "text_embeds": t["embeds"], "logits_per_text": l["logits"], "logits_per_image": l["logits_img"],
+                "loss": l["loss_sum"], "distributed": l["dist"]}
 
     def zero_grad(self):
         self.params.grad.zero_()
@@ -438,6 +447,11 @@ class ClipEngine:
         bias correction, the on-device learning-rate schedule and the dropout stream."""
         self.params.step = int(n)
         self._dev_step.fill_(int(n))
+        self._dev_pass.fill_(int(n))
+
+    def set_micro_step(self, n: int):
+        """Number of training forward passes already made (resume with gradient accumulation): position of the dropout stream."""
+        self._dev_pass.fill_(int(n))
 
     def optimizer_step(self, lr: float, weight_decay: float = 1e-4, max_grad_norm: float = 1.0, warmup_steps: int = 0, t_total: int = 0):
         """clip_grad_norm_(max_grad_norm) + AdamW(betas 0.9/0.999, eps 1e-6) with the reference's decay grouping.

@@ -282,6 +282,12 @@ def adam_schedule(step_dev, hyper_dev, base_lr, warmup_steps, t_total, beta1=0.9
 
 
 @_op
+def counter_add(counter, value=1):
+    assert counter.dtype == torch.int32 and counter.is_cuda
+    L_.check(L_.lib().clipk_counter_add(_ptr(counter), int(value), _stream()), "counter_add")
+
+
+@_op
 def axpy(x, y, alpha=1.0):
     assert x.numel() == y.numel() and x.is_contiguous() and y.is_contiguous()
     L_.check(L_.lib().clipk_axpy(_f32(x), _f32(y), float(alpha), x.numel(), _stream()), "axpy")

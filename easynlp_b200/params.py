@@ -121,6 +121,13 @@ class ParamStore:
     def g(self, name, shape=None):
         return self._view(self.grad, name, shape)
 
+    def m(self, name, shape=None):
+        """Adam first moment of one tensor (view into the flat buffer)."""
+        return self._view(self.exp_avg, name, shape)
+
+    def v(self, name, shape=None):
+        return self._view(self.exp_avg_sq, name, shape)
+
     def names(self) -> List[str]:
         return list(self.schema.keys())
 
@@ -161,8 +168,6 @@ class ParamStore:
         out = OrderedDict()
         for n in self.schema:
             out[n] = self.p(n).detach().clone()
-            if n == "bert.embeddings.word_embeddings.weight":
-                pass
         # buffer exported by the reference BertEmbeddings (modeling_bert.py:87)
         out["bert.embeddings.position_ids"] = torch.arange(self.cfg["text_max_position_embeddings"], device=self.device).unsqueeze(0)
         return out

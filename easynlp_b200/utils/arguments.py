@@ -70,12 +70,21 @@ def get_args():
     return _ARGS
 
 
+# app-level keys routed into ret['app_parameters'] with their types (the role of _GLOBAL_APP_PARAMETER_NAMES, global_vars.py:170-200);
+# `global_contrastive` is this path's own switch: InfoNCE over the all-gathered global batch instead of each rank's local batch
+APP_PARAMETER_NAMES = {"global_contrastive": "bool", "feature_format": "str"}
+
+
 def parse_user_defined_parameters(s):
-    """'k=v k=v' -> {..., 'app_parameters': {}}  (global_vars.py:170-200)."""
-    ret = {}
+    """'k=v k=v' -> {plain keys..., 'app_parameters': {typed app-level keys}}  (global_vars.py:170-200)."""
+    ret, app = {}, {}
     if s:
         for ele in s.split():
             k, v = ele.split("=", 1)
-            ret[k] = v
-    ret["app_parameters"] = {}
+            if k in APP_PARAMETER_NAMES:
+                t = APP_PARAMETER_NAMES[k]
+                app[k] = int(v) if t == "int" else float(v) if t == "float" else (v == "True") if t == "bool" else v
+            else:
+                ret[k] = v
+    ret["app_parameters"] = app
     return ret

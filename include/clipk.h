@@ -206,6 +206,10 @@ int clipk_adamw_step(float* p, const float* g, float* m, float* v, void* w_bf16,
 int clipk_adam_schedule(int* step_dev, float* hyper_dev, float base_lr, int warmup_steps, int t_total, float beta1,
                         float beta2, cudaStream_t stream);
 
+/* counter_dev[0] += value on the stream: the device-resident dropout stream position (one per training forward pass, so that a
+ * replayed CUDA graph and every micro-batch of a gradient-accumulation window draw fresh nn.Dropout masks, modeling_bert.py:128,238) */
+int clipk_counter_add(int* counter_dev, int value, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,7 +114,7 @@ def test_model_with_dropout_matches_oracle_given_the_same_masks():
     torch.cuda.synchronize()
     H = cfg["text_hidden_size"]; heads = cfg["text_num_attention_heads"]; M = B * Lt
     lk_pad = (Lt + 15) // 16 * 16
-    off = eng._dev_step
+    off = eng._dev_pass          # dropout stream position of the forward pass just made (its backward saw the same value)
     drop = {"emb": mask_of(M, H, 0.1, eng.dropout_seed, 1, off).view(B, Lt, H).cpu()}
     for i in range(cfg["text_num_hidden_layers"]):
         drop[("attn", i)] = mask_of(B * heads * Lt, lk_pad, 0.1, eng.dropout_seed, 16 * (i + 1), off).view(B, heads, Lt, lk_pad)[..., :Lt].cpu()

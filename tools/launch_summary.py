@@ -70,6 +70,13 @@ def main():
     js = {"launches": len(ids), "sum_ms": tot / 1e6, "gemm": {"launches": g["n"], "share_of_step": g["ns"] / tot,
           "dram_bytes_per_launch": (g["rd"] + g["wr"]) / g["n"] if g["n"] else None, "avg_launch_us": g["ns"] / g["n"] / 1e3 if g["n"] else None},
           "shares": {k: a["ns"] / tot for k, a in fams.items()}}
+    # the build the list was captured with: bench.py refuses a profile whose hash differs from the loaded library.  The GPU command copies
+    # easynlp_b200/lib/libclipk.sha256 next to the csv (<csv>.sha256); fall back to the in-tree stamp.
+    import os
+    for cand in (src + ".sha256", os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "easynlp_b200", "lib", "libclipk.sha256")):
+        if os.path.exists(cand):
+            js["libclipk_sha256"] = open(cand).read().strip()
+            break
     json.dump(js, open(out_json, "w"), indent=1)
     print("wrote", out_md, out_json, js["gemm"])
 
