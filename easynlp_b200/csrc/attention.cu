@@ -12,31 +12,12 @@
 //
 // Input layout: packed projections qkv[B*L, 3*d] bf16 (Q | K | V column blocks, head h at columns h*64 of each block),
 // i.e. exactly the output of the in_proj / fused query-key-value GEMM; output ctx[B*L, d].
+#include <stdlib.h>
 #include "common.cuh"
+#include "attention_common.cuh"
 #include "../../include/clipk.h"
 
 namespace clipk {
-
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
-
-struct AttnParams {
-  int B, L, H, d;
-  int lk_pad;          // keys padded to a multiple of 16 (<= 256)
-  int q_tiles;         // ceil(L / 128)
-  float scale;         // 1/sqrt(64)
-  const float* mask;   // [B, L] additive key mask or null
-  bf16* ctx;           // fwd out [B*L, d]
-  float* lse;          // [B, H, L] natural-log LSE of the scaled+masked scores
-  const bf16* ctx_in;  // bwd in
-  const bf16* dctx;    // bwd in  [B*L, d]
-  bf16* dqkv;          // bwd out [B*L, 3d]
-  float* dqkv_colsum;  // bwd out (optional) [3d] += column sums of dqkv = gradient of the QKV projection bias
-  DropArg drop;        // dropout on the attention probabilities (modeling_bert.py:238); element (b,h,q,j): row = (b*H+h)*L+q, quad = j/4
-};
-
-__device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return umma_smem_desc(addr, 16, 1024); }                // K-major
-__device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo) { return umma_smem_desc(addr, lbo, 1024); }  // MN-major
 
 __device__ __forceinline__ void store_row8_sw128(uint8_t* tile_base, int row, int col, const float* v) {
   // 8 consecutive bf16 (cols col..col+7, col % 8 == 0) of row `row` in a [128-row x 64-col]-blocked SWIZZLE_128B tile
@@ -685,6 +666,9 @@ extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void*
   p.scale = 0.125f;
   p.mask = key_mask; p.ctx = (bf16*)ctx; p.lse = lse;
   p.drop = make_drop_arg(drop);
+  // default: the persistent warp-specialised pipeline (attention_fwd2.cu); CLIPK_ATTN_V1=1 selects the first-generation kernel (A/B runs)
+  { const char* ev = getenv("CLIPK_ATTN_DBG_PTR"); if (ev) p.dbg = reinterpret_cast<long long*>(strtoull(ev, nullptr, 0)); }
+  { const char* ev = getenv("CLIPK_ATTN_V1"); if (!(ev && ev[0] == '1')) return attention_fwd2(qkv, p, stream); }
   CUtensorMap tQ, tKV;
   if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, p.lk_pad))) return rc;
@@ -732,6 +716,9 @@ extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const
     return 0;
   }
   if (p.drop.on && L > 128) { set_error("attention_bwd: attention dropout is implemented for L <= 128 (the text tower)"); return CLIPK_ERR_UNSUPPORTED; }
+  // default for 128 < L <= 256 without a key mask (the ViT tower): the persistent warp-specialised pipeline (attention_bwd2.cu);
+  // CLIPK_ATTN_V1=1 selects the first-generation kernel (A/B runs)
+  { const char* ev = getenv("CLIPK_ATTN_V1"); if (!(ev && ev[0] == '1') && !key_mask) return attention_bwd2(qkv, p, stream); }
   CUtensorMap tQ, tKV, tDO;
   if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, p.lk_pad))) return rc;
