@@ -518,10 +518,16 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_wait(&bars[0], 0);
     tc_fence_after();
     const uint32_t idesc = umma_idesc_bf16(128, p.lk_pad, 0, 0);
+    // S = Q K^T and dP = dO V^T are independent accumulators: alternating their k-steps hides the accumulate latency of each chain
+    // (back-to-back MMAs into one accumulator were measured at ~90 cycles each, whatever N; attention_bwd2.cu)
+    {
+      const uint32_t dQ_ = umma_desc_lo(aQ, 16), dK_ = umma_desc_lo(aK, 16), dDO_ = umma_desc_lo(aDO, 16), dV_ = umma_desc_lo(aV, 16);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_k(aQ + k * 32), desc_k(aK + k * 32), idesc, k > 0);            // S = Q K^T
-#pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16(tmem + 128, desc_k(aDO + k * 32), desc_k(aV + k * 32), idesc, k > 0);     // dP = dO V^T
+      for (int k = 0; k < 4; ++k) {       // descriptors advance by one add on the low word (common.cuh: umma_bf16_lh)
+        umma_bf16_lh(tmem, dQ_ + 2 * k, dK_ + 2 * k, idesc, k > 0);
+        umma_bf16_lh(tmem + 128, dDO_ + 2 * k, dV_ + 2 * k, idesc, k > 0);
+      }
+    }
     umma_commit(&bars[1]);
   }
   // D = rowsum(dO o O): each column half takes 32 of the 64 head columns; the loads overlap the TMA + MMA latency
@@ -601,13 +607,15 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (tid == 0) {
     tc_fence_after();
     const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);
-    for (int t = 0; t < ksteps; ++t)
-      umma_bf16(tmem, desc_k(aDS + (t >> 2) * 16384 + (t & 3) * 32), desc_mn(aK + t * 2048, 16384), idesc_dq, t > 0);
     const uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);
+    const uint32_t mP = umma_desc_lo(aP, 16384), mDS = umma_desc_lo(aDS, 16384), mDO = umma_desc_lo(aDO, 16384), mQ = umma_desc_lo(aQ, 16384);
+    const uint32_t mK = umma_desc_lo(aK, 16384), kDS = umma_desc_lo(aDS, 16);
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) umma_bf16(tmem + 64, desc_mn(aDS + ks * 2048, 16384), desc_mn(aQ + ks * 2048, 16384), idesc_t, ks > 0);
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) umma_bf16(tmem + 128, desc_mn(aP + ks * 2048, 16384), desc_mn(aDO + ks * 2048, 16384), idesc_t, ks > 0);
+    for (int ks = 0; ks < 8; ++ks) {       // three independent accumulators, k-steps interleaved
+      umma_bf16_lh(tmem + 64, mDS + 128 * ks, mQ + 128 * ks, idesc_t, ks > 0);
+      umma_bf16_lh(tmem + 128, mP + 128 * ks, mDO + 128 * ks, idesc_t, ks > 0);
+      if (ks < ksteps) umma_bf16_lh(tmem, kDS + (ks >> 2) * 1024 + (ks & 3) * 2, mK + 128 * ks, idesc_dq, ks > 0);
+    }
     umma_commit(&bars[2]);
   }
   mbar_wait(&bars[2], 0);
@@ -718,6 +726,8 @@ extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const
   if (p.drop.on && L > 128) { set_error("attention_bwd: attention dropout is implemented for L <= 128 (the text tower)"); return CLIPK_ERR_UNSUPPORTED; }
   // default for 128 < L <= 256 without a key mask (the ViT tower): the persistent warp-specialised pipeline (attention_bwd2.cu);
   // CLIPK_ATTN_V1=1 selects the first-generation kernel (A/B runs)
+  { const char* ev = getenv("CLIPK_ATTN_DBG_PTR"); if (ev) p.dbg = reinterpret_cast<long long*>(strtoull(ev, nullptr, 0)); }
+  { const char* ev = getenv("CLIPK_ATTN_FLAGS"); if (ev) p.flags = atoi(ev); }
   { const char* ev = getenv("CLIPK_ATTN_V1"); if (!(ev && ev[0] == '1') && !key_mask) return attention_bwd2(qkv, p, stream); }
   CUtensorMap tQ, tKV, tDO;
   if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;

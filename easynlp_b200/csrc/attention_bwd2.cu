@@ -12,8 +12,12 @@
 //   warp 1      MMA issuer  : S/dP of step s+1 are issued BEFORE the gradient MMAs of step s, so they run during sweep s
 //   warps 4-19  sweep       : 4 TMEM lane quarters x 4 column quarters; the math of sweep s+1 overlaps the gradient MMAs of step s, only
 //               the short store burst into the single P/dS buffer waits for them
-//   warps 20-23 read-out    : dV_kt / dK_kt after the last query tile of a key tile, dQ_t after the last key tile -> dqkv (bf16) and the
-//               fused QKV-bias gradient (column sums of the fp32 accumulators)
+//   warps 20-23 read-out    : dV_kt / dK_kt after the last query tile of a key tile, dQ_t after the last key tile -> dqkv (bf16)
+//
+// Fused QKV-bias gradient (no key mask, no dropout on this path): the QUERY block is the column sum of the fp32 dQ accumulators
+// (read-out warps); the KEY block is identically zero -- a key bias shifts every score of a row by the same amount and softmax is shift
+// invariant -- so nothing is added; the VALUE block is sum_q (sum_k P[q,k]) dO[q,:] = the column sum of dO (rows of P sum to 1), taken by
+// the sweep warps from the dO values they load for D anyway (a 16-column butterfly per warp and query tile).
 //
 // TMEM (512 columns): S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ_0 [384,448) | dQ_1 [448,512).
 // Replaces autograd through nn.MultiheadAttention's SDPA (modeling_chineseclip.py:188,198-200).
@@ -51,6 +55,9 @@ __host__ __device__ inline Bwd2Smem bwd2_layout(int kn0) {
   s.total = s.bar_off + 256;
   return s;
 }
+
+// timeline probe (diagnostics): event e of step g of CTA 0
+#define B2_DBG(g, e) do { if (p.dbg && blockIdx.x == 0 && (g) < 64) p.dbg[(g) * 16 + (e)] = clock64(); } while (0)
 
 // 8 consecutive bf16 (cols col..col+7, col % 8 == 0) of row `row` in a [128-row x 64-col]-blocked SWIZZLE_128B tile
 __device__ __forceinline__ void st_row8_packed(uint8_t* tile_base, int row, int col, const uint32_t* pk) {
@@ -142,54 +149,67 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     } else if (warp == 1) {
       // ========================================================================================== MMA issuer (one thread)
-      if (lane == 0) {
+      if (elect_one()) {
         const int n_steps = my_items * STEPS;
         // step g -> (item ordinal jj, kt, t); Q/dO pair ordinal = jj*T + t; K/V tile ordinal = jj*KT + kt
         auto issue_sdp = [&](int g) {
           const int jj = g / STEPS, r = g - jj * STEPS, kt = r / T, t = r - kt * T;
           const int qi = jj * T + t, ki = jj * KT + kt;
           const int qs = qi % NQ, ks = ki & 1;
+          B2_DBG(g, 0);
           if (kt == 0) mbar_wait(&qdo_full[qs], (qi / NQ) & 1);       // first use of this Q/dO pair
           if (t == 0) mbar_wait(&kv_full[ks], (ki >> 1) & 1);          // first use of this K/V tile
+          B2_DBG(g, 1);
           mbar_wait(sdp_free, (g & 1) ^ 1);                            // sweep g-1 has pulled S/dP into registers
           tc_fence_after();
+          B2_DBG(g, 2);
           const uint32_t aQ = smem_u32(smem + lay.qdo_off + qs * 32768), aDO = aQ + 16384;
           const uint32_t aK = smem_u32(smem + lay.kv_off + ks * 2 * lay.kv_slot), aV = aK + lay.kv_slot;
           const uint32_t idesc = kt == 0 ? umma_idesc_bf16(128, KN0, 0, 0) : umma_idesc_bf16(128, KN1 > 0 ? KN1 : 16, 0, 0);
+          // K-major operands: k-step = 16 head dims = 32 B -> +2 on the descriptor's low word
+          const uint32_t dQ_ = umma_desc_lo(aQ, 16), dK_ = umma_desc_lo(aK, 16), dDO_ = umma_desc_lo(aDO, 16), dV_ = umma_desc_lo(aV, 16);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_k(aQ + k * 32), desc_k(aK + k * 32), idesc, k > 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + 128, desc_k(aDO + k * 32), desc_k(aV + k * 32), idesc, k > 0);
+          for (int k = 0; k < 4; ++k) {       // S and dP: independent accumulators, k-steps alternate
+            umma_bf16_lh(tmem, dQ_ + 2 * k, dK_ + 2 * k, idesc, k > 0);
+            umma_bf16_lh(tmem + 128, dDO_ + 2 * k, dV_ + 2 * k, idesc, k > 0);
+          }
           umma_commit(sdp_full);
         };
         auto issue_grads = [&](int g) {
           const int jj = g / STEPS, r = g - jj * STEPS, kt = r / T, t = r - kt * T;
           const int qi = jj * T + t, ki = jj * KT + kt;
           const int qs = qi % NQ, ks = ki & 1;
+          B2_DBG(g, 3);
           mbar_wait(pds_full, g & 1);
+          B2_DBG(g, 4);
           // accumulators must have been read out: dV/dK at the first query tile of a key tile, dQ_t at the first key tile
           if (t == 0) mbar_wait(kvacc_free, (ki & 1) ^ 1);
           if (kt == 0) mbar_wait(&dq_free[t], (jj & 1) ^ 1);
           tc_fence_after();
+          B2_DBG(g, 5);
           const uint32_t aQ = smem_u32(smem + lay.qdo_off + qs * 32768), aDO = aQ + 16384;
           const uint32_t aK = smem_u32(smem + lay.kv_off + ks * 2 * lay.kv_slot);
           const uint32_t aP = smem_u32(sP), aDS = smem_u32(sDS);
           const int kn16 = (kt == 0 ? KN0 : KN1) >> 4;
           constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);
           constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 0, 1);
-          // dV_kt += P^T dO_t
+          // dV_kt += P^T dO_t ; dK_kt += dS^T Q_t ; dQ_t += dS K_kt : three independent accumulators, k-steps interleaved.
+          // MN-major operands (P^T, dS^T, dO, Q, K): k-step = 16 rows of 128 B = 2048 B -> +128; block stride (LBO) 16 KB.
+          // dS as the K-major A operand of dQ: k-step = 32 B inside a 64-key block (+2), next block +16 KB (+1024).
+          const uint32_t mP = umma_desc_lo(aP, 16384), mDS = umma_desc_lo(aDS, 16384), mDO = umma_desc_lo(aDO, 16384), mQ = umma_desc_lo(aQ, 16384);
+          const uint32_t mK = umma_desc_lo(aK, 16384), kDS = umma_desc_lo(aDS, 16);
+          const uint32_t acc_kv = t > 0 ? 1u : 0u, acc_q = kt > 0 ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) umma_bf16(tmem + 256, desc_mn(aP + k * 2048, 16384), desc_mn(aDO + k * 2048, 16384), idesc_t, (t > 0 || k > 0) ? 1u : 0u);
-          // dK_kt += dS^T Q_t
-#pragma unroll
-          for (int k = 0; k < 8; ++k) umma_bf16(tmem + 320, desc_mn(aDS + k * 2048, 16384), desc_mn(aQ + k * 2048, 16384), idesc_t, (t > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k) {
+            umma_bf16_lh(tmem + 256, mP + 128 * k, mDO + 128 * k, idesc_t, k > 0 ? 1u : acc_kv);
+            umma_bf16_lh(tmem + 320, mDS + 128 * k, mQ + 128 * k, idesc_t, k > 0 ? 1u : acc_kv);
+            if (k < kn16) umma_bf16_lh(tmem + 384 + t * 64, kDS + (k >> 2) * 1024 + (k & 3) * 2, mK + 128 * k, idesc_q, k > 0 ? 1u : acc_q);
+          }
           if (t == T - 1) umma_commit(kvacc_full);
-          // dQ_t += dS K_kt
-          for (int k = 0; k < kn16; ++k)
-            umma_bf16(tmem + 384 + t * 64, desc_k(aDS + (k >> 2) * 16384 + (k & 3) * 32), desc_mn(aK + k * 2048, 16384), idesc_q, (kt > 0 || k > 0) ? 1u : 0u);
           umma_commit(pds_empty);
           if (t == T - 1) umma_commit(&kv_empty[ks]);        // K / V tile: last read by this step's dQ MMAs
           if (kt == KT - 1) { umma_commit(&dq_full[t]); umma_commit(&qdo_empty[qs]); }
+          B2_DBG(g, 6);
         };
         // program order: S/dP(0) | S/dP(1) grads(0) | S/dP(2) grads(1) | ...
         if (n_steps > 0) issue_sdp(0);
@@ -223,6 +243,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int ng = gbase + (cq < grem ? 1 : 0);
         float dpart = 0.f, lse2 = 0.f;
         if (kt == 0) {
+          float dov[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dov[j] = 0.f;
           // first visit of this query tile: D = rowsum(dO o O) (16 of the 64 head columns per column quarter) and the row's LSE;
           // the global loads are in flight while S / dP are still being computed
           if (qvalid) {
@@ -237,9 +260,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               for (int j = 0; j < 4; ++j) {
                 float2 a = __bfloat1622float2(o2[j]), c = __bfloat1622float2(g2[j]);
                 dpart += a.x * c.x + a.y * c.y;
+                dov[i * 8 + 2 * j] = c.x; dov[i * 8 + 2 * j + 1] = c.y;
               }
             }
             lse2 = p.lse[((long long)b * p.H + h) * p.L + q] * LOG2E;
+          }
+          if (p.dqkv_colsum) {
+            // value-bias gradient: sum_q (sum_k P[q,k]) dO[q,:] = column sums of dO (rows of P sum to 1; no mask / dropout on this path).
+            // The dO values are in registers anyway: one 16-column butterfly per warp and query tile, 16 global reductions.
+            const float cs = colsum16(dov, lane);
+            if (!(lane & 1)) atomicAdd(p.dqkv_colsum + 2 * p.d + h * 64 + cq * 16 + (lane >> 1), cs);
           }
           sDpart[cq * 128 + row] = dpart;
           named_bar_sync(1 + q4, 128);
@@ -252,8 +282,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         const float Dq = dpart;
         const float nl = qvalid ? -lse2 : -INFINITY;         // rows beyond L: P = exp2(-inf) = 0 exactly
+        if (warp == B2_SWEEP_WARP0 && lane == 0) B2_DBG(g, 8);
         mbar_wait(sdp_full, g & 1);
         tc_fence_after();
+        if (warp == B2_SWEEP_WARP0 && lane == 0) B2_DBG(g, 9);
         uint32_t ppk[16], dpk[16];                             // packed bf16 pairs of P and dS: 4 groups x 4 words
         const int key0 = kt * KN0;                             // first key of this key tile
 #pragma unroll
@@ -288,12 +320,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
         // the gradient MMAs of the previous step must have finished reading the P / dS tiles
+        if (warp == B2_SWEEP_WARP0 && lane == 0) B2_DBG(g, 10);
         mbar_wait(pds_empty, (g & 1) ^ 1);
+        if (warp == B2_SWEEP_WARP0 && lane == 0) B2_DBG(g, 11);
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi)
           if (gi < ng) { st_row8_packed(sP, row, (g0 + gi) * 8, ppk + gi * 4); st_row8_packed(sDS, row, (g0 + gi) * 8, dpk + gi * 4); }
         fence_proxy_async_smem();
         __syncwarp();
+        if (warp == B2_SWEEP_WARP0 && lane == 0) B2_DBG(g, 12);
+        if (p.dbg && lane == 0 && blockIdx.x == 0 && g < 64) atomicMax(reinterpret_cast<unsigned long long*>(p.dbg) + g * 16 + 13, (unsigned long long)clock64());
         if (lane == 0) mbar_arrive(pds_full);
       }
     }
@@ -309,7 +345,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t r[32];
         tmem_ld_x32(t_row + tcol + hh * 32, r);
         tmem_wait_ld();
-        if (p.dqkv_colsum) {
+        if (cs) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
@@ -340,8 +376,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int key = kt * KN0 + row;
         const bool kvalid = row < (kt == 0 ? KN0 : KN1) && key < p.L;
         bf16* dstk = p.dqkv + (long long)(b * p.L + key) * (3 * p.d) + h * 64;
-        emit(256, dstk + 2 * p.d, kvalid, scol + 128);
-        emit(320, dstk + p.d, kvalid, scol + 64);
+        emit(256, dstk + 2 * p.d, kvalid, nullptr);
+        emit(320, dstk + p.d, kvalid, nullptr);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(kvacc_free);
@@ -351,7 +387,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             mbar_wait(&dq_full[t], jj & 1);
             tc_fence_after();
             const int q = t * 128 + row;
-            emit(384 + t * 64, p.dqkv + (long long)(b * p.L + q) * (3 * p.d) + h * 64, q < p.L, scol);
+            emit(384 + t * 64, p.dqkv + (long long)(b * p.L + q) * (3 * p.d) + h * 64, q < p.L, p.dqkv_colsum ? scol : nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&dq_free[t]);
@@ -362,9 +398,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (p.dqkv_colsum) {
         named_bar_sync(5, 128);
         const int i = (warp - B2_OUT_WARP0) * 32 + lane;
-        for (int c = i; c < 192; c += 128) {
-          atomicAdd(p.dqkv_colsum + (c >> 6) * p.d + h * 64 + (c & 63), scol[c]);
-          scol[c] = 0.f;
+        if (i < 64) {      // query block only (key block: identically zero; value block: added by the sweep warps)
+          atomicAdd(p.dqkv_colsum + h * 64 + i, scol[i]);
+          scol[i] = 0.f;
         }
         named_bar_sync(5, 128);
       }

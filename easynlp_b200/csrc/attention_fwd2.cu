@@ -122,7 +122,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 1) {
     // ============================================================================================ MMA issuer (one thread)
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, KEYS, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
       const int n_tiles = ((n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * T;
@@ -136,8 +136,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         F2_DBG(k, 1);
         const uint32_t aK = smem_u32(smem + stage * lay.stage_bytes);
         const uint32_t aQ = aK + 2 * lay.kv_bytes + t * 16384;
+        const uint32_t dQ_ = umma_desc_lo(aQ, 16), dK_ = umma_desc_lo(aK, 16);       // K-major: k-step of 16 head dims = 32 B -> +2
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem + buf * BUF_STRIDE, desc_k(aQ + kk * 32), desc_k(aK + kk * 32), idesc_s, kk > 0);
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_lh(tmem + buf * BUF_STRIDE, dQ_ + 2 * kk, dK_ + 2 * kk, idesc_s, kk > 0);
         umma_commit(&s_full[buf]);
       };
       auto issue_pv = [&](int k) {          // O(k) = P(k) V
@@ -151,8 +152,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t aV = smem_u32(smem + stage * lay.stage_bytes + lay.kv_bytes);
         const uint32_t tbuf = tmem + buf * BUF_STRIDE;
         const uint32_t tO = O_SEP ? tmem + 448 : tbuf + 128;
+        const uint32_t dV_ = umma_desc_lo(aV, 16384);          // V as MN-major B: k-step of 16 keys = 2048 B -> +128
 #pragma unroll
-        for (int kk = 0; kk < N16; ++kk) umma_bf16_ts(tO, tbuf + kk * 8, desc_mn(aV + kk * 2048, 16384), idesc_o, kk > 0);
+        for (int kk = 0; kk < N16; ++kk) umma_bf16_ts_lh(tO, tbuf + kk * 8, dV_ + 128 * kk, idesc_o, kk > 0);
         umma_commit(O_SEP ? &o_full[0] : &o_full[buf]);
         if (t == T - 1) umma_commit(&stage_empty[stage]);
         F2_DBG(k, 3);

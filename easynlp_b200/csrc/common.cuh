@@ -223,6 +223,37 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// The same descriptor as two 32-bit halves.  The MMA-issuing thread is a single thread whose instruction stream is mostly descriptor
+// arithmetic: rebuilding the 64-bit descriptor (shift / mask / or) for every tcgen05.mma costs ~20 dependent integer instructions per
+// MMA -- more than the 32 cycles an M128 x N64 x K16 MMA takes (attention timelines: 23 MMAs issued in ~2300 cycles).  With the halves
+// kept apart, the next k-step's descriptor is ONE add on the low word: lo + (byte offset >> 4) (start addresses stay below 2^14 * 16 B).
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  constexpr uint32_t hi = umma_desc_hi(1024);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
+      : "memory");
+}
+// A operand from tensor memory
+__device__ __forceinline__ void umma_bf16_ts_lh(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  constexpr uint32_t hi = umma_desc_hi(1024);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
+      : "memory");
+}
+
 // byte offset of element (row r, 16-byte chunk c) inside a [rows x 128 B] SWIZZLE_128B tile whose base is 1024-B aligned
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t chunk16) { return r * 128u + ((chunk16 ^ (r & 7u)) << 4); }
 

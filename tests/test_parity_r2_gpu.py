@@ -214,7 +214,9 @@ def _two_rank_worker(rank, world, port, tmp, q):
         tr.train_step(dict(mb[1]), 1); tr.after_iter(1, 0, 0.0)
         assert tr._global_step == 1 and tr.engine.params.step == 1 and tr._sched_step == 1
         res["ga_param"] = tr.engine.params.p("visual.proj").detach().cpu().clone()
-        q.put((rank, res))
+        # plain numpy payload: torch tensors travel through a multiprocessing queue as shared-memory handles that die with this process
+        to_np = lambda v: {k: to_np(x) for k, x in v.items()} if isinstance(v, dict) else (v.numpy() if torch.is_tensor(v) else v)
+        q.put((rank, to_np(res)))
     finally:
         dist.destroy_process_group()
 
@@ -232,9 +234,10 @@ def test_two_real_ranks_on_one_gpu_global_loss_and_trainer_accumulation(tmp_path
     for p in procs:
         p.start()
     got = {}
+    to_t = lambda v: {k: to_t(x) for k, x in v.items()} if isinstance(v, dict) else (torch.from_numpy(v) if isinstance(v, np.ndarray) else v)
     for _ in range(world):
         r, res = q.get(timeout=600)
-        got[r] = res
+        got[r] = to_t(res)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
