@@ -52,7 +52,7 @@ def _declare(L):
     L.clipk_layernorm_fwd.argtypes = [vp, ll, vp, ll, vp, vp, vp, f, vp, vp, vp, vp, i, i, dp, i, vp]
     L.clipk_layernorm_bwd.argtypes = [vp, i, vp, vp, ll, vp, vp, vp, vp, vp, ll, vp, vp, vp, vp, i, i, dp, i, vp]
     L.clipk_colsum.argtypes = [vp, i, ll, vp, i, i, vp]
-    L.clipk_im2col_patches.argtypes = [vp, vp, i, i, i, vp]
+    L.clipk_im2col_patches.argtypes = [vp, vp, i, i, i, i, vp]
     L.clipk_vit_assemble.argtypes = [vp, vp, vp, vp, i, i, i, vp]
     L.clipk_vit_assemble_bwd.argtypes = [vp, vp, i, i, i, vp]
     L.clipk_bert_embed.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
@@ -75,6 +75,11 @@ def _declare(L):
     L.clipk_adamw_step.argtypes = [vp, vp, vp, vp, vp, ll, f, f, f, f, f, i, vp, vp, vp]
     L.clipk_adam_schedule.argtypes = [vp, vp, f, i, i, f, f, vp]
     L.clipk_counter_add.argtypes = [vp, i, vp]
+    L.clipk_position_ids.argtypes = [vp, vp, i, i, i, vp]
+    L.clipk_embed_gather.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    L.clipk_embed_gather_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    L.clipk_tanh_fwd.argtypes = [vp, vp, vp, ll, vp]
+    L.clipk_tanh_bwd.argtypes = [vp, vp, vp, vp, ll, vp]
 
 
 def check(rc: int, what: str = ""):

@@ -71,9 +71,10 @@ class CLIPDataset(Dataset):
                  second_sequence=None, label_enumerate_values=None, user_defined_parameters=None, skip_first_line=False, *args, **kwargs):
         with open(os.path.join(pretrained_model_name_or_path, "config.json"), "r") as f:
             self.raw_config = json.load(f)
-        if self.raw_config.get("model_type") != "chinese_clip":
-            raise NotImplementedError("only model_type == chinese_clip is on the B200 path")
-        self.model_type = "chinese_clip"
+        mt = self.raw_config.get("model_type")
+        if mt == "open_clip":
+            raise NotImplementedError("model_type == open_clip (BPE SimpleTokenizer, causal text tower) is not on the B200 path")
+        self.model_type = "chinese_clip" if mt == "chinese_clip" else "huggingface_clip"      # both use BertTokenizer (data.py:226-229)
         self.columns = parse_schema(input_schema)
         self.text_col = first_sequence
         self.image_col = second_sequence

@@ -1,7 +1,9 @@
-"""CLIPApp -- drop-in for easynlp/appzoo/clip/model.py:40-164 (model_type == chinese_clip) whose math runs in the clipk
-sm_100a kernels.  Same constructor / from_pretrained / forward(inputs, feat) / compute_loss contract, same `.config`
-wrapper, same state_dict key names (`chinese_clip.` prefix), so Trainer / CLIPEvaluator / CLIPPredictor
-written against the reference keep working.  There is no CPU or PyTorch fallback."""
+"""CLIPApp -- drop-in for easynlp/appzoo/clip/model.py:40-164 whose math runs in the clipk sm_100a kernels.  Two of the reference's
+three branches are implemented: model_type == "chinese_clip" (ViT + BertModel, model.py:64-72) and the default "huggingface_clip"
+branch (CLIPVisionModel, frozen by `.detach()`, + RobertaModel with its tanh pooler and biased projections, model.py:73-104,128-144);
+"open_clip" raises.  Same constructor / from_pretrained / forward(inputs, feat) / compute_loss contract, same `.config` wrapper, same
+state_dict key names (`chinese_clip.` prefix resp. `text_encoder.` / `vision_encoder.` / `*_projection.`), so Trainer /
+CLIPEvaluator / CLIPPredictor written against the reference keep working.  There is no CPU or PyTorch fallback."""
 import json
 import os
 from collections import OrderedDict
@@ -9,7 +11,7 @@ from collections import OrderedDict
 import torch
 
 from ..application import Application
-from ...engine import ClipEngine
+from ...engine import ClipEngine, hf_engine_config
 
 PREFIX = "chinese_clip."
 
@@ -57,16 +59,26 @@ class CLIPApp(Application):
         with open(os.path.join(path, "config.json"), "r") as f:
             self.raw_config = json.load(f)
         mt = self.raw_config.get("model_type")
-        if mt != "chinese_clip":
-            raise NotImplementedError(f"model_type={mt!r}: only the chinese_clip branch (ViT + BertModel, model.py:64-72 of the "
-                                      "reference) is implemented by the B200 path")
-        self.model_type = "chinese_clip"
-        self.config = Config_Wrapper(self.raw_config)
-        cfg = {k: v for k, v in self.raw_config.items()}
-        self.engine = ClipEngine(cfg, device=kwargs.get("device", "cuda"))
         ckpt = os.path.join(path, "pytorch_model.bin")
+        if mt == "open_clip":
+            raise NotImplementedError("model_type='open_clip' (causal text tower, model.py:56-63 of the reference) is not implemented by the B200 path")
+        self.config = Config_Wrapper(self.raw_config)
         checkpoint = torch.load(ckpt, map_location="cpu")
-        self.engine.params.load_state_dict({k.replace(PREFIX, ""): v for k, v in checkpoint.items()}, strict=False)
+        if mt == "chinese_clip":
+            self.model_type = "chinese_clip"
+            self.prefix = PREFIX
+            cfg = {k: v for k, v in self.raw_config.items()}
+        else:
+            # every other config takes the reference's huggingface_clip branch (model.py:73-104): nested text_config / vision_config,
+            # checkpoint keys used as they are, projection width read off the checkpoint
+            self.model_type = "huggingface_clip"
+            self.prefix = ""
+            if "text_projection.weight" not in checkpoint:
+                raise KeyError("huggingface_clip checkpoint without text_projection.weight")
+            cfg = hf_engine_config(self.raw_config, checkpoint["text_projection.weight"].shape[0])
+        self.engine = ClipEngine(cfg, device=kwargs.get("device", "cuda"))
+        self.engine.params.load_state_dict({(k[len(self.prefix):] if self.prefix and k.startswith(self.prefix) else k): v for k, v in checkpoint.items()},
+                                           strict=False)
         self._wrap_params()
         self.distributed_loss = bool((user_defined_parameters or {}).get("app_parameters", {}).get("global_contrastive", False)) \
             if isinstance(user_defined_parameters, dict) else False
@@ -74,14 +86,16 @@ class CLIPApp(Application):
     # ------------------------------------------------------------------ parameters (reference names, shared storage)
     def _wrap_params(self):
         P = self.engine.params
+        pre = getattr(self, "prefix", PREFIX)
+        self.prefix = pre
         self._plist = OrderedDict()
         for n in P.names():
-            self._plist[PREFIX + n] = torch.nn.Parameter(P.p(n), requires_grad=True)
+            self._plist[pre + n] = torch.nn.Parameter(P.p(n), requires_grad=True)
 
     def _publish_grads(self):
         P = self.engine.params
         for n in P.trainable_names():
-            self._plist[PREFIX + n].grad = P.g(n)
+            self._plist[self.prefix + n].grad = P.g(n)
 
     def named_parameters(self, prefix="", recurse=True, remove_duplicate=True):
         for n, p in self._plist.items():
@@ -93,10 +107,11 @@ class CLIPApp(Application):
 
     def state_dict(self, *args, **kwargs):
         sd = self.engine.params.state_dict()
-        return OrderedDict((PREFIX + k, v) for k, v in sd.items())
+        return OrderedDict((self.prefix + k, v) for k, v in sd.items())
 
     def load_state_dict(self, state_dict, strict=True):
-        self.engine.params.load_state_dict({k.replace(PREFIX, ""): v for k, v in state_dict.items()}, strict=False)
+        pre = self.prefix
+        self.engine.params.load_state_dict({(k[len(pre):] if pre and k.startswith(pre) else k): v for k, v in state_dict.items()}, strict=False)
 
     def zero_grad(self, set_to_none=False):
         self.engine.zero_grad()
@@ -118,10 +133,17 @@ class CLIPApp(Application):
             pix = pix.float().contiguous()
         if ids is not None:
             ids = ids.long().contiguous()
+        # the huggingface_clip branch feeds the batch's token_type_ids / attention_mask to the text tower (model.py:132-134); chinese_clip
+        # ignores them and masks with ids != 0 (quirk A.4-3)
+        tt = am = None
+        if self.model_type == "huggingface_clip" and ids is not None:
+            tt = inputs.get("token_type_ids"); am = inputs.get("attention_mask")
+            tt = tt if torch.is_tensor(tt) else None; am = am if torch.is_tensor(am) else None
         if feat is True:    # outputs are copies: the engine reuses its buffers on the next call
-            return {k: (v.clone() if v is not None else None) for k, v in self.engine.encode(pix, ids).items()}
+            return {k: (v.clone() if v is not None else None) for k, v in self.engine.encode(pix, ids, token_type_ids=tt, attention_mask=am).items()}
         assert pix is not None and ids is not None, "text and image cannot both be None!"
-        out = self.engine.forward(pix, ids, save=self.training and torch.is_grad_enabled(), distributed=self.distributed_loss)
+        out = self.engine.forward(pix, ids, save=self.training and torch.is_grad_enabled(), distributed=self.distributed_loss,
+                                  token_type_ids=tt, attention_mask=am)
         lpt = out["logits_per_text"].clone()
         self._last_loss = out["loss"]
         # world size 1 (and local-loss data parallelism): logits_per_image is the transpose view, as in the reference (model.py:149).

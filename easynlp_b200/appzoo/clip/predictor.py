@@ -20,9 +20,10 @@ class CLIPPredictor(Predictor):
         super().__init__()
         with open(os.path.join(model_dir, "config.json"), "r") as f:
             self.raw_config = json.load(f)
-        if self.raw_config.get("model_type") != "chinese_clip":
-            raise NotImplementedError("only model_type == chinese_clip is on the B200 path")
-        self.model_type = "chinese_clip"
+        mt = self.raw_config.get("model_type")
+        if mt == "open_clip":
+            raise NotImplementedError("model_type == open_clip (BPE SimpleTokenizer, causal text tower) is not on the B200 path")
+        self.model_type = "chinese_clip" if mt == "chinese_clip" else "huggingface_clip"      # both use BertTokenizer (data.py:226-229)
         self.tokenizer = BertTokenizer.from_pretrained(os.path.join(model_dir, "vocab.txt"))
         if model_cls is None:
             from .model import CLIPApp as model_cls

@@ -170,7 +170,8 @@ class Trainer(object):
         if ga == 1:
             out = self.engine.train_step(batch["pixel_values"], batch["input_ids"], lr=args.learning_rate, weight_decay=args.weight_decay,
                                          max_grad_norm=args.max_grad_norm, warmup_steps=self._warmup_steps, t_total=self._t_total,
-                                         distributed=dist_loss, use_graph=self.use_graph)
+                                         distributed=dist_loss, use_graph=self.use_graph,
+                                         token_type_ids=batch.get("token_type_ids"), attention_mask=batch.get("attention_mask"))
             self._sched_step += 1
             return self._global_loss(out["loss"])
         forward_outputs = self._model(batch)

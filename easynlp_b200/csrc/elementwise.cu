@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x,
 // ------------------------------------------------------------------------------------------------ patch im2col
 // pixels f32 [B,3,R,R] -> patches bf16 [B*g*g, 3*P*P], column = c*P*P + i*P + j  (== conv1.weight.view(W, -1) order,
 // modeling_chineseclip.py:224,237).  P % 2 == 0.
-__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ pix, bf16* __restrict__ out, int B, int R, int P, int g) {
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ pix, bf16* __restrict__ out, int B, int R, int P, int g, int ld) {
   const int kdim = 3 * P * P;
   const long long total2 = (long long)B * g * g * kdim / 2;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total2; t += (long long)gridDim.x * blockDim.x) {
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ p
     const int px = (int)(rowi % g), py = (int)((rowi / g) % g), b = (int)(rowi / ((long long)g * g));
     const int c = col / (P * P), i = (col / P) % P, j = col % P;
     const float2 v = *reinterpret_cast<const float2*>(pix + (((long long)b * 3 + c) * R + (py * P + i)) * R + px * P + j);
-    *reinterpret_cast<uint32_t*>(out + e) = pack_bf16x2(v.x, v.y);
+    *reinterpret_cast<uint32_t*>(out + rowi * ld + col) = pack_bf16x2(v.x, v.y);
   }
 }
 
@@ -278,6 +278,82 @@ __global__ void __launch_bounds__(256) bert_embed_bwd_kernel(const long long* __
   for (int c = lane * 4; c < H; c += 128) {
     float4 v = ld_f4(de + (long long)row * H + c);
     atomicAdd(reinterpret_cast<float4*>(dword + id * H + c), v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RoBERTa-style embeddings
+// position ids of create_position_ids_from_input_ids (modeling_roberta.py:1497-1510): pos = cumsum(ids != pad) * (ids != pad) + pad.
+// One warp per sequence: 32 tokens per step, warp-inclusive scan of the 0/1 flags plus the running count.
+__global__ void __launch_bounds__(256) position_ids_kernel(const long long* __restrict__ ids, int* __restrict__ pos, int B, int L, int pad) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  int run = 0;
+  for (int l0 = 0; l0 < L; l0 += 32) {
+    const int l = l0 + lane;
+    const int m = (l < L && ids[(long long)b * L + l] != pad) ? 1 : 0;
+    int x = m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (l < L) pos[(long long)b * L + l] = (run + x) * m + pad;
+    run += __shfl_sync(0xffffffffu, x, 31);
+  }
+}
+// e[row,:] = word[ids[row]] + pos_table[pos_ids[row]] + type_table[type_ids[row]]  (RobertaEmbeddings.forward, modeling_roberta.py:100-130)
+// key_mask[row] = (1 - attention_mask[row]) * -10000 (modeling_utils.py:438-439), or from ids != pad when no mask is given
+__global__ void __launch_bounds__(256) embed_gather_kernel(const long long* __restrict__ ids, const int* __restrict__ pos_ids,
+                                                           const long long* __restrict__ type_ids, const long long* __restrict__ attn_mask,
+                                                           const float* __restrict__ word, const float* __restrict__ pos,
+                                                           const float* __restrict__ type, float* __restrict__ e, float* __restrict__ key_mask,
+                                                           int rows, int H, int vocab, int npos, int ntype, int pad) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  long long id = ids[row];
+  if (id < 0 || id >= vocab) id = pad;
+  int pi = pos_ids[row]; if (pi < 0 || pi >= npos) pi = 0;
+  long long ti = type_ids ? type_ids[row] : 0; if (ti < 0 || ti >= ntype) ti = 0;
+  if (key_mask && lane == 0) key_mask[row] = attn_mask ? (1.0f - (float)attn_mask[row]) * -10000.0f : (id == pad ? -10000.0f : 0.0f);
+  for (int c = lane * 4; c < H; c += 128) {
+    float4 w = ld_f4(word + id * H + c), p = ld_f4(pos + (long long)pi * H + c), t = ld_f4(type + ti * H + c);
+    st_f4(e + (long long)row * H + c, make_float4(w.x + p.x + t.x, w.y + p.y + t.y, w.z + p.z + t.z, w.w + p.w + t.w));
+  }
+}
+// scatter of de into the three tables; the padding rows of nn.Embedding(padding_idx=pad) (word and position tables) get no gradient
+__global__ void __launch_bounds__(256) embed_gather_bwd_kernel(const long long* __restrict__ ids, const int* __restrict__ pos_ids,
+                                                               const long long* __restrict__ type_ids, const float* __restrict__ de,
+                                                               float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
+                                                               int rows, int H, int vocab, int npos, int ntype, int pad) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long id = ids[row];
+  const int pi = pos_ids[row];
+  long long ti = type_ids ? type_ids[row] : 0; if (ti < 0 || ti >= ntype) ti = 0;
+  const bool wok = id >= 0 && id < vocab && id != pad, pok = pi >= 0 && pi < npos && pi != pad;
+  for (int c = lane * 4; c < H; c += 128) {
+    const float4 v = ld_f4(de + (long long)row * H + c);
+    if (wok) atomicAdd(reinterpret_cast<float4*>(dword + id * H + c), v);
+    if (pok) atomicAdd(reinterpret_cast<float4*>(dpos + (long long)pi * H + c), v);
+    atomicAdd(reinterpret_cast<float4*>(dtype + ti * H + c), v);
+  }
+}
+// y = tanh(x) (BertPooler / RobertaPooler activation, modeling_bert.py:529-541); dx = dy * (1 - y^2)
+__global__ void __launch_bounds__(256) tanh_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, bf16* __restrict__ y_bf16, long long n4) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+    const float4 a = ld_f4(x + t * 4);
+    const float4 o = make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w));
+    st_f4(y + t * 4, o);
+    if (y_bf16) st_bf4(y_bf16 + t * 4, o);
+  }
+}
+__global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                                                       bf16* __restrict__ dx_bf16, long long n4) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+    const float4 g = ld_f4(dy + t * 4), v = ld_f4(y + t * 4);
+    const float4 o = make_float4(g.x * (1.f - v.x * v.x), g.y * (1.f - v.y * v.y), g.z * (1.f - v.z * v.z), g.w * (1.f - v.w * v.w));
+    if (dx) st_f4(dx + t * 4, o);
+    if (dx_bf16) st_bf4(dx_bf16 + t * 4, o);
   }
 }
 
@@ -420,11 +496,13 @@ extern "C" int clipk_colsum(const void* x, int is_f32, long long ldx, float* out
   return 0;
 }
 
-extern "C" int clipk_im2col_patches(const float* pixels, void* patches_bf16, int B, int R, int P, cudaStream_t stream) {
+extern "C" int clipk_im2col_patches(const float* pixels, void* patches_bf16, int B, int R, int P, int ld_out, cudaStream_t stream) {
   if (R % P || P % 2) { set_error("im2col: R=%d P=%d unsupported", R, P); return CLIPK_ERR_UNSUPPORTED; }
   const int g = R / P;
+  if (ld_out <= 0) ld_out = 3 * P * P;
+  if (ld_out < 3 * P * P || (ld_out % 2)) { set_error("im2col: ld_out=%d < 3*P*P or odd", ld_out); return CLIPK_ERR_ARG; }
   const long long total2 = (long long)B * g * g * 3 * P * P / 2;
-  im2col_kernel<<<grid_for(total2, 256 * 4), 256, 0, stream>>>(pixels, (bf16*)patches_bf16, B, R, P, g);
+  im2col_kernel<<<grid_for(total2, 256 * 4), 256, 0, stream>>>(pixels, (bf16*)patches_bf16, B, R, P, g, ld_out);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;
@@ -458,6 +536,52 @@ extern "C" int clipk_bert_embed(const long long* ids, const float* word, const f
 extern "C" int clipk_bert_embed_bwd(const long long* ids, const float* de, float* dword, int rows, int H, int vocab, cudaStream_t stream) {
   if (H % 4) { set_error("bert_embed_bwd: H %% 4 != 0"); return CLIPK_ERR_ARG; }
   bert_embed_bwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, de, dword, rows, H, vocab);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_position_ids(const long long* ids, int* pos_ids, int B, int L, int pad_id, cudaStream_t stream) {
+  if (B <= 0 || L <= 0) return 0;
+  position_ids_kernel<<<(B + 7) / 8, 256, 0, stream>>>(ids, pos_ids, B, L, pad_id);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_embed_gather(const long long* ids, const int* pos_ids, const long long* type_ids, const long long* attn_mask,
+                                  const float* word, const float* pos, const float* type, float* e, float* key_mask, int rows, int H,
+                                  int vocab, int npos, int ntype, int pad_id, cudaStream_t stream) {
+  if (H % 4) { set_error("embed_gather: H %% 4 != 0"); return CLIPK_ERR_ARG; }
+  embed_gather_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, pos_ids, type_ids, attn_mask, word, pos, type, e, key_mask, rows, H, vocab, npos, ntype, pad_id);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_embed_gather_bwd(const long long* ids, const int* pos_ids, const long long* type_ids, const float* de, float* dword,
+                                      float* dpos, float* dtype, int rows, int H, int vocab, int npos, int ntype, int pad_id,
+                                      cudaStream_t stream) {
+  if (H % 4) { set_error("embed_gather_bwd: H %% 4 != 0"); return CLIPK_ERR_ARG; }
+  embed_gather_bwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, pos_ids, type_ids, de, dword, dpos, dtype, rows, H, vocab, npos, ntype, pad_id);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_tanh_fwd(const float* x, float* y, void* y_bf16, long long n, cudaStream_t stream) {
+  if (n % 4) { set_error("tanh_fwd: n %% 4 != 0"); return CLIPK_ERR_ARG; }
+  if (n == 0) return 0;
+  tanh_fwd_kernel<<<grid_for(n / 4, 256 * 4), 256, 0, stream>>>(x, y, (bf16*)y_bf16, n / 4);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_tanh_bwd(const float* dy, const float* y, float* dx, void* dx_bf16, long long n, cudaStream_t stream) {
+  if (n % 4) { set_error("tanh_bwd: n %% 4 != 0"); return CLIPK_ERR_ARG; }
+  if (n == 0) return 0;
+  tanh_bwd_kernel<<<grid_for(n / 4, 256 * 4), 256, 0, stream>>>(dy, y, dx, (bf16*)dx_bf16, n / 4);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

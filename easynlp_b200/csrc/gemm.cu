@@ -507,8 +507,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (atomicAdd(p.tile_counter + 1, 1) == (int)gridDim.x - 1) { p.tile_counter[0] = 0; p.tile_counter[1] = 0; __threadfence(); }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (one thread)
-    if (lane == 0) {
+    // ================================================================ MMA issuer (one thread; elect.sync lets ptxas keep the issue loop in
+    // the uniform datapath without a per-MMA "for each active lane" loop)
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -531,11 +532,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sB = sA + L::A_BYTES;
+          // descriptors as (lo, hi) halves: the next k-step is one add on the low word (K-major: 16 elements = 32 B -> +2; MN-major: 16 rows
+          // of 128 B = 2048 B -> +128) instead of rebuilding 64-bit descriptors (common.cuh: umma_bf16_lh)
+          const uint32_t da = A_MN ? umma_desc_lo(sA, BK * 128) : umma_desc_lo(sA, 16);
+          const uint32_t db = B_MN ? umma_desc_lo(sB, BK * 128) : umma_desc_lo(sB, 16);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? umma_smem_desc(sA + k * 2048, BK * 128, 1024) : umma_smem_desc(sA + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? umma_smem_desc(sB + k * 2048, BK * 128, 1024) : umma_smem_desc(sB + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, accumulate);
+            umma_bf16_lh(d_tmem, da + (A_MN ? 128 : 2) * k, db + (B_MN ? 128 : 2) * k, idesc, accumulate);
             accumulate = 1;
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it

@@ -35,23 +35,78 @@ def _splits_for(m, n, k):
     return max(1, min(s, max(1, k // 256)))
 
 
+def hf_engine_config(raw: dict, embed_dim: int) -> dict:
+    """Flat engine config of the huggingface_clip branch from the reference's nested config.json ({'text_config': CLIPTextConfig kwargs,
+    'vision_config': CLIPVisionConfig kwargs}, appzoo/clip/model.py:82-85; defaults of modelzoo/models/clip/configuration_clip.py:88-120,
+    203-235).  embed_dim = rows of text_projection.weight in the checkpoint (model.py:93-96)."""
+    t = dict(vocab_size=21128, hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+             max_position_embeddings=512, hidden_act="gelu", layer_norm_eps=1e-12, pad_token_id=0, type_vocab_size=2,
+             hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+    t.update(raw.get("text_config", {}))
+    v = dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12, image_size=224, patch_size=32,
+             hidden_act="quick_gelu", layer_norm_eps=1e-5, attention_dropout=0.0)
+    v.update(raw.get("vision_config", {}))
+    if float(v.get("attention_dropout", 0.0) or 0.0) != 0.0:
+        raise NotImplementedError("vision attention_dropout > 0 is not on the hot path (the reference default is 0)")
+    return dict(model_type="huggingface_clip", embed_dim=int(embed_dim), image_resolution=v["image_size"], vision_layers=v["num_hidden_layers"],
+                vision_width=v["hidden_size"], vision_patch_size=v["patch_size"], vision_heads=v["num_attention_heads"],
+                vision_intermediate_size=v["intermediate_size"], vision_hidden_act=v["hidden_act"],
+                vocab_size=t["vocab_size"], text_hidden_size=t["hidden_size"], text_intermediate_size=t["intermediate_size"],
+                text_num_hidden_layers=t["num_hidden_layers"], text_num_attention_heads=t["num_attention_heads"],
+                text_max_position_embeddings=t["max_position_embeddings"], text_type_vocab_size=t["type_vocab_size"],
+                text_hidden_act=t["hidden_act"], text_layer_norm_eps=t["layer_norm_eps"], text_pad_token_id=t["pad_token_id"],
+                text_hidden_dropout_prob=t["hidden_dropout_prob"], text_attention_probs_dropout_prob=t["attention_probs_dropout_prob"],
+                text_initializer_range=t.get("initializer_range", 0.02))
+
+
 class ClipEngine:
     def __init__(self, cfg: dict, device="cuda", with_optimizer_state: bool = True):
         if isinstance(cfg.get("vision_layers"), (tuple, list)):
             raise NotImplementedError("ModifiedResNet visual towers are outside the hot path (ViT only)")
         self.cfg = cfg
+        self.kind = cfg.get("model_type", "chinese_clip")
+        self.hf = self.kind == "huggingface_clip"
+        if self.kind not in ("chinese_clip", "huggingface_clip"):
+            raise NotImplementedError(f"model_type {self.kind!r}")
         self.dev = torch.device(device)
         self.W = cfg["vision_width"]; self.P = cfg["vision_patch_size"]; self.R = cfg["image_resolution"]
         self.E = cfg["embed_dim"]; self.g = self.R // self.P; self.Lv = self.g * self.g + 1
         self.Hv = self.W // 64                                   # modeling_chineseclip.py:289
+        self.Iv = cfg.get("vision_intermediate_size", 4 * self.W)
         self.H = cfg["text_hidden_size"]; self.I = cfg["text_intermediate_size"]; self.Ht = cfg["text_num_attention_heads"]
         self.nv = cfg["vision_layers"]; self.nt = cfg["text_num_hidden_layers"]
         if self.H != self.Ht * 64 or self.W % 128 or self.H % 128 or self.E % 128:
             raise NotImplementedError("clipk kernels need head_dim 64 and widths that are multiples of 128")
-        if (3 * self.P * self.P) % 8:
-            raise NotImplementedError("patch dim 3*P*P must be a multiple of 8 (pad the patch matrix for ViT-*/14)")
+        if self.hf and cfg["vision_heads"] * 64 != self.W:
+            raise NotImplementedError("clipk attention needs head_dim 64 in the vision tower")
+        self.kdim = 3 * self.P * self.P
+        self.kdim_pad = (self.kdim + 7) // 8 * 8                 # ViT-L/14: 588 -> 592 (TMA rows are 16-byte multiples)
+        if self.kdim_pad != self.kdim and not self.hf:
+            raise NotImplementedError("patch dim 3*P*P % 8 != 0 is supported for frozen (forward-only) image towers only")
         if cfg.get("text_hidden_act", "gelu") != "gelu":
             raise NotImplementedError("text tower activation must be erf-GELU")
+        self.vit_act = L.EPI_QUICK_GELU
+        if self.hf:
+            va = cfg.get("vision_hidden_act", "quick_gelu")
+            if va not in ("quick_gelu", "gelu"):
+                raise NotImplementedError(f"vision hidden_act {va!r}")
+            self.vit_act = L.EPI_QUICK_GELU if va == "quick_gelu" else L.EPI_ERF_GELU
+        self.text_eps = float(cfg.get("text_layer_norm_eps", 1e-12))   # modeling_chineseclip.py:311 / CLIPTextConfig.layer_norm_eps
+        self.pad_id = int(cfg.get("text_pad_token_id", 0))
+        # parameter names of the two branches (SURVEY.md A.3)
+        if self.hf:
+            v = "vision_encoder.vision_model."
+            self.vn = {"conv": v + "embeddings.patch_embedding.weight", "cls": v + "embeddings.class_embedding",
+                       "pos": v + "embeddings.position_embedding.weight", "ln_pre": v + "pre_layrnorm", "ln_post": v + "post_layernorm",
+                       "layer": v + "encoder.layers.{}.", "ln1": "layer_norm1", "ln2": "layer_norm2", "qkv_w": "self_attn.q_proj.weight",
+                       "qkv_b": "self_attn.q_proj.bias", "out": "self_attn.out_proj", "fc1": "mlp.fc1", "fc2": "mlp.fc2"}
+            self.tp = "text_encoder."
+        else:
+            self.vn = {"conv": "visual.conv1.weight", "cls": "visual.class_embedding", "pos": "visual.positional_embedding",
+                       "ln_pre": "visual.ln_pre", "ln_post": "visual.ln_post", "layer": "visual.transformer.resblocks.{}.", "ln1": "ln_1",
+                       "ln2": "ln_2", "qkv_w": "attn.in_proj_weight", "qkv_b": "attn.in_proj_bias", "out": "attn.out_proj",
+                       "fc1": "mlp.c_fc", "fc2": "mlp.c_proj"}
+            self.tp = "bert."
         self.params = ParamStore(cfg, device, with_optimizer_state)
         self._buf: Dict[tuple, torch.Tensor] = {}
         self._saved = None
@@ -69,6 +124,7 @@ class ClipEngine:
         self.p_attn = float(cfg.get("text_attention_probs_dropout_prob", 0.0) or 0.0)
         self.dropout_seed = 0x5EED_C11B
         self._drops = {}
+        self._conv_pad = None; self._conv_pad_version = -1
 
     # ------------------------------------------------------------------ buffers
     def buf(self, name, shape, dtype):
@@ -95,70 +151,98 @@ class ClipEngine:
         return self.buf(name, shape, torch.float32)
 
     # ------------------------------------------------------------------ ViT
+    def _conv_operand(self):
+        """patch-embedding weight as the [W, kdim_pad] bf16 GEMM operand (zero-padded copy when 3*P*P is not a multiple of 8)"""
+        P_ = self.params
+        if self.kdim_pad == self.kdim:
+            return P_.w(self.vn["conv"], (self.W, self.kdim))
+        if self._conv_pad is None or self._conv_pad_version != P_.version:
+            if self._conv_pad is None:
+                self._conv_pad = torch.zeros((self.W, self.kdim_pad), dtype=torch.bfloat16, device=self.dev)
+            self._conv_pad[:, :self.kdim].copy_(P_.w(self.vn["conv"], (self.W, self.kdim)))
+            self._conv_pad_version = P_.version
+        return self._conv_pad
+
     def vit_forward(self, pixels: torch.Tensor, save: bool):
-        P_ = self.params; W = self.W; B = pixels.shape[0]; Lv = self.Lv; M = B * Lv; Hh = self.Hv
+        """VisualTransformer.forward (modeling_chineseclip.py:219-253) / CLIPVisionTransformer.forward (modeling_clip.py:731-776): the two
+        towers are the same pre-LN ViT; the HF one stores q/k/v separately (adjacent here -> one packed projection), takes its MLP width
+        and activation from the config and ends in a biased `vision_projection` Linear instead of the `proj` matrix."""
+        P_ = self.params; W = self.W; B = pixels.shape[0]; Lv = self.Lv; M = B * Lv; Hh = self.Hv; vn = self.vn; Iv = self.Iv
         assert pixels.dtype == torch.float32 and pixels.is_contiguous() and pixels.shape[1:] == (3, self.R, self.R)
         npatch = B * self.g * self.g
-        kdim = 3 * self.P * self.P
-        patches = self.bf("v.patches", npatch, kdim)
+        patches = self.zbuf("v.patches", (npatch, self.kdim_pad), torch.bfloat16)
         ops.im2col_patches(pixels, patches, B, self.R, self.P)
         patch_out = self.f32("v.patch_out", npatch, W)
-        ops.gemm(patches, P_.w("visual.conv1.weight", (W, kdim)), patch_out)
+        ops.gemm(patches, self._conv_operand(), patch_out)
         x0 = self.f32("v.x0", M, W)
-        ops.vit_assemble(patch_out, P_.p("visual.class_embedding"), P_.p("visual.positional_embedding"), x0, B, Lv, W)
+        ops.vit_assemble(patch_out, P_.p(vn["cls"]), P_.p(vn["pos"]), x0, B, Lv, W)
         x = self.f32("v.x.0", M, W)
         st = {"B": B, "mean0": self.f32("v.mean0", M), "rstd0": self.f32("v.rstd0", M), "layers": []}
-        ops.layernorm_fwd(x0, P_.p("visual.ln_pre.weight"), P_.p("visual.ln_pre.bias"), 1e-5, None, x, st["mean0"], st["rstd0"])
+        ops.layernorm_fwd(x0, P_.p(vn["ln_pre"] + ".weight"), P_.p(vn["ln_pre"] + ".bias"), 1e-5, None, x, st["mean0"], st["rstd0"])
         # Residual stream: every projection GEMM writes its branch output as bf16 (plain epilogue); the fp32 residual add is fused
         # into the LayerNorm that follows it (x_new = x + branch is stored by that kernel for backward / the next residual).
         ybr = self.bf("v.ybr", M, W)                 # branch output (attention out-proj / MLP c_proj), reused
         pending = None                               # (x_res, add): residual add owed to the next LayerNorm
         for i in range(self.nv):
-            p = f"visual.transformer.resblocks.{i}."
+            p = vn["layer"].format(i)
             tag = f"v.{i}." if save else "v.t."
             ly = {}
             ly["h"] = self.bf(tag + "h", M, W); ly["m1"] = self.f32(tag + "m1", M); ly["r1"] = self.f32(tag + "r1", M)
+            g1, b1 = P_.p(p + vn["ln1"] + ".weight"), P_.p(p + vn["ln1"] + ".bias")
             if pending is None:
-                ops.layernorm_fwd(x, P_.p(p + "ln_1.weight"), P_.p(p + "ln_1.bias"), 1e-5, ly["h"], None, ly["m1"], ly["r1"])
+                ops.layernorm_fwd(x, g1, b1, 1e-5, ly["h"], None, ly["m1"], ly["r1"])
             else:       # x = x1_prev + c_proj(...) of the previous block
                 x_new = self.f32(f"v.x.{i}" if save else f"v.x.t{i % 2}", M, W)
-                ops.layernorm_fwd(pending, P_.p(p + "ln_1.weight"), P_.p(p + "ln_1.bias"), 1e-5, ly["h"], None, ly["m1"], ly["r1"],
-                                  add=ybr, x_out=x_new)
+                ops.layernorm_fwd(pending, g1, b1, 1e-5, ly["h"], None, ly["m1"], ly["r1"], add=ybr, x_out=x_new)
                 x = x_new
             ly["x_in"] = x
             ly["qkv"] = self.bf(tag + "qkv", M, 3 * W)
-            ops.gemm(ly["h"], P_.w(p + "attn.in_proj_weight"), ly["qkv"], bias=P_.p(p + "attn.in_proj_bias"))
+            ops.gemm(ly["h"], P_.w(p + vn["qkv_w"], (3 * W, W)), ly["qkv"], bias=P_.p(p + vn["qkv_b"], (3 * W,)))
             ly["ctx"] = self.bf(tag + "ctx", M, W); ly["lse"] = self.f32(tag + "lse", B * Hh * Lv)
             ops.attention_fwd(ly["qkv"], None, ly["ctx"], ly["lse"], B, Lv, Hh)
-            ops.gemm(ly["ctx"], P_.w(p + "attn.out_proj.weight"), ybr, bias=P_.p(p + "attn.out_proj.bias"))
+            ops.gemm(ly["ctx"], P_.w(p + vn["out"] + ".weight"), ybr, bias=P_.p(p + vn["out"] + ".bias"))
             ly["x1"] = self.f32(tag + "x1", M, W)
             ly["h2"] = self.bf(tag + "h2", M, W); ly["m2"] = self.f32(tag + "m2", M); ly["r2"] = self.f32(tag + "r2", M)
-            ops.layernorm_fwd(x, P_.p(p + "ln_2.weight"), P_.p(p + "ln_2.bias"), 1e-5, ly["h2"], None, ly["m2"], ly["r2"],
+            ops.layernorm_fwd(x, P_.p(p + vn["ln2"] + ".weight"), P_.p(p + vn["ln2"] + ".bias"), 1e-5, ly["h2"], None, ly["m2"], ly["r2"],
                               add=ybr, x_out=ly["x1"])
-            # "z" holds act'(z) (QuickGELU derivative) saved for backward, "a" the activation
-            ly["z"] = self.bf(tag + "z", M, 4 * W); ly["a"] = self.bf(tag + "a", M, 4 * W)
-            ops.gemm(ly["h2"], P_.w(p + "mlp.c_fc.weight"), ly["z"], bias=P_.p(p + "mlp.c_fc.bias"), mode=L.EPI_QUICK_GELU, out2=ly["a"])
-            ops.gemm(ly["a"], P_.w(p + "mlp.c_proj.weight"), ybr, bias=P_.p(p + "mlp.c_proj.bias"))
+            # "z" holds act'(z) (the activation's derivative) saved for backward, "a" the activation
+            ly["z"] = self.bf(tag + "z", M, Iv); ly["a"] = self.bf(tag + "a", M, Iv)
+            ops.gemm(ly["h2"], P_.w(p + vn["fc1"] + ".weight"), ly["z"], bias=P_.p(p + vn["fc1"] + ".bias"), mode=self.vit_act, out2=ly["a"])
+            ops.gemm(ly["a"], P_.w(p + vn["fc2"] + ".weight"), ybr, bias=P_.p(p + vn["fc2"] + ".bias"))
             pending = ly["x1"]
             st["layers"].append(ly)
         # ln_post on the CLS rows of x_final = x1_last + c_proj(...): the add is fused here too; x_cls [B, W] is kept for backward
         st["x_cls"] = self.f32("v.x_cls", B, W)
         st["pooled"] = self.bf("v.pooled", B, W); st["mp"] = self.f32("v.mp", B); st["rp"] = self.f32("v.rp", B)
+        gp, bp = P_.p(vn["ln_post"] + ".weight"), P_.p(vn["ln_post"] + ".bias")
         if pending is None:      # zero-layer tower (degenerate configs): no pending residual
-            ops.layernorm_fwd(x, P_.p("visual.ln_post.weight"), P_.p("visual.ln_post.bias"), 1e-5, st["pooled"], None, st["mp"], st["rp"],
-                              rows=B, ldx=Lv * W)
+            ops.layernorm_fwd(x, gp, bp, 1e-5, st["pooled"], None, st["mp"], st["rp"], rows=B, ldx=Lv * W)
             st["x_cls"] = None; st["x_final"] = x
         else:
-            ops.layernorm_fwd(pending, P_.p("visual.ln_post.weight"), P_.p("visual.ln_post.bias"), 1e-5, st["pooled"], None, st["mp"], st["rp"],
+            ops.layernorm_fwd(pending, gp, bp, 1e-5, st["pooled"], None, st["mp"], st["rp"],
                               rows=B, ldx=Lv * W, add=ybr, ldadd=Lv * W, x_out=st["x_cls"])
         st["feat"] = self.f32("v.feat", B, self.E)
-        ops.gemm(st["pooled"], P_.w("visual.proj"), st["feat"], b_mn_major=1)
+        if self.hf:   # image_embeds = vision_projection(pooled.detach())  (appzoo/clip/model.py:142-143)
+            ops.gemm(st["pooled"], P_.w("vision_projection.weight"), st["feat"], bias=P_.p("vision_projection.bias"))
+        else:
+            ops.gemm(st["pooled"], P_.w("visual.proj"), st["feat"], b_mn_major=1)
         st["embeds"] = self.f32("v.embeds", B, self.E); st["norm"] = self.f32("v.norm", B)
         ops.l2norm_fwd(st["feat"], st["embeds"], st["norm"], B, self.E)
         return st
 
+    def vit_head_backward_hf(self, st, d_embeds: torch.Tensor):
+        """huggingface_clip: the image tower is frozen by `.detach()` (model.py:142) -- only vision_projection receives a gradient"""
+        P_ = self.params; B = st["B"]; E = self.E
+        dfeat = self.f32("v.dfeat", B, E); dfeat_b = self.bf("v.dfeat_b", B, E)
+        ops.l2norm_bwd(d_embeds, st["embeds"], st["norm"], dfeat, dfeat_b, B, E)
+        ops.gemm(dfeat_b, st["pooled"], P_.g("vision_projection.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)   # dW[E,W] += dfeat^T pooled
+        ops.colsum(dfeat, P_.g("vision_projection.bias"), B, E)
+        self._grads_ready("vision_projection.")
+
     def vit_backward(self, st, d_embeds: torch.Tensor):
-        P_ = self.params; W = self.W; B = st["B"]; Lv = self.Lv; M = B * Lv; Hh = self.Hv; E = self.E
+        P_ = self.params; W = self.W; B = st["B"]; Lv = self.Lv; M = B * Lv; Hh = self.Hv; E = self.E; vn = self.vn; Iv = self.Iv
+        if self.hf:
+            return self.vit_head_backward_hf(st, d_embeds)
         dfeat_b = self.bf("v.dfeat_b", B, E)
         ops.l2norm_bwd(d_embeds, st["embeds"], st["norm"], None, dfeat_b, B, E)
         # d proj[W,E] += pooled^T dfeat ; dpooled = dfeat proj^T
@@ -168,49 +252,49 @@ class ClipEngine:
         dX = self.f32("v.dX.a", M, W); dXb = self.bf("v.dXb.a", M, W)
         dX.zero_()
         last = st["layers"][-1] if self.nv else None
-        bias_prev = P_.g(f"visual.transformer.resblocks.{self.nv - 1}.mlp.c_proj.bias") if self.nv else None
+        bias_prev = P_.g(vn["layer"].format(self.nv - 1) + vn["fc2"] + ".bias") if self.nv else None
         x_post, ld_post = (st["x_cls"], W) if st.get("x_cls") is not None else (st["x_final"], Lv * W)
-        ops.layernorm_bwd(dpooled, x_post, P_.p("visual.ln_post.weight"), st["mp"], st["rp"], dx_f32=dX,
-                          dgamma=P_.g("visual.ln_post.weight"), dbeta=P_.g("visual.ln_post.bias"), dbias=bias_prev,
+        ops.layernorm_bwd(dpooled, x_post, P_.p(vn["ln_post"] + ".weight"), st["mp"], st["rp"], dx_f32=dX,
+                          dgamma=P_.g(vn["ln_post"] + ".weight"), dbeta=P_.g(vn["ln_post"] + ".bias"), dbias=bias_prev,
                           rows=B, ldx=ld_post, lddx=Lv * W)
         ops.cast_bf16(dX, dXb)
-        dz = self.bf("v.dz", M, 4 * W); dh = self.bf("v.dh", M, W); dctx = self.bf("v.dctx", M, W); dqkv = self.bf("v.dqkv", M, 3 * W)
+        dz = self.bf("v.dz", M, Iv); dh = self.bf("v.dh", M, W); dctx = self.bf("v.dctx", M, W); dqkv = self.bf("v.dqkv", M, 3 * W)
         for i in reversed(range(self.nv)):
-            p = f"visual.transformer.resblocks.{i}."
+            p = vn["layer"].format(i)
             ly = st["layers"][i]
             # MLP
-            ops.gemm(dXb, ly["a"], P_.g(p + "mlp.c_proj.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
-                     splits=_splits_for(W, 4 * W, M))
-            ops.gemm(dXb, P_.w(p + "mlp.c_proj.weight"), dz, b_mn_major=1, mode=L.EPI_MUL_AUX, aux=ly["z"],
-                     colsum=P_.g(p + "mlp.c_fc.bias"))            # dz = (dX W) o act'(z); its column sums = d(c_fc.bias)
-            ops.gemm(dz, ly["h2"], P_.g(p + "mlp.c_fc.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
-                     splits=_splits_for(4 * W, W, M))
-            ops.gemm(dz, P_.w(p + "mlp.c_fc.weight"), dh, b_mn_major=1)
+            ops.gemm(dXb, ly["a"], P_.g(p + vn["fc2"] + ".weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+                     splits=_splits_for(W, Iv, M))
+            ops.gemm(dXb, P_.w(p + vn["fc2"] + ".weight"), dz, b_mn_major=1, mode=L.EPI_MUL_AUX, aux=ly["z"],
+                     colsum=P_.g(p + vn["fc1"] + ".bias"))            # dz = (dX W) o act'(z); its column sums = d(c_fc.bias)
+            ops.gemm(dz, ly["h2"], P_.g(p + vn["fc1"] + ".weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+                     splits=_splits_for(Iv, W, M))
+            ops.gemm(dz, P_.w(p + vn["fc1"] + ".weight"), dh, b_mn_major=1)
             dX1 = self.f32("v.dX.b", M, W); dX1b = self.bf("v.dXb.b", M, W)
-            ops.layernorm_bwd(dh, ly["x1"], P_.p(p + "ln_2.weight"), ly["m2"], ly["r2"], dx_add=dX, dx_f32=dX1, dx_bf16=dX1b,
-                              dgamma=P_.g(p + "ln_2.weight"), dbeta=P_.g(p + "ln_2.bias"), dbias=P_.g(p + "attn.out_proj.bias"))
+            ops.layernorm_bwd(dh, ly["x1"], P_.p(p + vn["ln2"] + ".weight"), ly["m2"], ly["r2"], dx_add=dX, dx_f32=dX1, dx_bf16=dX1b,
+                              dgamma=P_.g(p + vn["ln2"] + ".weight"), dbeta=P_.g(p + vn["ln2"] + ".bias"), dbias=P_.g(p + vn["out"] + ".bias"))
             # attention
-            ops.gemm(dX1b, ly["ctx"], P_.g(p + "attn.out_proj.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+            ops.gemm(dX1b, ly["ctx"], P_.g(p + vn["out"] + ".weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
                      splits=_splits_for(W, W, M))
-            ops.gemm(dX1b, P_.w(p + "attn.out_proj.weight"), dctx, b_mn_major=1)
-            ops.attention_bwd(ly["qkv"], None, ly["ctx"], ly["lse"], dctx, dqkv, B, Lv, Hh, dqkv_colsum=P_.g(p + "attn.in_proj_bias"))
-            ops.gemm(dqkv, ly["h"], P_.g(p + "attn.in_proj_weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+            ops.gemm(dX1b, P_.w(p + vn["out"] + ".weight"), dctx, b_mn_major=1)
+            ops.attention_bwd(ly["qkv"], None, ly["ctx"], ly["lse"], dctx, dqkv, B, Lv, Hh, dqkv_colsum=P_.g(p + vn["qkv_b"], (3 * W,)))
+            ops.gemm(dqkv, ly["h"], P_.g(p + vn["qkv_w"], (3 * W, W)), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
                      splits=_splits_for(3 * W, W, M))
-            ops.gemm(dqkv, P_.w(p + "attn.in_proj_weight"), dh, b_mn_major=1)
-            bias_prev = P_.g(f"visual.transformer.resblocks.{i - 1}.mlp.c_proj.bias") if i > 0 else None
-            ops.layernorm_bwd(dh, ly["x_in"], P_.p(p + "ln_1.weight"), ly["m1"], ly["r1"], dx_add=dX1, dx_f32=dX, dx_bf16=dXb,
-                              dgamma=P_.g(p + "ln_1.weight"), dbeta=P_.g(p + "ln_1.bias"), dbias=bias_prev)
+            ops.gemm(dqkv, P_.w(p + vn["qkv_w"], (3 * W, W)), dh, b_mn_major=1)
+            bias_prev = P_.g(vn["layer"].format(i - 1) + vn["fc2"] + ".bias") if i > 0 else None
+            ops.layernorm_bwd(dh, ly["x_in"], P_.p(p + vn["ln1"] + ".weight"), ly["m1"], ly["r1"], dx_add=dX1, dx_f32=dX, dx_bf16=dXb,
+                              dgamma=P_.g(p + vn["ln1"] + ".weight"), dbeta=P_.g(p + vn["ln1"] + ".bias"), dbias=bias_prev)
             self._grads_ready(p)
         # ln_pre, token assembly, patch embedding
         dx0 = self.f32("v.dx0", M, W)
-        ops.layernorm_bwd(dX, self.f32("v.x0", M, W), P_.p("visual.ln_pre.weight"), st["mean0"], st["rstd0"], dx_f32=dx0,
-                          dgamma=P_.g("visual.ln_pre.weight"), dbeta=P_.g("visual.ln_pre.bias"))
-        ops.colsum(dx0, P_.g("visual.positional_embedding").view(-1), B, Lv * W)
-        ops.colsum(dx0, P_.g("visual.class_embedding"), B, W, ldx=Lv * W)
+        ops.layernorm_bwd(dX, self.f32("v.x0", M, W), P_.p(vn["ln_pre"] + ".weight"), st["mean0"], st["rstd0"], dx_f32=dx0,
+                          dgamma=P_.g(vn["ln_pre"] + ".weight"), dbeta=P_.g(vn["ln_pre"] + ".bias"))
+        ops.colsum(dx0, P_.g(vn["pos"]).view(-1), B, Lv * W)
+        ops.colsum(dx0, P_.g(vn["cls"]), B, W, ldx=Lv * W)
         npatch = B * self.g * self.g; kdim = 3 * self.P * self.P
         dpatch = self.bf("v.dpatch", npatch, W)
         ops.vit_assemble_bwd(dx0, dpatch, B, Lv, W)
-        ops.gemm(dpatch, self.bf("v.patches", npatch, kdim), P_.g("visual.conv1.weight", (W, kdim)), a_mn_major=1, b_mn_major=1,
+        ops.gemm(dpatch, self.zbuf("v.patches", (npatch, self.kdim_pad), torch.bfloat16), P_.g(vn["conv"], (W, kdim)), a_mn_major=1, b_mn_major=1,
                  mode=L.EPI_ATOMIC_ADD, splits=_splits_for(W, kdim, npatch))
 
     # ------------------------------------------------------------------ BERT
@@ -225,23 +309,34 @@ class ClipEngine:
             self._drops[key] = d
         return d
 
-    def bert_forward(self, ids: torch.Tensor, save: bool, train: bool = False):
-        P_ = self.params; H = self.H; I = self.I; B, Lt = ids.shape; M = B * Lt; Hh = self.Ht
+    def bert_forward(self, ids: torch.Tensor, save: bool, train: bool = False, token_type_ids=None, attention_mask=None):
+        """BertModel (chinese_clip: mask = ids != 0, modeling_chineseclip.py:347-349) or RobertaModel (huggingface_clip: pad-aware
+        position ids, the batch's token_type_ids / attention_mask, tanh pooler; appzoo/clip/model.py:128-137)"""
+        P_ = self.params; H = self.H; I = self.I; B, Lt = ids.shape; M = B * Lt; Hh = self.Ht; tp = self.tp
         assert ids.dtype == torch.int64 and ids.is_contiguous()
-        if Lt > self.cfg["text_max_position_embeddings"]:
+        if Lt > self.cfg["text_max_position_embeddings"] - (self.pad_id + 1 if self.hf else 0):
             raise ValueError("sequence longer than the position table")
-        eps = 1e-12                                                   # modeling_chineseclip.py:311
+        eps = self.text_eps
         st = {"B": B, "Lt": Lt, "ids": ids, "layers": [], "train": train}
         st["e"] = self.f32("t.e", M, H); st["mask"] = self.f32("t.mask", M)
-        ops.bert_embed(ids.view(-1), P_.p("bert.embeddings.word_embeddings.weight"), P_.p("bert.embeddings.position_embeddings.weight"),
-                       P_.p("bert.embeddings.token_type_embeddings.weight"), st["e"], M, Lt, H, self.cfg["vocab_size"], key_mask=st["mask"])
+        if self.hf:
+            st["pos_ids"] = self.buf("t.pos_ids", (B, Lt), torch.int32)
+            st["type_ids"] = token_type_ids.to(self.dev).long().contiguous() if token_type_ids is not None else None
+            am = attention_mask.to(self.dev).long().contiguous() if attention_mask is not None else None
+            ops.position_ids(ids, st["pos_ids"], self.pad_id)
+            ops.embed_gather(ids, st["pos_ids"], st["type_ids"], am, P_.p(tp + "embeddings.word_embeddings.weight"),
+                             P_.p(tp + "embeddings.position_embeddings.weight"), P_.p(tp + "embeddings.token_type_embeddings.weight"),
+                             st["e"], st["mask"], self.pad_id)
+        else:
+            ops.bert_embed(ids.view(-1), P_.p("bert.embeddings.word_embeddings.weight"), P_.p("bert.embeddings.position_embeddings.weight"),
+                           P_.p("bert.embeddings.token_type_embeddings.weight"), st["e"], M, Lt, H, self.cfg["vocab_size"], key_mask=st["mask"])
         x = self.f32("t.x.0", M, H); xb = self.bf("t.xb.0", M, H)
         st["me"] = self.f32("t.me", M); st["re"] = self.f32("t.re", M)
-        ops.layernorm_fwd(st["e"], P_.p("bert.embeddings.LayerNorm.weight"), P_.p("bert.embeddings.LayerNorm.bias"), eps, xb, x,
+        ops.layernorm_fwd(st["e"], P_.p(tp + "embeddings.LayerNorm.weight"), P_.p(tp + "embeddings.LayerNorm.bias"), eps, xb, x,
                           st["me"], st["re"], drop=self._drop(train, self.p_hidden, 1), drop_mode=2)
         tbr = self.bf("t.tbr", M, H)                 # bf16 branch output of attention.output.dense / output.dense
         for i in range(self.nt):
-            p = f"bert.encoder.layer.{i}."
+            p = f"{tp}encoder.layer.{i}."
             tag = f"t.{i}." if save else "t.t."
             ly = {"x_in": x, "xb_in": xb}
             ly["qkv"] = self.bf(tag + "qkv", M, 3 * H)
@@ -269,27 +364,48 @@ class ClipEngine:
         st["xb_final"] = xb
         st["feat"] = self.f32("t.feat", B, self.E)
         cls_rows = xb.view(B, Lt * H)[:, :H]                           # x[:, 0, :]  (modeling_chineseclip.py:350)
-        ops.gemm(cls_rows, P_.w("text_projection"), st["feat"], b_mn_major=1)
+        if self.hf:
+            # text_embeds = text_projection(pooler_output), pooler_output = tanh(dense(h[:, 0]))  (model.py:135-136, modeling_roberta.py:559-575)
+            st["pool_pre"] = self.f32("t.pool_pre", B, H); st["pool"] = self.f32("t.pool", B, H); st["pool_b"] = self.bf("t.pool_b", B, H)
+            ops.gemm(cls_rows, P_.w(tp + "pooler.dense.weight"), st["pool_pre"], bias=P_.p(tp + "pooler.dense.bias"))
+            ops.tanh_fwd(st["pool_pre"], st["pool"], st["pool_b"])
+            ops.gemm(st["pool_b"], P_.w("text_projection.weight"), st["feat"], bias=P_.p("text_projection.bias"))
+        else:
+            ops.gemm(cls_rows, P_.w("text_projection"), st["feat"], b_mn_major=1)
         st["embeds"] = self.f32("t.embeds", B, self.E); st["norm"] = self.f32("t.norm", B)
         ops.l2norm_fwd(st["feat"], st["embeds"], st["norm"], B, self.E)
         return st
 
     def bert_backward(self, st, d_embeds: torch.Tensor):
-        P_ = self.params; H = self.H; I = self.I; B = st["B"]; Lt = st["Lt"]; M = B * Lt; Hh = self.Ht; E = self.E
+        P_ = self.params; H = self.H; I = self.I; B = st["B"]; Lt = st["Lt"]; M = B * Lt; Hh = self.Ht; E = self.E; tp = self.tp
         train = st.get("train", False)
         dfeat_b = self.bf("t.dfeat_b", B, E)
-        ops.l2norm_bwd(d_embeds, st["embeds"], st["norm"], None, dfeat_b, B, E)
         cls_rows = st["xb_final"].view(B, Lt * H)[:, :H]
-        ops.gemm(cls_rows, dfeat_b, P_.g("text_projection"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
         dOut = self.f32("t.dOut", M, H)
         dOut.zero_()
-        ops.gemm(dfeat_b, P_.w("text_projection"), dOut.view(B, Lt * H)[:, :H])
+        if self.hf:
+            dfeat = self.f32("t.dfeat", B, E)
+            ops.l2norm_bwd(d_embeds, st["embeds"], st["norm"], dfeat, dfeat_b, B, E)
+            # text_projection (Linear [E,H] + bias) <- tanh pooler (dense [H,H] + bias) <- CLS hidden state
+            ops.gemm(dfeat_b, st["pool_b"], P_.g("text_projection.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
+            ops.colsum(dfeat, P_.g("text_projection.bias"), B, E)
+            dpool = self.f32("t.dpool", B, H); dpre = self.f32("t.dpre", B, H); dpre_b = self.bf("t.dpre_b", B, H)
+            ops.gemm(dfeat_b, P_.w("text_projection.weight"), dpool, b_mn_major=1)
+            ops.tanh_bwd(dpool, st["pool"], dpre, dpre_b)
+            ops.gemm(dpre_b, cls_rows, P_.g(tp + "pooler.dense.weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
+            ops.colsum(dpre, P_.g(tp + "pooler.dense.bias"), B, H)
+            ops.gemm(dpre_b, P_.w(tp + "pooler.dense.weight"), dOut.view(B, Lt * H)[:, :H], b_mn_major=1)
+            self._grads_ready("text_projection."); self._grads_ready(tp + "pooler.")
+        else:
+            ops.l2norm_bwd(d_embeds, st["embeds"], st["norm"], None, dfeat_b, B, E)
+            ops.gemm(cls_rows, dfeat_b, P_.g("text_projection"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
+            ops.gemm(dfeat_b, P_.w("text_projection"), dOut.view(B, Lt * H)[:, :H])
         dy, dy_add = dOut, None
         ds2 = self.f32("t.ds2", M, H); ds2b = self.bf("t.ds2b", M, H); ds1 = self.f32("t.ds1", M, H); ds1b = self.bf("t.ds1b", M, H)
         dz = self.bf("t.dz", M, I); dpart = self.bf("t.dpart", M, H); dctx = self.bf("t.dctx", M, H); dqkv = self.bf("t.dqkv", M, 3 * H)
         dxp = self.bf("t.dxp", M, H)
         for i in reversed(range(self.nt)):
-            p = f"bert.encoder.layer.{i}."
+            p = f"{tp}encoder.layer.{i}."
             ly = st["layers"][i]
             ops.layernorm_bwd(dy, ly["s2"], P_.p(p + "output.LayerNorm.weight"), ly["m2"], ly["r2"], dy_add=dy_add, dx_f32=ds2, dx_bf16=ds2b,
                               dgamma=P_.g(p + "output.LayerNorm.weight"), dbeta=P_.g(p + "output.LayerNorm.bias"), dbias=P_.g(p + "output.dense.bias"),
@@ -316,13 +432,17 @@ class ClipEngine:
             dy, dy_add = dxp, ds1
             self._grads_ready(p)
         de = self.f32("t.de", M, H)
-        ops.layernorm_bwd(dy, st["e"], P_.p("bert.embeddings.LayerNorm.weight"), st["me"], st["re"], dy_add=dy_add, dx_f32=de,
-                          dgamma=P_.g("bert.embeddings.LayerNorm.weight"), dbeta=P_.g("bert.embeddings.LayerNorm.bias"),
+        ops.layernorm_bwd(dy, st["e"], P_.p(tp + "embeddings.LayerNorm.weight"), st["me"], st["re"], dy_add=dy_add, dx_f32=de,
+                          dgamma=P_.g(tp + "embeddings.LayerNorm.weight"), dbeta=P_.g(tp + "embeddings.LayerNorm.bias"),
                           drop=self._drop(train, self.p_hidden, 1), drop_mode=2)
-        ops.bert_embed_bwd(st["ids"].view(-1), de, P_.g("bert.embeddings.word_embeddings.weight"), M, H, self.cfg["vocab_size"])
-        ops.colsum(de, P_.g("bert.embeddings.position_embeddings.weight").view(-1)[:Lt * H], B, Lt * H)
-        ops.colsum(de, P_.g("bert.embeddings.token_type_embeddings.weight")[0], M, H)
-        self._grads_ready("bert.embeddings.")
+        if self.hf:
+            ops.embed_gather_bwd(st["ids"], st["pos_ids"], st["type_ids"], de, P_.g(tp + "embeddings.word_embeddings.weight"),
+                                 P_.g(tp + "embeddings.position_embeddings.weight"), P_.g(tp + "embeddings.token_type_embeddings.weight"), self.pad_id)
+        else:
+            ops.bert_embed_bwd(st["ids"].view(-1), de, P_.g("bert.embeddings.word_embeddings.weight"), M, H, self.cfg["vocab_size"])
+            ops.colsum(de, P_.g("bert.embeddings.position_embeddings.weight").view(-1)[:Lt * H], B, Lt * H)
+            ops.colsum(de, P_.g("bert.embeddings.token_type_embeddings.weight")[0], M, H)
+        self._grads_ready(tp + "embeddings.")
 
     # ------------------------------------------------------------------ contrastive head
     def loss_forward(self, text_embeds, image_embeds, gallery_image=None, gallery_text=None, label_offset=0, want_logits=True):
@@ -333,7 +453,7 @@ class ClipEngine:
         gt = text_embeds if gallery_text is None else gallery_text
         B = text_embeds.shape[0]; G = gi.shape[0]; E = self.E
         Gp = (G + 7) // 8 * 8                                   # GEMM N / leading dimensions are multiples of 8; padding rows stay zero
-        ls = self.params.p("logit_scale")
+        ls = self.params.p("logit_scale").view(-1)
         Ts = self.bf("l.Ts", B, 3 * E); Is = self.bf("l.Is", B, 3 * E)
         GIs = self.zbuf("l.GIs", (Gp, 3 * E), torch.bfloat16); GTs = self.zbuf("l.GTs", (Gp, 3 * E), torch.bfloat16)
         ops.split_bf16x3(text_embeds, Ts, 0); ops.split_bf16x3(image_embeds, Is, 0)
@@ -360,7 +480,7 @@ class ClipEngine:
         the distributed wrapper can reduce-scatter them to their owners."""
         B = st["T"].shape[0]; G = st["G"]; Gp = st["Gp"]; E = self.E
         coef = grad_scale / (2.0 * G)
-        ls = self.params.p("logit_scale"); dls = self.params.g("logit_scale").view(1)
+        ls = self.params.p("logit_scale").view(-1); dls = self.params.g("logit_scale").view(1)
         dS_t = self.bf("l.dS_t", B, Gp); dS_i = self.bf("l.dS_i", B, Gp)
         ops.ce_rows_bwd(st["S_t"], ls, st["lse_t"], st["off"], coef, dS_t, B, G, dscale_log=dls)
         ops.ce_rows_bwd(st["S_i"], ls, st["lse_i"], st["off"], coef, dS_i, B, G, dscale_log=dls)
@@ -379,16 +499,16 @@ class ClipEngine:
         return dT, dI, dGI, dGT
 
     # ------------------------------------------------------------------ public steps
-    def encode(self, pixels: Optional[torch.Tensor], ids: Optional[torch.Tensor]):
+    def encode(self, pixels: Optional[torch.Tensor], ids: Optional[torch.Tensor], token_type_ids=None, attention_mask=None):
         """feat=True path of CLIPApp.forward (model.py:145-146): embeddings only, no activations kept."""
         out = {"image_embeds": None, "text_embeds": None}
         if pixels is not None:
             out["image_embeds"] = self.vit_forward(pixels, save=False)["embeds"]
         if ids is not None:
-            out["text_embeds"] = self.bert_forward(ids, save=False)["embeds"]
+            out["text_embeds"] = self.bert_forward(ids, save=False, token_type_ids=token_type_ids, attention_mask=attention_mask)["embeds"]
         return out
 
-    def forward(self, pixels, ids, save=True, want_logits=True, distributed=False, train=None):
+    def forward(self, pixels, ids, save=True, want_logits=True, distributed=False, train=None, token_type_ids=None, attention_mask=None):
         """Both towers + the contrastive head.  distributed=True: all-gather the embedding shards over the default process
         group and take the loss over the GLOBAL batch (labels offset by rank * local_B); 'loss' is then this rank's share
         (sum over ranks = global loss) and 'logits_per_text' the local [b, G] strip."""
@@ -397,8 +517,8 @@ class ClipEngine:
             train = save           # training step <=> activations are kept; dropout is active only then
         if train and (self.p_hidden > 0.0 or self.p_attn > 0.0):
             ops.counter_add(self._dev_pass, 1)       # new dropout masks for this pass (its backward sees the same value)
-        v = self.vit_forward(pixels, save)
-        t = self.bert_forward(ids, save, train=train)
+        v = self.vit_forward(pixels, save and not self.hf)       # huggingface_clip: the image tower is frozen -> no activations kept
+        t = self.bert_forward(ids, save, train=train, token_type_ids=token_type_ids, attention_mask=attention_mask)
         if distributed and D.world_size() > 1:
             B = pixels.shape[0]; Wd = D.world_size()
             gi = D.gather_rows(v["embeds"], self.f32("l.gi", Wd * B, self.E))
@@ -470,11 +590,13 @@ class ClipEngine:
                        lr, weight_decay, 0, coef, dev_hyper=self._dev_hyper)
         ops.adamw_step(P_.master[n_dec:n_tr], P_.grad[n_dec:n_tr], P_.exp_avg[n_dec:n_tr], P_.exp_avg_sq[n_dec:n_tr],
                        P_.shadow[n_dec:n_tr], n_tr - n_dec, lr, 0.0, 0, coef, dev_hyper=self._dev_hyper)
+        P_.version += 1
 
     # ------------------------------------------------------------------ whole training step, optionally as ONE CUDA graph
     def _step_body(self, pixels, ids, hp):
         self.zero_grad()
-        out = self.forward(pixels, ids, save=True, want_logits=hp["want_logits"], distributed=hp["distributed"])
+        out = self.forward(pixels, ids, save=True, want_logits=hp["want_logits"], distributed=hp["distributed"],
+                           token_type_ids=hp.get("token_type_ids"), attention_mask=hp.get("attention_mask"))
         if hp["allreduce"] and hp.get("overlap", False):
             # eager multi-GPU step: per-layer gradient slices are all-reduced while the rest of the backward pass runs
             from . import distributed as D
@@ -492,7 +614,7 @@ class ClipEngine:
         return out
 
     def train_step(self, pixels, ids, lr, weight_decay=1e-4, max_grad_norm=1.0, warmup_steps=0, t_total=0, distributed=False,
-                   want_logits=False, use_graph=True, grad_scale=None, allreduce=None):
+                   want_logits=False, use_graph=True, grad_scale=None, allreduce=None, token_type_ids=None, attention_mask=None):
         """zero_grad -> forward -> backward -> (grad all-reduce) -> clip + AdamW.  `pixels` / `ids` may live on the host (pinned):
         they are copied into static device buffers.  After two eager calls (which size every buffer and set kernel attributes) the
         whole step is captured once into a CUDA graph and replayed: ~2.6 k kernel launches collapse into one cudaGraphLaunch.
@@ -504,7 +626,8 @@ class ClipEngine:
         if grad_scale is None:      # local-loss data parallelism averages gradients like DDP; the global loss is already normalised
             grad_scale = 1.0 if (distributed or D.world_size() == 1) else 1.0 / D.world_size()
         B, Lt = ids.shape
-        key = (B, Lt, bool(allreduce), float(lr), float(weight_decay), float(max_grad_norm), int(warmup_steps), int(t_total), bool(distributed), bool(want_logits), float(grad_scale))
+        extra = self.hf and (token_type_ids is not None, attention_mask is not None)
+        key = (B, Lt, bool(allreduce), float(lr), float(weight_decay), float(max_grad_norm), int(warmup_steps), int(t_total), bool(distributed), bool(want_logits), float(grad_scale), extra)
         st = getattr(self, "_gs", None)
         if st is None or st["key"] != key:
             st = {"key": key, "calls": 0, "graph": None, "out": None,
@@ -513,7 +636,13 @@ class ClipEngine:
             self._gs = st
         st["pixels"].copy_(pixels, non_blocking=True)
         st["ids"].copy_(ids, non_blocking=True)
-        hp = {"lr": lr, "weight_decay": weight_decay, "max_grad_norm": max_grad_norm, "warmup_steps": warmup_steps, "t_total": t_total,
+        tt = am = None
+        if self.hf:       # the text tower of the huggingface_clip branch reads the batch's token_type_ids / attention_mask (static buffers too)
+            if token_type_ids is not None:
+                tt = st.setdefault("tt", torch.empty((B, Lt), dtype=torch.int64, device=self.dev)); tt.copy_(token_type_ids, non_blocking=True)
+            if attention_mask is not None:
+                am = st.setdefault("am", torch.empty((B, Lt), dtype=torch.int64, device=self.dev)); am.copy_(attention_mask, non_blocking=True)
+        hp = {"token_type_ids": tt, "attention_mask": am, "lr": lr, "weight_decay": weight_decay, "max_grad_norm": max_grad_norm, "warmup_steps": warmup_steps, "t_total": t_total,
               "distributed": distributed, "want_logits": want_logits, "grad_scale": grad_scale, "allreduce": allreduce,
               "overlap": bool(allreduce) and not use_graph and os.environ.get("CLIPK_NO_OVERLAP", "0") != "1"}
         if not use_graph or st["calls"] < 2:

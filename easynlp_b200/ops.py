@@ -177,7 +177,7 @@ def colsum(x, out, rows, n, ldx=None):
 
 @_op
 def im2col_patches(pixels, patches, B, R, P):
-    L_.check(L_.lib().clipk_im2col_patches(_f32(pixels), _b16(patches), B, R, P, _stream()), "im2col")
+    L_.check(L_.lib().clipk_im2col_patches(_f32(pixels), _b16(patches), B, R, P, patches.stride(0), _stream()), "im2col")
 
 
 @_op
@@ -200,6 +200,42 @@ def bert_embed(ids, word, pos, type0, e, rows, L, H, vocab, key_mask=None):
 @_op
 def bert_embed_bwd(ids, de, dword, rows, H, vocab):
     L_.check(L_.lib().clipk_bert_embed_bwd(_ptr(ids), _f32(de), _f32(dword), rows, H, vocab, _stream()), "bert_embed_bwd")
+
+
+def _i64(t):
+    assert t is None or (t.dtype == torch.int64 and t.is_cuda and t.is_contiguous()), "expected a contiguous CUDA int64 tensor"
+    return _ptr(t)
+
+
+@_op
+def position_ids(ids, pos_ids, pad_id):
+    B, Lt = ids.shape
+    assert pos_ids.dtype == torch.int32 and pos_ids.shape == (B, Lt) and pos_ids.is_contiguous()
+    L_.check(L_.lib().clipk_position_ids(_i64(ids), _ptr(pos_ids), B, Lt, int(pad_id), _stream()), "position_ids")
+
+
+@_op
+def embed_gather(ids, pos_ids, type_ids, attn_mask, word, pos, type_, e, key_mask, pad_id):
+    rows = ids.numel(); H = word.shape[1]
+    L_.check(L_.lib().clipk_embed_gather(_i64(ids), _ptr(pos_ids), _i64(type_ids), _i64(attn_mask), _f32(word), _f32(pos), _f32(type_), _f32(e),
+                                         _f32(key_mask), rows, H, word.shape[0], pos.shape[0], type_.shape[0], int(pad_id), _stream()), "embed_gather")
+
+
+@_op
+def embed_gather_bwd(ids, pos_ids, type_ids, de, dword, dpos, dtype_, pad_id):
+    rows = ids.numel(); H = dword.shape[1]
+    L_.check(L_.lib().clipk_embed_gather_bwd(_i64(ids), _ptr(pos_ids), _i64(type_ids), _f32(de), _f32(dword), _f32(dpos), _f32(dtype_), rows, H,
+                                             dword.shape[0], dpos.shape[0], dtype_.shape[0], int(pad_id), _stream()), "embed_gather_bwd")
+
+
+@_op
+def tanh_fwd(x, y, y_bf16=None):
+    L_.check(L_.lib().clipk_tanh_fwd(_f32(x), _f32(y), _b16(y_bf16), x.numel(), _stream()), "tanh_fwd")
+
+
+@_op
+def tanh_bwd(dy, y, dx=None, dx_bf16=None):
+    L_.check(L_.lib().clipk_tanh_bwd(_f32(dy), _f32(y), _f32(dx), _b16(dx_bf16), dy.numel(), _stream()), "tanh_bwd")
 
 
 @_op

@@ -60,6 +60,55 @@ def param_schema(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
     return s
 
 
+def hf_param_schema(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
+    """(name -> shape) for the huggingface_clip branch (appzoo/clip/model.py:82-104): `text_encoder.*` = RobertaModel
+    (modelzoo/models/roberta/modeling_roberta.py), `vision_encoder.*` = CLIPVisionModel (modelzoo/models/clip/modeling_clip.py:112-140,
+    173-334,731-838), biased `text_projection` / `vision_projection` Linears and `logit_scale` [1].  cfg = the flat engine config built by
+    easynlp_b200.engine.hf_engine_config.  q/k/v projection matrices (and biases) are adjacent so that the QKV projection is one operand."""
+    W = cfg["vision_width"]; P = cfg["vision_patch_size"]; E = cfg["embed_dim"]; Iv = cfg["vision_intermediate_size"]
+    n_tok = (cfg["image_resolution"] // P) ** 2 + 1
+    H = cfg["text_hidden_size"]; I = cfg["text_intermediate_size"]
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    s["logit_scale"] = (1,)
+    s["text_projection.weight"] = (E, H); s["text_projection.bias"] = (E,)
+    s["vision_projection.weight"] = (E, W); s["vision_projection.bias"] = (E,)
+    v = "vision_encoder.vision_model."
+    s[v + "embeddings.class_embedding"] = (W,)
+    s[v + "embeddings.patch_embedding.weight"] = (W, 3, P, P)
+    s[v + "embeddings.position_embedding.weight"] = (n_tok, W)
+    s[v + "pre_layrnorm.weight"] = (W,); s[v + "pre_layrnorm.bias"] = (W,)
+    for i in range(cfg["vision_layers"]):
+        p = v + f"encoder.layers.{i}."
+        for nm in ("q_proj", "k_proj", "v_proj"):
+            s[p + f"self_attn.{nm}.weight"] = (W, W)
+        for nm in ("q_proj", "k_proj", "v_proj"):
+            s[p + f"self_attn.{nm}.bias"] = (W,)
+        s[p + "self_attn.out_proj.weight"] = (W, W); s[p + "self_attn.out_proj.bias"] = (W,)
+        s[p + "layer_norm1.weight"] = (W,); s[p + "layer_norm1.bias"] = (W,)
+        s[p + "mlp.fc1.weight"] = (Iv, W); s[p + "mlp.fc1.bias"] = (Iv,)
+        s[p + "mlp.fc2.weight"] = (W, Iv); s[p + "mlp.fc2.bias"] = (W,)
+        s[p + "layer_norm2.weight"] = (W,); s[p + "layer_norm2.bias"] = (W,)
+    s[v + "post_layernorm.weight"] = (W,); s[v + "post_layernorm.bias"] = (W,)
+    t = "text_encoder."
+    s[t + "embeddings.word_embeddings.weight"] = (cfg["vocab_size"], H)
+    s[t + "embeddings.position_embeddings.weight"] = (cfg["text_max_position_embeddings"], H)
+    s[t + "embeddings.token_type_embeddings.weight"] = (cfg["text_type_vocab_size"], H)
+    s[t + "embeddings.LayerNorm.weight"] = (H,); s[t + "embeddings.LayerNorm.bias"] = (H,)
+    for i in range(cfg["text_num_hidden_layers"]):
+        p = t + f"encoder.layer.{i}."
+        for nm in ("query", "key", "value"):
+            s[p + f"attention.self.{nm}.weight"] = (H, H)
+        for nm in ("query", "key", "value"):
+            s[p + f"attention.self.{nm}.bias"] = (H,)
+        s[p + "attention.output.dense.weight"] = (H, H); s[p + "attention.output.dense.bias"] = (H,)
+        s[p + "attention.output.LayerNorm.weight"] = (H,); s[p + "attention.output.LayerNorm.bias"] = (H,)
+        s[p + "intermediate.dense.weight"] = (I, H); s[p + "intermediate.dense.bias"] = (I,)
+        s[p + "output.dense.weight"] = (H, I); s[p + "output.dense.bias"] = (H,)
+        s[p + "output.LayerNorm.weight"] = (H,); s[p + "output.LayerNorm.bias"] = (H,)
+    s[t + "pooler.dense.weight"] = (H, H); s[t + "pooler.dense.bias"] = (H,)
+    return s
+
+
 # the pooler is computed-but-unused by chinese_clip (modeling_chineseclip.py:349 takes [0]); its parameters never get a
 # gradient, so the reference optimizer skips them (optimizers.py:420-421) -- they sit outside the updated range.
 NO_GRAD = ("bert.pooler.dense.weight", "bert.pooler.dense.bias")
@@ -79,10 +128,22 @@ def _pad(n):
 class ParamStore:
     def __init__(self, cfg: dict, device="cuda", with_optimizer_state: bool = True):
         self.cfg = cfg
-        self.schema = param_schema(cfg)
-        decay = [n for n in self.schema if n not in NO_GRAD and uses_weight_decay(n)]
-        nodecay = [n for n in self.schema if n not in NO_GRAD and not uses_weight_decay(n)]
-        frozen = [n for n in self.schema if n in NO_GRAD]
+        self.kind = cfg.get("model_type", "chinese_clip")
+        if self.kind == "huggingface_clip":
+            # the image tower is frozen by the reference's `.detach()` (appzoo/clip/model.py:142): its parameters never get a gradient
+            self.schema = hf_param_schema(cfg)
+            self.no_grad = tuple(n for n in self.schema if n.startswith("vision_encoder."))
+            self.buffers = {"text_encoder.embeddings.position_ids": cfg["text_max_position_embeddings"],
+                            "vision_encoder.vision_model.embeddings.position_ids": (cfg["image_resolution"] // cfg["vision_patch_size"]) ** 2 + 1}
+        else:
+            self.schema = param_schema(cfg)
+            self.no_grad = NO_GRAD
+            # buffer exported by the reference BertEmbeddings (modeling_bert.py:87)
+            self.buffers = {"bert.embeddings.position_ids": cfg["text_max_position_embeddings"]}
+        NO_GRAD_ = set(self.no_grad)
+        decay = [n for n in self.schema if n not in NO_GRAD_ and uses_weight_decay(n)]
+        nodecay = [n for n in self.schema if n not in NO_GRAD_ and not uses_weight_decay(n)]
+        frozen = [n for n in self.schema if n in NO_GRAD_]
         self.offsets: Dict[str, int] = {}
         off = 0
         for group in (decay, nodecay, frozen):
@@ -103,6 +164,7 @@ class ParamStore:
             self.exp_avg = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
             self.exp_avg_sq = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
         self.step = 0
+        self.version = 0          # bumped whenever the master weights change (load / optimizer step): derived operand caches key on it
 
     # ---- views
     def _view(self, buf, name, shape=None, numel=None):
@@ -132,7 +194,8 @@ class ParamStore:
         return list(self.schema.keys())
 
     def trainable_names(self) -> List[str]:
-        return [n for n in self.schema if n not in NO_GRAD]
+        ng = set(self.no_grad)
+        return [n for n in self.schema if n not in ng]
 
     def ranges_for(self, prefix: str) -> List[Tuple[int, int]]:
         """Contiguous [start, end) element ranges of the flat gradient covering every trainable tensor whose name starts with
@@ -156,11 +219,14 @@ class ParamStore:
                 missing.append(n)
                 continue
             t = sd[n]
+            if n == "logit_scale" and t.numel() == 1:
+                t = t.reshape(shape)          # scalar in chinese_clip checkpoints, [1] in huggingface_clip ones
             if tuple(t.shape) != tuple(shape):
                 raise ValueError(f"shape mismatch for {n}: checkpoint {tuple(t.shape)} vs model {tuple(shape)}")
             self.p(n).copy_(t.to(device=self.device, dtype=torch.float32))
         if strict and missing:
             raise KeyError(f"missing keys: {missing[:5]}...")
+        self.version += 1
         self.refresh_shadow()
         return missing
 
@@ -168,8 +234,8 @@ class ParamStore:
         out = OrderedDict()
         for n in self.schema:
             out[n] = self.p(n).detach().clone()
-        # buffer exported by the reference BertEmbeddings (modeling_bert.py:87)
-        out["bert.embeddings.position_ids"] = torch.arange(self.cfg["text_max_position_embeddings"], device=self.device).unsqueeze(0)
+        for name, n in self.buffers.items():
+            out[name] = torch.arange(n, device=self.device).unsqueeze(0)
         return out
 
     def refresh_shadow(self):

@@ -133,7 +133,9 @@ int clipk_colsum(const void* x, int is_f32, long long ldx, float* out, int rows,
 /* -------------------------------------------------------------------------------------------- embeddings
  * ViT patch embed (modeling_chineseclip.py:224,237-241): pixels f32 [B,3,R,R] -> bf16 patches [B*g*g, 3*P*P]
  * (column order of conv1.weight.view(W,-1)); then a GEMM; then token assembly x0 = [cls | patches] + pos.       */
-int clipk_im2col_patches(const float* pixels, void* patches_bf16, int B, int R, int P, cudaStream_t stream);
+/* ld_out: leading dimension of the patch matrix in elements (0 = 3*P*P); ViT-L-14 pads 588 -> 592 so that rows stay 16-byte multiples
+ * for the TMA loads of the patch GEMM (the caller zero-fills the padding columns once) */
+int clipk_im2col_patches(const float* pixels, void* patches_bf16, int B, int R, int P, int ld_out, cudaStream_t stream);
 int clipk_vit_assemble(const float* patch_f32, const float* cls, const float* pos, float* x0, int B, int L, int W,
                        cudaStream_t stream);
 int clipk_vit_assemble_bwd(const float* dx0, void* dpatch_bf16, int B, int L, int W, cudaStream_t stream);
@@ -144,6 +146,21 @@ int clipk_bert_embed(const long long* ids, const float* word, const float* pos, 
                      cudaStream_t stream);
 int clipk_bert_embed_bwd(const long long* ids, const float* de, float* dword, int rows, int H, int vocab,
                          cudaStream_t stream);
+
+/* RoBERTa-style embeddings of the huggingface_clip branch's text tower (modelzoo/models/roberta/modeling_roberta.py:65-130):
+ * position ids = cumsum(ids != pad) * (ids != pad) + pad (:1497-1510); e = word[ids] + pos[pos_ids] + type[type_ids];
+ * key_mask = (1 - attention_mask) * -10000 (the batch's mask, appzoo/clip/model.py:132-134) or from ids != pad when NULL.
+ * Backward scatters de into the three tables; rows `pad_id` of the word and position tables (padding_idx) get no gradient. */
+int clipk_position_ids(const long long* ids, int* pos_ids, int B, int L, int pad_id, cudaStream_t stream);
+int clipk_embed_gather(const long long* ids, const int* pos_ids, const long long* type_ids /* optional */,
+                       const long long* attn_mask /* optional */, const float* word, const float* pos, const float* type, float* e,
+                       float* key_mask /* optional */, int rows, int H, int vocab, int npos, int ntype, int pad_id, cudaStream_t stream);
+int clipk_embed_gather_bwd(const long long* ids, const int* pos_ids, const long long* type_ids, const float* de, float* dword,
+                           float* dpos, float* dtype, int rows, int H, int vocab, int npos, int ntype, int pad_id, cudaStream_t stream);
+/* pooler activation (RobertaPooler: tanh(dense(h[:,0])), modeling_roberta.py:559-575; used as the text feature by the
+ * huggingface_clip branch, appzoo/clip/model.py:135): y = tanh(x) (+ bf16 copy); dx = dy * (1 - y^2) */
+int clipk_tanh_fwd(const float* x, float* y, void* y_bf16 /* optional */, long long n, cudaStream_t stream);
+int clipk_tanh_bwd(const float* dy, const float* y, float* dx /* optional */, void* dx_bf16 /* optional */, long long n, cudaStream_t stream);
 
 /* -------------------------------------------------------------------------------------------- head
  * y = x / ||x||_2 per row (modeling_chineseclip.py:360,363) and its backward.                                   */

@@ -370,3 +370,138 @@ def rank_of_match(text_embeds: Tensor, image_embeds: Tensor) -> Tensor:
     agreement = text_embeds @ image_embeds.t()
     diag = agreement.diagonal().unsqueeze(1)
     return (agreement > diag).sum(dim=1)
+
+
+# =========================================================================== huggingface_clip branch
+# appzoo/clip/model.py:73-104,128-144: text = RobertaModel (modelzoo/models/roberta/modeling_roberta.py:65-575: pad-aware position ids
+# :1497-1510, BERT-style post-LN encoder, tanh pooler), image = CLIPVisionModel (modelzoo/models/clip/modeling_clip.py:112-140,173-334,
+# 731-776) whose pooled output is DETACHED (model.py:142), biased text_projection / vision_projection Linears, logit_scale [1].
+def hf_tiny_config() -> dict:
+    """nested config.json of the reference's huggingface_clip branch at a small shape (2 heads of 64 per tower)"""
+    return {"text_config": dict(vocab_size=512, hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                                max_position_embeddings=64, hidden_act="gelu", layer_norm_eps=1e-12, pad_token_id=0, type_vocab_size=2,
+                                hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0),
+            "vision_config": dict(hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2, image_size=64,
+                                  patch_size=16, hidden_act="quick_gelu", layer_norm_eps=1e-5, attention_dropout=0.0),
+            "projection_dim": 128}
+
+
+def hf_init_state_dict(raw_cfg: dict, seed: int = 1234, scale_boost: float = 1.0) -> Dict[str, Tensor]:
+    """seeded random checkpoint with the reference's huggingface_clip key names"""
+    g = torch.Generator().manual_seed(seed)
+    t = raw_cfg["text_config"]; v = raw_cfg["vision_config"]; E = raw_cfg.get("projection_dim", 512)
+
+    def randn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    sd: Dict[str, Tensor] = {}
+    W = v["hidden_size"]; P = v["patch_size"]; Iv = v["intermediate_size"]; n_tok = (v["image_size"] // P) ** 2 + 1
+    H = t["hidden_size"]; I = t["intermediate_size"]; r = 0.02
+    sd["logit_scale"] = torch.tensor([math.log(1 / 0.07)])
+    sd["text_projection.weight"] = randn(E, H, std=H ** -0.5); sd["text_projection.bias"] = 0.02 * randn(E)
+    sd["vision_projection.weight"] = randn(E, W, std=W ** -0.5); sd["vision_projection.bias"] = 0.02 * randn(E)
+    p = "vision_encoder.vision_model."
+    sd[p + "embeddings.class_embedding"] = randn(W, std=W ** -0.5)
+    sd[p + "embeddings.patch_embedding.weight"] = randn(W, 3, P, P, std=(3 * P * P) ** -0.5)
+    sd[p + "embeddings.position_embedding.weight"] = randn(n_tok, W, std=W ** -0.5)
+    sd[p + "embeddings.position_ids"] = torch.arange(n_tok).unsqueeze(0)
+
+    def ln(prefix, d):
+        sd[prefix + ".weight"] = 1.0 + 0.1 * randn(d); sd[prefix + ".bias"] = 0.1 * randn(d)
+
+    ln(p + "pre_layrnorm", W)
+    for i in range(v["num_hidden_layers"]):
+        q = p + f"encoder.layers.{i}."
+        for nm in ("q_proj", "k_proj", "v_proj"):
+            sd[q + f"self_attn.{nm}.weight"] = randn(W, W, std=W ** -0.5) * scale_boost; sd[q + f"self_attn.{nm}.bias"] = 0.02 * randn(W)
+        sd[q + "self_attn.out_proj.weight"] = randn(W, W, std=W ** -0.5 * (2 * v["num_hidden_layers"]) ** -0.5); sd[q + "self_attn.out_proj.bias"] = 0.02 * randn(W)
+        ln(q + "layer_norm1", W)
+        sd[q + "mlp.fc1.weight"] = randn(Iv, W, std=(2 * W) ** -0.5); sd[q + "mlp.fc1.bias"] = 0.02 * randn(Iv)
+        sd[q + "mlp.fc2.weight"] = randn(W, Iv, std=W ** -0.5 * (2 * v["num_hidden_layers"]) ** -0.5); sd[q + "mlp.fc2.bias"] = 0.02 * randn(W)
+        ln(q + "layer_norm2", W)
+    ln(p + "post_layernorm", W)
+    p = "text_encoder."
+    sd[p + "embeddings.position_ids"] = torch.arange(t["max_position_embeddings"]).unsqueeze(0)
+    sd[p + "embeddings.word_embeddings.weight"] = randn(t["vocab_size"], H, std=r); sd[p + "embeddings.word_embeddings.weight"][t["pad_token_id"]].zero_()
+    sd[p + "embeddings.position_embeddings.weight"] = randn(t["max_position_embeddings"], H, std=r)
+    sd[p + "embeddings.position_embeddings.weight"][t["pad_token_id"]].zero_()
+    sd[p + "embeddings.token_type_embeddings.weight"] = randn(t["type_vocab_size"], H, std=r)
+    ln(p + "embeddings.LayerNorm", H)
+    for i in range(t["num_hidden_layers"]):
+        q = p + f"encoder.layer.{i}."
+        for nm in ("query", "key", "value"):
+            sd[q + f"attention.self.{nm}.weight"] = randn(H, H, std=r) * scale_boost; sd[q + f"attention.self.{nm}.bias"] = 0.02 * randn(H)
+        sd[q + "attention.output.dense.weight"] = randn(H, H, std=r); sd[q + "attention.output.dense.bias"] = 0.02 * randn(H)
+        ln(q + "attention.output.LayerNorm", H)
+        sd[q + "intermediate.dense.weight"] = randn(I, H, std=r); sd[q + "intermediate.dense.bias"] = 0.02 * randn(I)
+        sd[q + "output.dense.weight"] = randn(H, I, std=r); sd[q + "output.dense.bias"] = 0.02 * randn(H)
+        ln(q + "output.LayerNorm", H)
+    sd[p + "pooler.dense.weight"] = randn(H, H, std=H ** -0.5); sd[p + "pooler.dense.bias"] = 0.02 * randn(H)
+    return sd
+
+
+def hf_vision_forward(sd: Dict[str, Tensor], v: dict, pixels: Tensor) -> Tensor:
+    """CLIPVisionTransformer.forward -> pooled = post_layernorm(last_hidden[:, 0])  (modeling_clip.py:731-776)"""
+    p = "vision_encoder.vision_model."
+    W = v["hidden_size"]; heads = v["num_attention_heads"]
+    act = quick_gelu if v.get("hidden_act", "quick_gelu") == "quick_gelu" else F.gelu
+    x = F.conv2d(pixels, sd[p + "embeddings.patch_embedding.weight"], stride=v["patch_size"])
+    B = x.shape[0]
+    x = x.flatten(2).transpose(1, 2)
+    x = torch.cat([sd[p + "embeddings.class_embedding"].expand(B, 1, W), x], dim=1) + sd[p + "embeddings.position_embedding.weight"]
+    x = F.layer_norm(x, (W,), sd[p + "pre_layrnorm.weight"], sd[p + "pre_layrnorm.bias"], 1e-5)
+    for i in range(v["num_hidden_layers"]):
+        q = p + f"encoder.layers.{i}."
+        h = F.layer_norm(x, (W,), sd[q + "layer_norm1.weight"], sd[q + "layer_norm1.bias"], 1e-5)
+        w_in = torch.cat([sd[q + f"self_attn.{n}.weight"] for n in ("q_proj", "k_proj", "v_proj")], 0)
+        b_in = torch.cat([sd[q + f"self_attn.{n}.bias"] for n in ("q_proj", "k_proj", "v_proj")], 0)
+        x = x + _mha(h, w_in, b_in, sd[q + "self_attn.out_proj.weight"], sd[q + "self_attn.out_proj.bias"], heads)   # q * scale == scores / sqrt(dh)
+        h = F.layer_norm(x, (W,), sd[q + "layer_norm2.weight"], sd[q + "layer_norm2.bias"], 1e-5)
+        h = act(h @ sd[q + "mlp.fc1.weight"].t() + sd[q + "mlp.fc1.bias"])
+        x = x + (h @ sd[q + "mlp.fc2.weight"].t() + sd[q + "mlp.fc2.bias"])
+    return F.layer_norm(x[:, 0, :], (W,), sd[p + "post_layernorm.weight"], sd[p + "post_layernorm.bias"], 1e-5)
+
+
+def hf_text_forward(sd: Dict[str, Tensor], t: dict, ids: Tensor, token_type_ids: Optional[Tensor] = None,
+                    attention_mask: Optional[Tensor] = None) -> Tensor:
+    """RobertaModel(...)[1] = tanh pooler output (modeling_roberta.py:100-130,559-575,1497-1510)"""
+    p = "text_encoder."
+    H = t["hidden_size"]; heads = t["num_attention_heads"]; pad = t.get("pad_token_id", 0); eps = t.get("layer_norm_eps", 1e-12)
+    B, L = ids.shape
+    m = ids.ne(pad).int()
+    pos = (torch.cumsum(m, dim=1) * m).long() + pad
+    tt = token_type_ids if token_type_ids is not None else torch.zeros_like(ids)
+    x = (sd[p + "embeddings.word_embeddings.weight"][ids] + sd[p + "embeddings.token_type_embeddings.weight"][tt]
+         + sd[p + "embeddings.position_embeddings.weight"][pos])
+    x = F.layer_norm(x, (H,), sd[p + "embeddings.LayerNorm.weight"], sd[p + "embeddings.LayerNorm.bias"], eps)
+    am = attention_mask if attention_mask is not None else ids.ne(pad).long()
+    mask = (1.0 - am.to(x.dtype))[:, None, None, :] * -10000.0
+    for i in range(t["num_hidden_layers"]):
+        q = p + f"encoder.layer.{i}."
+        w_in = torch.cat([sd[q + f"attention.self.{n}.weight"] for n in ("query", "key", "value")], 0)
+        b_in = torch.cat([sd[q + f"attention.self.{n}.bias"] for n in ("query", "key", "value")], 0)
+        a = _mha(x, w_in, b_in, sd[q + "attention.output.dense.weight"], sd[q + "attention.output.dense.bias"], heads, mask)
+        x = F.layer_norm(a + x, (H,), sd[q + "attention.output.LayerNorm.weight"], sd[q + "attention.output.LayerNorm.bias"], eps)
+        h = F.gelu(x @ sd[q + "intermediate.dense.weight"].t() + sd[q + "intermediate.dense.bias"])
+        h = h @ sd[q + "output.dense.weight"].t() + sd[q + "output.dense.bias"]
+        x = F.layer_norm(h + x, (H,), sd[q + "output.LayerNorm.weight"], sd[q + "output.LayerNorm.bias"], eps)
+    return torch.tanh(x[:, 0] @ sd[p + "pooler.dense.weight"].t() + sd[p + "pooler.dense.bias"])
+
+
+def hf_clip_forward(sd: Dict[str, Tensor], raw_cfg: dict, pixels: Optional[Tensor], ids: Optional[Tensor],
+                    token_type_ids: Optional[Tensor] = None, attention_mask: Optional[Tensor] = None) -> dict:
+    """CLIPApp.forward, huggingface_clip branch (appzoo/clip/model.py:128-150)"""
+    image_embeds = text_embeds = None
+    if ids is not None:
+        tfeat = hf_text_forward(sd, raw_cfg["text_config"], ids, token_type_ids, attention_mask)
+        tfeat = tfeat @ sd["text_projection.weight"].t() + sd["text_projection.bias"]
+        text_embeds = tfeat / tfeat.norm(dim=-1, keepdim=True)
+    if pixels is not None:
+        pooled = hf_vision_forward(sd, raw_cfg["vision_config"], pixels).detach()          # model.py:142
+        f = pooled @ sd["vision_projection.weight"].t() + sd["vision_projection.bias"]
+        image_embeds = f / f.norm(dim=-1, keepdim=True)
+    out = {"image_embeds": image_embeds, "text_embeds": text_embeds}
+    if image_embeds is not None and text_embeds is not None:
+        lpt = (text_embeds @ image_embeds.t()) * sd["logit_scale"].exp()
+        out["logits_per_text"] = lpt; out["logits_per_image"] = lpt.T
+    return out

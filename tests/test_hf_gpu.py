@@ -1,0 +1,115 @@
+"""GPU parity of the huggingface_clip branch (appzoo/clip/model.py:73-104,128-144; BASELINE configs[3] family): RobertaModel text tower
+with pad-aware position ids / batch token types / batch attention mask / tanh pooler, frozen CLIPVisionModel image tower, biased
+projections -- against the fixture written by the unmodified reference (oracle/make_golden_hf.py) and the oracle on fresh inputs."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from easynlp_b200.engine import ClipEngine, hf_engine_config  # noqa: E402
+from oracle import clip_oracle as O  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def max_err(a, b):
+    return (a.detach().float().cpu() - b.detach().float().cpu()).abs().max().item()
+
+
+def load():
+    z = np.load(os.path.join(GOLD, "hf_tiny_fwd_bwd.npz"))
+    raw = json.loads(bytes(z["cfg_json"]).decode())
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w.")}
+    return z, raw, sd
+
+
+def yardstick(sd, raw, pixels, ids, tt, am):
+    names = [k for k, v in sd.items() if v.is_floating_point()]
+    params = {k: sd[k].clone().requires_grad_(True) for k in names}
+    full = dict(sd); full.update(params)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        out = O.hf_clip_forward(full, raw, pixels, ids, tt, am)
+    out = {k: v.float() for k, v in out.items()}
+    loss = O.clip_loss(out["logits_per_text"])
+    g = torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)
+    return loss.item(), out, {k: v for k, v in zip(names, g) if v is not None}
+
+
+def test_hf_tiny_forward_backward_vs_reference_golden():
+    z, raw, sd = load()
+    cfg = hf_engine_config(raw, sd["text_projection.weight"].shape[0])
+    eng = ClipEngine(cfg)
+    missing = eng.params.load_state_dict(sd)
+    assert not missing
+    pixels = torch.from_numpy(z["pixels"]); ids = torch.from_numpy(z["ids"]); tt = torch.from_numpy(z["token_type_ids"]); am = torch.from_numpy(z["attention_mask"])
+    out = eng.forward(pixels.cuda(), ids.cuda(), token_type_ids=tt.cuda(), attention_mask=am.cuda())
+    torch.cuda.synchronize()
+    ref = {k: torch.from_numpy(z["out." + k]) for k in ("image_embeds", "text_embeds", "logits_per_text")}
+    yl, yo, yg = yardstick(sd, raw, pixels, ids, tt, am)
+    e = {k: max_err(out[k], ref[k]) for k in ref}; y = {k: max_err(yo[k], ref[k]) for k in ref}
+    loss_ref = float(z["out.loss"]); loss = out["loss"].item()
+    print(f"PARITY hf tiny fwd: err {e} (PyTorch bf16 yardstick {y}); loss {loss:.6f} vs {loss_ref:.6f}")
+    # same bound as the chinese_clip tests: no worse than 1.5x PyTorch's own bf16 autocast on the same inputs
+    assert e["image_embeds"] < 1.5 * y["image_embeds"] + 1e-4 and e["text_embeds"] < 1.5 * y["text_embeds"] + 1e-4
+    assert e["logits_per_text"] < 1.5 * y["logits_per_text"] + 1e-3
+    assert abs(loss - loss_ref) < max(1e-3 * abs(loss_ref), 2.0 * abs(yl - loss_ref))
+    eng.zero_grad(); eng.backward()
+    torch.cuda.synchronize()
+    refg = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("g.")}
+    gnorm = math.sqrt(sum(float(v.double().norm()) ** 2 for v in refg.values()))
+    worst = (0.0, None)
+    for k, r in refg.items():
+        got = eng.params.g(k).detach().float().cpu().view_as(r)
+        err = (got - r).norm().item(); yerr = (yg[k].float() - r).norm().item()
+        tol = max(0.03 * r.norm().item(), 1.5 * yerr) + 1e-4 * gnorm
+        worst = max(worst, (err / (r.norm().item() + 1e-4 * gnorm), k))
+        assert err <= tol, f"grad {k}: err {err:.3e} > tol {tol:.3e} (|ref| {r.norm().item():.3e}, yardstick {yerr:.3e})"
+    print(f"PARITY hf tiny bwd: worst per-tensor relative gradient error {worst[0]:.3e} ({worst[1]})")
+    # the frozen tower's parameters sit outside the updated range and carry no gradient slots
+    assert all(n.startswith("vision_encoder.") for n in eng.params.no_grad)
+    assert "vision_encoder.vision_model.post_layernorm.weight" not in eng.params.trainable_names()
+    before = eng.params.p("vision_encoder.vision_model.embeddings.class_embedding").clone()
+    tb = eng.params.p("text_encoder.pooler.dense.weight").clone()
+    eng.optimizer_step(lr=1e-3)
+    torch.cuda.synchronize()
+    assert torch.equal(before, eng.params.p("vision_encoder.vision_model.embeddings.class_embedding"))
+    assert (eng.params.p("text_encoder.pooler.dense.weight") - tb).abs().max().item() > 1e-5      # the pooler IS trained on this branch
+
+
+def test_hf_plugin_surface_and_defaults(tmp_path):
+    """get_application_model on a huggingface_clip checkpoint directory: key names without a prefix, feat=True paths, missing
+    token_type_ids / attention_mask (type 0, mask from ids != pad), Trainer step with dropout on."""
+    from easynlp_b200.appzoo import get_application_model
+    z, raw, sd = load()
+    raw = json.loads(json.dumps(raw)); raw["text_config"]["hidden_dropout_prob"] = 0.1; raw["text_config"]["attention_probs_dropout_prob"] = 0.1
+    d = str(tmp_path / "hf")
+    os.makedirs(d)
+    json.dump(raw, open(os.path.join(d, "config.json"), "w"))
+    torch.save(sd, os.path.join(d, "pytorch_model.bin"))
+    open(os.path.join(d, "vocab.txt"), "w").write("[PAD]\n[UNK]\n[CLS]\n[SEP]\n")
+    model = get_application_model("clip", d, user_defined_parameters={"app_parameters": {}})
+    assert model.model_type == "huggingface_clip"
+    names = [n for n, _ in model.named_parameters()]
+    assert "text_projection.bias" in names and "vision_encoder.vision_model.pre_layrnorm.weight" in names and "logit_scale" in names
+    sd2 = model.state_dict()
+    assert "text_encoder.embeddings.position_ids" in sd2 and torch.equal(sd2["vision_projection.weight"].cpu(), sd["vision_projection.weight"])
+    ids = torch.from_numpy(z["ids"]); pixels = torch.from_numpy(z["pixels"])
+    model.eval()
+    with torch.no_grad():
+        f = model({"input_ids": ids.clone()}, feat=True)               # no token types / mask given
+        g = model({"pixel_values": pixels.clone()}, feat=True)
+    ref = O.hf_clip_forward(sd, json.loads(bytes(z["cfg_json"]).decode()), pixels, ids, None, None)
+    assert f["image_embeds"] is None and max_err(f["text_embeds"], ref["text_embeds"]) < 5e-3
+    assert g["text_embeds"] is None and max_err(g["image_embeds"], ref["image_embeds"]) < 5e-3
+    # one fused training step through the engine (dropout on): finite, moves only trainable tensors
+    model.train()
+    vis = model.engine.params.p("vision_encoder.vision_model.encoder.layers.0.mlp.fc1.weight").clone()
+    out = model.engine.train_step(pixels, ids, lr=1e-3, use_graph=False, token_type_ids=torch.from_numpy(z["token_type_ids"]),
+                                  attention_mask=torch.from_numpy(z["attention_mask"]))
+    assert math.isfinite(out["loss"].item())
+    assert torch.equal(vis, model.engine.params.p("vision_encoder.vision_model.encoder.layers.0.mlp.fc1.weight"))

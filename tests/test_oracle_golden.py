@@ -92,3 +92,34 @@ def test_decay_grouping_and_schedule():
     assert O.warmup_linear_lambda(10, 10, 100) == 1.0
     assert abs(O.warmup_linear_lambda(55, 10, 100) - 0.5) < 1e-12
     assert O.warmup_linear_lambda(100, 10, 100) == 0.0
+
+
+def test_hf_oracle_matches_reference_golden():
+    """huggingface_clip branch (RobertaModel + frozen CLIPVisionModel + biased projections, appzoo/clip/model.py:73-104,128-144): the
+    oracle restatement against the fixture written by the UNMODIFIED reference (oracle/make_golden_hf.py), forward and every gradient."""
+    import json
+    z = np.load(os.path.join(GOLD, "hf_tiny_fwd_bwd.npz"))
+    raw = json.loads(bytes(z["cfg_json"]).decode())
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w.")}
+    names = [k for k, v in sd.items() if v.is_floating_point()]
+    params = {k: sd[k].clone().requires_grad_(True) for k in names}
+    full = dict(sd); full.update(params)
+    out = O.hf_clip_forward(full, raw, torch.from_numpy(z["pixels"]), torch.from_numpy(z["ids"]), torch.from_numpy(z["token_type_ids"]),
+                            torch.from_numpy(z["attention_mask"]))
+    for k in ("image_embeds", "text_embeds", "logits_per_text"):
+        assert torch.allclose(out[k], torch.from_numpy(z["out." + k]), rtol=2e-4, atol=2e-5), k
+    loss = O.clip_loss(out["logits_per_text"])
+    assert abs(loss.item() - float(z["out.loss"])) < 1e-5
+    grads = dict(zip(names, torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)))
+    ref = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("g.")}
+    assert len(ref) == 44
+    for k, g in grads.items():
+        if k.startswith("vision_encoder."):
+            assert g is None and k not in ref, k                      # frozen by .detach()
+        else:
+            assert k in ref and torch.allclose(g, ref[k], rtol=2e-3, atol=2e-6), k
+    # pad-aware position ids (modeling_roberta.py:1497-1510): padded tokens stay at pad_token_id, real ones count from pad + 1
+    ids = torch.from_numpy(z["ids"])
+    m = ids.ne(0).int()
+    pos = torch.cumsum(m, 1) * m
+    assert pos[3].tolist()[:3] == [1, 2, 0] and pos.max().item() == 16
