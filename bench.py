@@ -42,6 +42,21 @@ def b16_config():
                 text_max_position_embeddings=512, text_num_attention_heads=12, text_num_hidden_layers=12, text_type_vocab_size=2)
 
 
+def l14_config():
+    """BASELINE configs[3]: CLIP ViT-L/14 + BERT-large-shaped text tower = the reference's huggingface_clip branch (frozen image tower,
+    RobertaModel text tower, E = 768)"""
+    from easynlp_b200.engine import hf_engine_config
+    raw = {"text_config": dict(vocab_size=21128, hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                               max_position_embeddings=512, hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1),
+           "vision_config": dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16, image_size=224, patch_size=14,
+                                 hidden_act="quick_gelu")}
+    return hf_engine_config(raw, 768)
+
+
+# SURVEY.md 8(d): ViT-L/14 fwd 162.03 GF (no backward: frozen) + text tower 47.09 GF fwd + 2x bwd = 303.3 GF per pair
+FLOPS_TRAIN_PER_PAIR_L14 = 162_025_537_536 + 3 * 47_092_957_184
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -236,7 +251,9 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist_on = world > 1
-    cfg = b16_config()
+    l14 = args.config == "l14"
+    cfg = l14_config() if l14 else b16_config()
+    flops_pair = FLOPS_TRAIN_PER_PAIR_L14 if l14 else FLOPS_TRAIN_PER_PAIR
     B, Lt = args.batch, args.seq_len
     eng = ClipEngine(cfg, device=dev)
     eng.params.load_state_dict(random_state_dict(cfg, seed=1234, device="cpu"))
@@ -296,7 +313,8 @@ def run_native(args):
             def batch_fn(self, f):
                 return f
         app = CLIPApp()
-        app.engine = eng; app.model_type = "chinese_clip"; app._wrap_params(); app.distributed_loss = dist_on
+        app.engine = eng; app.model_type = "huggingface_clip" if l14 else "chinese_clip"; app.prefix = "" if l14 else "chinese_clip."
+        app._wrap_params(); app.distributed_loss = dist_on
         app.train()
         targs = parse_args(["--micro_batch_size", str(B), "--learning_rate", str(lr), "--epoch_num", "1", "--warmup_proportion", "0.0",
                             "--data_threads", "0", "--logging_steps", "1000000"])
@@ -353,10 +371,12 @@ def run_native(args):
                     "step_breakdown_ms": {k: round(v[2], 3) for k, v in agg.items()} | {"step_total": round(ms_per_step, 3)},
                     "gemm_shapes_MxNxK|majors|mode": gemm_shapes,
                     "attention_tflops": {k: round(agg[k][1] / (agg[k][2] * 1e-3) / 1e12, 1) for k in agg if k.startswith("attention")},
-                    "whole_step_frac_of_peak": (B * FLOPS_TRAIN_PER_PAIR / (ms_per_step * 1e-3) / 1e12) / peak}
+                    "whole_step_frac_of_peak": (B * flops_pair / (ms_per_step * 1e-3) / 1e12) / peak}
 
     # ---- CPU baseline: the oracle port on the host cores (rank 0, N = 1 only), bounded sample
     cpu = None
+    if l14:
+        args.no_cpu_baseline = True; args.no_gpu_baseline = True      # the CPU / GPU reference legs and the parity fixture are for configs[1]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, cores, nst, ncpu, kind = reference_cpu_throughput(8, Lt, 3, 1, budget_s=30.0)
         cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
@@ -379,7 +399,8 @@ def run_native(args):
         line = {"metric": "train_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": "CLIP ViT-B/16 + BERT-base contrastive training step (BASELINE configs[1]): fwd + InfoNCE + bwd + clip + AdamW",
+                "config": {"workload": ("CLIP ViT-L/14 (frozen, forward only) + 24-layer d=1024 text tower, huggingface_clip branch (BASELINE configs[3]): fwd + InfoNCE + text-tower bwd + clip + AdamW"
+                                        if l14 else "CLIP ViT-B/16 + BERT-base contrastive training step (BASELINE configs[1]): fwd + InfoNCE + bwd + clip + AdamW"),
                            "per_gpu_batch": B, "global_batch": world * B, "seq_len": Lt, "image": "224x224x3 fp32", "parallelism": f"dp{world}",
                            "loss": "global-batch InfoNCE via embedding all-gather" if dist_on else "local == global batch",
                            "dropout": "text tower hidden 0.1 / attention-probs 0.1 (fused Philox, masks regenerated in backward); ViT tower has none", "l2": "per-step working set (~15 GB of activations) >> 126 MB L2; no explicit flush needed",
@@ -419,6 +440,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--seq-len", type=int, default=77)
+    ap.add_argument("--config", default="b16", choices=["b16", "l14"], help="b16 = BASELINE configs[1]/[2] (default); l14 = configs[3] (ViT-L/14 + 24-layer text tower, huggingface_clip)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference sample and the parity checker leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-on-this-GPU leg (unmodified reference under bf16 autocast)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured CUDA graph")

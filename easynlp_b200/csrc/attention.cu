@@ -653,9 +653,9 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
-static int check_shapes(const char* who, int B, int L, int H, int d) {
+static int check_shapes(const char* who, int B, int L, int H, int d, int lmax = 256) {
   if (B <= 0 || L <= 0 || H <= 0 || d != H * 64) { set_error("%s: need d == 64*H (B=%d L=%d H=%d d=%d)", who, B, L, H, d); return CLIPK_ERR_ARG; }
-  if (L > 256) { set_error("%s: sequence length %d > 256 is not supported by the one-shot kernel yet", who, L); return CLIPK_ERR_UNSUPPORTED; }
+  if (L > lmax) { set_error("%s: sequence length %d > 256 is not supported by the one-shot kernel yet", who, L); return CLIPK_ERR_UNSUPPORTED; }
   return 0;
 }
 
@@ -665,7 +665,7 @@ using namespace clipk;
 
 extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void* ctx, float* lse, int B, int L, int H, int d,
                                    const clipk_dropout_t* drop, cudaStream_t stream) {
-  int rc = check_shapes("attention_fwd", B, L, H, d);
+  int rc = check_shapes("attention_fwd", B, L, H, d, 272);
   if (rc) return rc;
   AttnParams p{};
   p.B = B; p.L = L; p.H = H; p.d = d;
@@ -677,6 +677,7 @@ extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void*
   // default: the persistent warp-specialised pipeline (attention_fwd2.cu); CLIPK_ATTN_V1=1 selects the first-generation kernel (A/B runs)
   { const char* ev = getenv("CLIPK_ATTN_DBG_PTR"); if (ev) p.dbg = reinterpret_cast<long long*>(strtoull(ev, nullptr, 0)); }
   { const char* ev = getenv("CLIPK_ATTN_V1"); if (!(ev && ev[0] == '1')) return attention_fwd2(qkv, p, stream); }
+  if (L > 256) { set_error("attention_fwd: the first-generation kernel handles L <= 256 (L=%d)", L); return CLIPK_ERR_UNSUPPORTED; }
   CUtensorMap tQ, tKV;
   if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, p.lk_pad))) return rc;

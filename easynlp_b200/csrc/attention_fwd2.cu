@@ -35,13 +35,16 @@ struct Fwd2Smem {            // byte offsets inside the dynamic shared memory (b
   int stage_bytes;           // K + V + q_tiles * 16 KB
   int mask_off, red_off, bar_off, total;
 };
+constexpr int F2_MASK = 288;     // floats of key mask per stage (keys <= 272)
+// one item stage = K + V + all query tiles; two stages (the next item is prefetched) when they fit, else one
+__host__ __device__ inline int fwd2_stages(int n16, int q_tiles) { return 2 * (2 * n16 * 2048 + q_tiles * 16384) + 16384 <= 232448 - 1024 ? 2 : 1; }
 __host__ __device__ inline Fwd2Smem fwd2_layout(int n16, int q_tiles) {
   Fwd2Smem s;
   s.kv_bytes = n16 * 16 * 128;
   s.stage_bytes = 2 * s.kv_bytes + q_tiles * 16384;
-  s.mask_off = 2 * s.stage_bytes;                 // [2 stages][256] floats
-  s.red_off = s.mask_off + 2 * 256 * 4;           // max [2 buf][4][128], sum [2 buf][4][128], rowmax [2 buf][128]
-  s.bar_off = s.red_off + (2 * 4 * 128 * 2 + 2 * 128) * 4;
+  s.mask_off = fwd2_stages(n16, q_tiles) * s.stage_bytes;   // [2 stages][F2_MASK] floats
+  s.red_off = s.mask_off + 2 * F2_MASK * 4;       // max [2 buf][4][128], sum [3][4][128], rowmax [3][128]
+  s.bar_off = s.red_off + (2 * 4 * 128 + 3 * 4 * 128 + 3 * 128) * 4;
   s.total = s.bar_off + 256;
   return s;
 }
@@ -53,15 +56,20 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   constexpr int KEYS = N16 * 16;          // key columns of S (keys beyond L are masked to -inf)
   constexpr int CPT = N16 * 4;            // columns per softmax thread
   constexpr int BUF1 = (KEYS + 31) / 32 * 32;             // column of the second tile buffer
-  constexpr bool O_SEP = BUF1 + KEYS <= 448;              // room for a separate O accumulator at [448, 512)
-  constexpr int BUF_STRIDE = O_SEP ? BUF1 : 256;
+  constexpr int NBUF = KEYS <= 256 ? 2 : 1;               // keys > 256 (ViT-L/14: 257 tokens -> 272): one tile buffer of 272 columns
+  constexpr bool O_SEP = NBUF == 1 || BUF1 + KEYS <= 448; // room for a separate O accumulator at [448, 512)
+  constexpr int BUF_STRIDE = NBUF == 1 ? 0 : (O_SEP ? BUF1 : 256);
+  constexpr int KBOX = KEYS <= 256 ? 1 : 2;               // TMA boxes per K / V tile (a box holds <= 256 rows)
+  const int NST = fwd2_stages(N16, p.q_tiles);
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const Fwd2Smem lay = fwd2_layout(N16, p.q_tiles);
   float* smask = reinterpret_cast<float*>(smem + lay.mask_off);
   float* sred_max = reinterpret_cast<float*>(smem + lay.red_off);         // [buf][cq][row]
-  float* sred_sum = sred_max + 2 * 4 * 128;                               // [buf][cq][row]
-  float* srow_max = sred_sum + 2 * 4 * 128;                               // [buf][row]
+  // row sums / row maxima travel from the softmax warps of tile i to its epilogue in slot i % 3: the slot is rewritten by tile i+3, whose
+  // S is issued after PV(i+1), which waited for the epilogue of tile i (o_free / buf_free)
+  float* sred_sum = sred_max + 2 * 4 * 128;                               // [i % 3][cq][row]
+  float* srow_max = sred_sum + 3 * 4 * 128;                               // [i % 3][row]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
   uint64_t* kq_full = bars;            // [2] K + Q tiles + mask of a stage have landed
   uint64_t* v_full = bars + 2;         // [2]
@@ -102,20 +110,22 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     int j = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
       const int b = item / p.H, h = item - b * p.H;
-      const int stage = j & 1;
-      mbar_wait(&stage_empty[stage], ((j >> 1) & 1) ^ 1);
+      const int stage = j % NST;
+      mbar_wait(&stage_empty[stage], ((j / NST) & 1) ^ 1);
       uint8_t* sK = smem + stage * lay.stage_bytes;
       uint8_t* sV = sK + lay.kv_bytes;
       uint8_t* sQ = sV + lay.kv_bytes;
       if (lane == 0) {
         mbar_expect_tx(&kq_full[stage], lay.kv_bytes + T * 16384);
-        tma_load_2d(sK, &tmKV, &kq_full[stage], p.d + h * 64, b * p.L);
+#pragma unroll
+        for (int bx = 0; bx < KBOX; ++bx) tma_load_2d(sK + bx * (lay.kv_bytes / KBOX), &tmKV, &kq_full[stage], p.d + h * 64, b * p.L + bx * (KEYS / KBOX));
         for (int t = 0; t < T; ++t) tma_load_2d(sQ + t * 16384, &tmQ, &kq_full[stage], h * 64, b * p.L + t * 128);
         mbar_expect_tx(&v_full[stage], lay.kv_bytes);
-        tma_load_2d(sV, &tmKV, &v_full[stage], 2 * p.d + h * 64, b * p.L);
+#pragma unroll
+        for (int bx = 0; bx < KBOX; ++bx) tma_load_2d(sV + bx * (lay.kv_bytes / KBOX), &tmKV, &v_full[stage], 2 * p.d + h * 64, b * p.L + bx * (KEYS / KBOX));
       }
       // additive key mask of this sample in log2 units; keys beyond L (padding rows of the box = the next sample's tokens) -> -inf
-      float* m = smask + stage * 256;
+      float* m = smask + stage * F2_MASK;
       for (int c = lane; c < KEYS; c += 32) m[c] = (c < p.L) ? (p.mask ? p.mask[(long long)b * p.L + c] * LOG2E : 0.f) : -INFINITY;
       __syncwarp();
       if (lane == 0) mbar_arrive(&kq_full[stage]);
@@ -123,29 +133,36 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   } else if (warp == 1) {
     // ============================================================================================ MMA issuer (one thread)
     if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, KEYS, 0, 0);
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, KEYS <= 256 ? KEYS : 256, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
       const int n_tiles = ((n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * T;
       auto issue_s = [&](int k) {           // S(k) = Q_t K^T of tile k -> tile buffer k & 1
-        const int j = (T == 2) ? (k >> 1) : k, t = (T == 2) ? (k & 1) : 0;
-        const int stage = j & 1, buf = k & 1;
-        if (t == 0) mbar_wait(&kq_full[stage], (j >> 1) & 1);
+        const int j = k / T, t = k - j * T;
+        const int stage = j % NST, buf = k % NBUF;
+        if (t == 0) mbar_wait(&kq_full[stage], (j / NST) & 1);
         F2_DBG(k, 0);
-        if (!O_SEP) mbar_wait(&buf_free[buf], ((k >> 1) & 1) ^ 1);
+        if (!O_SEP) mbar_wait(&buf_free[buf], ((k / NBUF) & 1) ^ 1);
         tc_fence_after();
         F2_DBG(k, 1);
         const uint32_t aK = smem_u32(smem + stage * lay.stage_bytes);
         const uint32_t aQ = aK + 2 * lay.kv_bytes + t * 16384;
         const uint32_t dQ_ = umma_desc_lo(aQ, 16), dK_ = umma_desc_lo(aK, 16);       // K-major: k-step of 16 head dims = 32 B -> +2
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_bf16_lh(tmem + buf * BUF_STRIDE, dQ_ + 2 * kk, dK_ + 2 * kk, idesc_s, kk > 0);
+        for (int kk = 0; kk < 4; ++kk) {
+          if constexpr (KEYS <= 256) {
+            umma_bf16_lh(tmem + buf * BUF_STRIDE, dQ_ + 2 * kk, dK_ + 2 * kk, idesc_s, kk > 0);
+          } else {      // N = 256 + (KEYS - 256): an MMA instruction takes at most 256 columns
+            umma_bf16_lh(tmem, dQ_ + 2 * kk, dK_ + 2 * kk, umma_idesc_bf16(128, 256, 0, 0), kk > 0);
+            umma_bf16_lh(tmem + 256, dQ_ + 2 * kk, dK_ + (256 * 128 >> 4) + 2 * kk, umma_idesc_bf16(128, KEYS - 256, 0, 0), kk > 0);
+          }
+        }
         umma_commit(&s_full[buf]);
       };
       auto issue_pv = [&](int k) {          // O(k) = P(k) V
-        const int j = (T == 2) ? (k >> 1) : k, t = (T == 2) ? (k & 1) : 0;
-        const int stage = j & 1, buf = k & 1;
-        mbar_wait(&p_full[buf], (k >> 1) & 1);
-        if (t == 0) mbar_wait(&v_full[stage], (j >> 1) & 1);
+        const int j = k / T, t = k - j * T;
+        const int stage = j % NST, buf = k % NBUF;
+        mbar_wait(&p_full[buf], (k / NBUF) & 1);
+        if (t == 0) mbar_wait(&v_full[stage], (j / NST) & 1);
         if (O_SEP) mbar_wait(o_free, (k & 1) ^ 1);           // the epilogue of tile k-1 has drained O
         tc_fence_after();
         F2_DBG(k, 2);
@@ -159,12 +176,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (t == T - 1) umma_commit(&stage_empty[stage]);
         F2_DBG(k, 3);
       };
-      // program order S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ... : S(k+2) overwrites the buffer whose P was just consumed by PV(k)
-      if (n_tiles > 0) issue_s(0);
-      if (n_tiles > 1) issue_s(1);
+      // program order S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ... : S(k+NBUF) overwrites the buffer whose P was just consumed by PV(k)
+      for (int k = 0; k < NBUF && k < n_tiles; ++k) issue_s(k);
       for (int k = 0; k < n_tiles; ++k) {
         issue_pv(k);
-        if (k + 2 < n_tiles) issue_s(k + 2);
+        if (k + NBUF < n_tiles) issue_s(k + NBUF);
       }
     }
   }
@@ -183,13 +199,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const bool plain = (p.mask == nullptr) && (n_valid >= CPT || tail);
     int i = 0, j = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
-      const int stage = j & 1;
-      const float* m = smask + stage * 256 + cq * CPT;
+      const int stage = j % NST;
+      const float* m = smask + stage * F2_MASK + cq * CPT;
       for (int t = 0; t < T; ++t, ++i) {
-        const int buf = i & 1;
+        const int buf = i % NBUF;
         const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16) + buf * BUF_STRIDE;
         if (warp == F2_SOFTMAX_WARP0 && lane == 0) F2_DBG(i, 4);
-        mbar_wait(&s_full[buf], (i >> 1) & 1);
+        mbar_wait(&s_full[buf], (i / NBUF) & 1);
         tc_fence_after();
         if (warp == F2_SOFTMAX_WARP0 && lane == 0) F2_DBG(i, 5);
         uint32_t s[CPT];
@@ -264,8 +280,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           else if (n == 8) TmemIO<4>::st(dstc, pk);
           else TmemIO<2>::st(dstc, pk);                               // n == 4
         }
-        sred_sum[(buf * 4 + cq) * 128 + row] = sum;
-        if (cq == 0) srow_max[buf * 128 + row] = mx;
+        sred_sum[((i % 3) * 4 + cq) * 128 + row] = sum;
+        if (cq == 0) srow_max[(i % 3) * 128 + row] = mx;
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -283,15 +299,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.H, h = item - b * p.H;
       for (int t = 0; t < T; ++t, ++i) {
-        const int buf = i & 1;
+        const int buf = i % NBUF;
         const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16) + (O_SEP ? 448 : buf * BUF_STRIDE + 128);
         const int q = t * 128 + row;
-        if (O_SEP) mbar_wait(&o_full[0], i & 1); else mbar_wait(&o_full[buf], (i >> 1) & 1);
+        if (O_SEP) mbar_wait(&o_full[0], i & 1); else mbar_wait(&o_full[buf], (i / NBUF) & 1);
         tc_fence_after();
         if (warp == F2_EPI_WARP0 && lane == 0) F2_DBG(i, 10);
-        const float* rs = sred_sum + buf * 4 * 128 + row;
+        const float* rs = sred_sum + (i % 3) * 4 * 128 + row;
         const float sum = (rs[0] + rs[128]) + (rs[256] + rs[384]);
-        const float mx = srow_max[buf * 128 + row];
+        const float mx = srow_max[(i % 3) * 128 + row];
         const float inv = 1.0f / sum;
         bf16* dst = p.ctx + (long long)(b * p.L + q) * p.d + h * 64;
         // The tile buffer is handed back to the MMA warp as soon as the second half of O sits in registers (the next-but-one S = Q K^T
@@ -349,7 +365,7 @@ static int launch_fwd2(const CUtensorMap& tQ, const CUtensorMap& tKV, const Attn
 
 // supported padded key counts (x16): a sequence is rounded up to the next one, the extra key columns are masked
 static int fwd2_round_n16(int n16) {
-  const int sizes[] = {2, 4, 5, 8, 13, 16};
+  const int sizes[] = {2, 4, 5, 8, 13, 16, 17};
   for (int s : sizes) if (n16 <= s) return s;
   return 0;
 }
@@ -357,19 +373,20 @@ static int fwd2_round_n16(int n16) {
 int attention_fwd2(const void* qkv, const AttnParams& p_in, cudaStream_t stream) {
   AttnParams p = p_in;
   const int n16 = fwd2_round_n16((p.L + 15) / 16);
-  if (!n16) { set_error("attention_fwd2: L=%d > 256", p.L); return CLIPK_ERR_UNSUPPORTED; }
+  if (!n16) { set_error("attention_fwd2: L=%d > 272", p.L); return CLIPK_ERR_UNSUPPORTED; }
   p.lk_pad = n16 * 16;
   CUtensorMap tQ, tKV;
   int rc;
   if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * p.d, (uint64_t)p.B * p.L, 3ull * p.d, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * p.d, (uint64_t)p.B * p.L, 3ull * p.d, 64, p.lk_pad))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * p.d, (uint64_t)p.B * p.L, 3ull * p.d, 64, p.lk_pad <= 256 ? p.lk_pad : p.lk_pad / 2))) return rc;
   switch (n16) {
     case 2: return launch_fwd2<2>(tQ, tKV, p, stream);
     case 4: return launch_fwd2<4>(tQ, tKV, p, stream);
     case 5: return launch_fwd2<5>(tQ, tKV, p, stream);
     case 8: return launch_fwd2<8>(tQ, tKV, p, stream);
     case 13: return launch_fwd2<13>(tQ, tKV, p, stream);
-    default: return launch_fwd2<16>(tQ, tKV, p, stream);
+    case 16: return launch_fwd2<16>(tQ, tKV, p, stream);
+    default: return launch_fwd2<17>(tQ, tKV, p, stream);
   }
 }
 

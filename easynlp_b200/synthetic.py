@@ -9,7 +9,39 @@ import math
 import torch
 
 
+def random_state_dict_hf(cfg: dict, seed: int = 1234, device="cpu"):
+    """random-init checkpoint of the huggingface_clip branch (flat engine config from engine.hf_engine_config): normal(0, 0.02) matrices,
+    width^-1/2 projections / class / position embeddings, unit LayerNorm gains, zero biases, zero padding rows"""
+    from .params import hf_param_schema
+    g = torch.Generator(device=device).manual_seed(seed)
+    W = cfg["vision_width"]; H = cfg["text_hidden_size"]
+    sd = {}
+    for name, shape in hf_param_schema(cfg).items():
+        if name == "logit_scale":
+            t = torch.full(shape, math.log(1 / 0.07), device=device)
+        elif name.endswith("norm.weight") or name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("LayerNorm.weight"):
+            t = torch.ones(shape, device=device)
+        elif name.endswith("bias"):
+            t = torch.zeros(shape, device=device)
+        else:
+            std = 0.02
+            if name.startswith("vision_projection") or "class_embedding" in name or "position_embedding.weight" in name:
+                std = W ** -0.5
+            elif name.startswith("text_projection") or "pooler" in name:
+                std = H ** -0.5
+            elif "patch_embedding" in name:
+                std = (3 * cfg["vision_patch_size"] ** 2) ** -0.5
+            t = torch.randn(shape, generator=g, device=device) * std
+        sd[name] = t
+    pad = cfg.get("text_pad_token_id", 0)
+    sd["text_encoder.embeddings.word_embeddings.weight"][pad].zero_()
+    sd["text_encoder.embeddings.position_embeddings.weight"][pad].zero_()
+    return sd
+
+
 def random_state_dict(cfg: dict, seed: int = 1234, device="cpu"):
+    if cfg.get("model_type") == "huggingface_clip":
+        return random_state_dict_hf(cfg, seed, device)
     from .params import param_schema
     g = torch.Generator(device=device).manual_seed(seed)
     W = cfg["vision_width"]; H = cfg["text_hidden_size"]; r = cfg["text_initializer_range"]

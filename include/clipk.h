@@ -95,7 +95,7 @@ int clipk_dropout_mask(float* out, int rows, int cols, const clipk_dropout_t* dr
 /* -------------------------------------------------------------------------------------------- attention
  * Fused softmax(Q K^T / 8 + key_mask) V for head dim 64 on packed projections qkv[B*L, 3d] (Q|K|V blocks, head h at
  * columns h*64).  Replaces nn.MultiheadAttention's SDPA (modeling_chineseclip.py:188,198-200) and BertSelfAttention
- * (modeling_bert.py:210-244, additive mask from modeling_utils.py:438-439).  L <= 256.
+ * (modeling_bert.py:210-244, additive mask from modeling_utils.py:438-439).  Forward: L <= 272 (ViT-L/14 has 257 tokens); backward: L <= 256.
  * key_mask: optional f32 [B, L] additive (0 / -10000).  lse: f32 [B, H, L] saved for backward.                  */
 int clipk_attention_fwd(const void* qkv, const float* key_mask, void* ctx, float* lse, int B, int L, int H, int d,
                         const clipk_dropout_t* drop /* optional: dropout on the probabilities, row = (b*H+h)*L+q, col = key */,

@@ -48,7 +48,7 @@ def run(B, L, H, masked, which):
 
 if __name__ == "__main__":
     shapes = [(2, 197, 12, False), (3, 77, 12, True), (2, 17, 2, False), (2, 16, 2, True), (1, 256, 2, False), (2, 128, 1, True), (5, 50, 3, True),
-              (40, 197, 12, False), (256, 197, 12, False), (256, 77, 12, True)]
+              (40, 197, 12, False), (256, 197, 12, False), (256, 77, 12, True), (2, 257, 3, False), (3, 270, 2, False), (64, 257, 16, False)]
     only = sys.argv[1:] and sys.argv[1]
     if len(sys.argv) > 2:
         shapes = [shapes[int(x)] for x in sys.argv[2].split(",")]

@@ -115,3 +115,26 @@ def test_hf_plugin_surface_and_defaults(tmp_path):
                                   attention_mask=torch.from_numpy(z["attention_mask"]))
     assert math.isfinite(out["loss"].item())
     assert torch.equal(vis, model.engine.params.p("vision_encoder.vision_model.encoder.layers.0.mlp.fc1.weight"))
+
+
+def test_hf_patch14_257_tokens_forward_vs_oracle():
+    """ViT-*/14 geometry of BASELINE configs[3] at a small width: 224 x 224 / patch 14 -> 257 tokens (the single-buffer 272-key attention
+    path) and patch dim 3*14*14 = 588 padded to 592 for the TMA rows of the patch GEMM; forward only (the tower is frozen on this branch)."""
+    raw = O.hf_tiny_config()
+    raw = json.loads(json.dumps(raw)); raw["vision_config"].update(image_size=224, patch_size=14)
+    sd = O.hf_init_state_dict(raw, seed=3, scale_boost=2.0)
+    cfg = hf_engine_config(raw, 128)
+    eng = ClipEngine(cfg, with_optimizer_state=False)
+    assert eng.Lv == 257 and eng.kdim == 588 and eng.kdim_pad == 592
+    eng.params.load_state_dict(sd)
+    g = torch.Generator().manual_seed(0)
+    pixels = torch.randn(5, 3, 224, 224, generator=g)
+    out = eng.encode(pixels.cuda(), None)["image_embeds"]
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = O.hf_clip_forward(sd, raw, pixels, None)["image_embeds"]
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            yard = O.hf_clip_forward(sd, raw, pixels, None)["image_embeds"].float()
+    e, y = max_err(out, ref), max_err(yard, ref)
+    print(f"PARITY hf patch14 L=257 fwd: image embeds max err {e:.2e} (PyTorch bf16 yardstick {y:.2e})")
+    assert e < 1.5 * y + 1e-4

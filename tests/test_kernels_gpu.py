@@ -148,6 +148,18 @@ def test_attention_fwd_bwd(B, L, H, masked):
     assert_close(dbias - 0.5, cref, 1e-2, 5e-3 * cref.abs().max().item() + 1e-3 * scale * math.sqrt(B * L), "fused QKV bias gradient")
 
 
+@pytest.mark.parametrize("B,L,H", [(2, 257, 3), (1, 272, 2), (3, 260, 1)])
+def test_attention_fwd_more_than_256_tokens(B, L, H):
+    """forward only (ViT-L/14: 257 tokens): one 272-column score buffer, two K / V boxes, three query tiles"""
+    d = H * 64
+    qkv = rnd(B * L, 3 * d, seed=13, scale=1.5).bfloat16()
+    ctx = torch.zeros(B * L, d, device=DEV, dtype=torch.bfloat16); lse = torch.zeros(B, H, L, device=DEV)
+    ops.attention_fwd(qkv, None, ctx, lse, B, L, H)
+    o_ref, lse_ref = attn_ref(qkv.float(), None, B, L, H)
+    assert_close(ctx, o_ref, 2e-2, 2e-2, "ctx")
+    assert_close(lse, lse_ref, 1e-3, 1e-2, "lse")
+
+
 # --------------------------------------------------------------------------------------------- LayerNorm
 @pytest.mark.parametrize("rows,d,eps", [(394, 768, 1e-5), (77, 768, 1e-12), (33, 128, 1e-5), (20, 1024, 1e-5)])
 def test_layernorm_fwd_bwd(rows, d, eps):
