@@ -238,6 +238,108 @@ def gpu_reference_baseline(dev, B, Lt, steps=3, warmup=2):
     return {"value": None, "unavailable": "out of memory at every tried batch: " + str(last)}
 
 
+# ------------------------------------------------------------------------------------------------ retrieval / inference (configs[4])
+def run_retrieval(args):
+    """BASELINE configs[4]: forward-only encode throughput (ViT-B/16 + BERT-base, no activations kept) and blocked text->image retrieval
+    with the queries sharded over the ranks and the gallery all-gathered (easynlp_b200/retrieval.py).
+      encode : `--pairs` pairs per GPU through ClipEngine.encode in batches of `--batch`, every batch copied from pinned host memory (a pool
+               of 4 distinct synthetic host batches is cycled: 1 M distinct fp32 images would be 602 GB of host memory); pairs/s = metric.
+      rank   : `--gallery` synthetic unit embeddings per GPU (text = normalize(image + noise): recall is non-trivial), ranks on the tensor
+               cores, recall@1/5/10 summed over ranks, and an exact fp64 check of a 2048-query subsample against the full gallery."""
+    import torch
+    from easynlp_b200 import _lib as L
+    from easynlp_b200 import distributed as D
+    from easynlp_b200 import ops
+    from easynlp_b200.engine import ClipEngine
+    from easynlp_b200.retrieval import sharded_recall
+    from easynlp_b200.synthetic import random_state_dict, synthetic_batch
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = b16_config()
+    B, Lt = args.batch, args.seq_len
+    eng = ClipEngine(cfg, device=dev, with_optimizer_state=False)
+    eng.params.load_state_dict(random_state_dict(cfg, seed=1234, device="cpu"))
+    pool = [synthetic_batch(cfg, B, Lt, seed=1234 + 17 * rank + i, device="cpu", pin=True) for i in range(4)]
+    n_batches = max(1, args.pairs // B)
+    l0 = L.launch_count()
+    for i in range(3):
+        eng.encode(pool[i][0].to(dev, non_blocking=True), pool[i][1].to(dev, non_blocking=True))
+    launches_per_batch = (L.launch_count() - l0) // 3
+    torch.cuda.synchronize(); D.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    acc = torch.zeros(2, device=dev)
+    D.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for i in range(n_batches):
+        px, tk = pool[i % 4]
+        out = eng.encode(px.to(dev, non_blocking=True), tk.to(dev, non_blocking=True))
+        acc[0] += out["image_embeds"][0, 0]; acc[1] += out["text_embeds"][0, 0]      # the embeddings are consumed on the device
+    e1.record(); torch.cuda.synchronize(); D.barrier()
+    _ = acc.cpu()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    enc_ms = t.item()
+    enc_pairs = world * n_batches * B
+    value = enc_pairs / (enc_ms * 1e-3)
+    # ---- ranking at scale on synthetic embeddings
+    n_loc, E = args.gallery, cfg["embed_dim"]
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    img = torch.nn.functional.normalize(torch.randn(n_loc, E, generator=g, device=dev), dim=-1)
+    # noise of norm ~5 on a unit image embedding: the match scores ~0.2 = 4.4 sigma of the other scores -> recall@1 well inside (0, 1)
+    txt = torch.nn.functional.normalize(img + (5.0 / E ** 0.5) * torch.randn(n_loc, E, generator=g, device=dev), dim=-1)
+    sharded_recall(txt[:4096].contiguous(), img[:4096].contiguous())       # warm-up (workspace, kernel attributes, NCCL channels)
+    torch.cuda.synchronize(); D.barrier()
+    r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True)
+    r0.record()
+    hits, nq = sharded_recall(txt, img)
+    r1.record(); torch.cuda.synchronize(); D.barrier()
+    t2 = torch.tensor([r0.elapsed_time(r1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
+    rank_ms = t2.item()
+    # exact check (checker role): 2048 queries of this rank against the full gathered gallery in fp64
+    gal = D.gather_rows(img) if world > 1 else img
+    sub = torch.arange(0, n_loc, max(1, n_loc // 2048), device=dev)[:2048]
+    ranks = torch.empty(n_loc, dtype=torch.int32, device=dev)
+    ops.retrieval_rank_tc(txt, gal, ranks, label_offset=rank * n_loc)
+    exact = torch.zeros(sub.numel(), dtype=torch.int64, device=dev)
+    qd = txt[sub].double(); thr = (qd * gal[rank * n_loc + sub].double()).sum(-1, keepdim=True)
+    for c0 in range(0, gal.shape[0], 65536):
+        exact += ((qd @ gal[c0:c0 + 65536].double().t()) > thr).sum(1)
+    # recall@K exact <=> the hit decisions agree (full ranks of queries whose match sits in the bulk may differ by near-ties at the 3e-6 level)
+    recall_exact = all(bool(torch.equal(exact < k, ranks[sub].long() < k)) for k in (1, 5, 10))
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        flops = 2.0 * nq * nq * 3 * E
+        line = {"metric": "retrieval_encode_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": n_batches, "warmup": 3,
+                "ms_per_step": enc_ms / n_batches, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[4]: forward-only encode (ViT-B/16 + BERT-base) + sharded text->image retrieval", "per_gpu_batch": B,
+                           "pairs_encoded": enc_pairs, "seq_len": Lt, "host_pool": "4 distinct pinned host batches per rank, cycled; H2D copy every batch",
+                           "gallery_total": nq, "parallelism": f"queries sharded over {world} ranks, gallery all-gathered"},
+                "clocks": clocks, "gpu_launches": launches_per_batch * n_batches,
+                "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": pool[0][0].numel() * 4 + pool[0][1].numel() * 8, "d2h_bytes_per_step": 0,
+                        "api": "ClipEngine.encode on host batches (the feat=True path of CLIPApp.forward / CLIPPredictor.predict)"},
+                "encode": {"pairs_per_s": value, "tflops": value * FLOPS_FWD_PER_PAIR / 1e12,
+                           "frac_of_peak": value / world * FLOPS_FWD_PER_PAIR / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0)},
+                "retrieval": {"queries": nq, "gallery": nq, "ms": rank_ms, "queries_per_s": nq / (rank_ms * 1e-3), "tflops": flops / (rank_ms * 1e-3) / 1e12,
+                              "frac_of_peak": flops / (rank_ms * 1e-3) / 1e12 / world / peaks.get("bf16_tflops_sustained", 1400.0),
+                              "recall@1": hits[1] / nq, "recall@5": hits[5] / nq, "recall@10": hits[10] / nq,
+                              "recall_exact_vs_fp64_subsample": recall_exact, "subsample": int(sub.numel())},
+                "roofline": {"bound": "tensor", "kernel": "rank-count GEMM (K = 3E hi/lo split) of clipk_retrieval_rank_tc",
+                             "achieved": flops / (rank_ms * 1e-3) / 1e12 / world, "peak": peaks.get("bf16_tflops_sustained", 1400.0), "unit": "TFLOP/s",
+                             "frac": flops / (rank_ms * 1e-3) / 1e12 / world / peaks.get("bf16_tflops_sustained", 1400.0), "traffic": None,
+                             "peak_kind": peak_kind + " sustained cuBLAS bf16"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ native arm (B200)
 def run_native(args):
     import torch
@@ -440,7 +542,10 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--seq-len", type=int, default=77)
-    ap.add_argument("--config", default="b16", choices=["b16", "l14"], help="b16 = BASELINE configs[1]/[2] (default); l14 = configs[3] (ViT-L/14 + 24-layer text tower, huggingface_clip)")
+    ap.add_argument("--config", default="b16", choices=["b16", "l14", "retrieval"],
+                    help="b16 = BASELINE configs[1]/[2] (default); l14 = configs[3] (ViT-L/14 + 24-layer text tower, huggingface_clip); retrieval = configs[4]")
+    ap.add_argument("--pairs", type=int, default=32768, help="--config retrieval: pairs encoded per GPU")
+    ap.add_argument("--gallery", type=int, default=131072, help="--config retrieval: synthetic embedding pairs per GPU for the ranking leg")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference sample and the parity checker leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-on-this-GPU leg (unmodified reference under bf16 autocast)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured CUDA graph")
@@ -457,7 +562,10 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                    "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
             sys.exit(subprocess.call(cmd))
-        run_native(args)
+        if args.config == "retrieval":
+            run_retrieval(args)
+        else:
+            run_native(args)
 
 
 if __name__ == "__main__":

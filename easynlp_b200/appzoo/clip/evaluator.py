@@ -22,6 +22,12 @@ def recall_from_embeddings(text_embeds: torch.Tensor, image_embeds: torch.Tensor
     return {k: int((r < k).sum()) for k in ks}
 
 
+def recall_sharded(text_embeds_local: torch.Tensor, image_embeds_local: torch.Tensor, ks=(1, 5, 10)):
+    """multi-GPU form: queries sharded over the ranks, gallery all-gathered (easynlp_b200/retrieval.py)"""
+    from ...retrieval import sharded_recall
+    return sharded_recall(text_embeds_local, image_embeds_local, ks)
+
+
 class CLIPEvaluator(Evaluator):
 
     def __init__(self, valid_dataset, **kwargs):

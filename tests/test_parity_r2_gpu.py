@@ -214,6 +214,15 @@ def _two_rank_worker(rank, world, port, tmp, q):
         tr.train_step(dict(mb[1]), 1); tr.after_iter(1, 0, 0.0)
         assert tr._global_step == 1 and tr.engine.params.step == 1 and tr._sched_step == 1
         res["ga_param"] = tr.engine.params.p("visual.proj").detach().cpu().clone()
+        # (3) sharded retrieval: this rank's queries against the all-gathered gallery, hit counts summed over ranks
+        from easynlp_b200.retrieval import sharded_recall
+        gg = torch.Generator().manual_seed(123)
+        n_loc, E = 700, 128
+        img = torch.nn.functional.normalize(torch.randn(world * n_loc, E, generator=gg), dim=-1)
+        txt = torch.nn.functional.normalize(img + 0.9 * torch.randn(world * n_loc, E, generator=gg), dim=-1)
+        sl2 = slice(rank * n_loc, (rank + 1) * n_loc)
+        hits, nq = sharded_recall(txt[sl2].cuda(), img[sl2].cuda())
+        res["recall"] = [hits[1], hits[5], hits[10], nq]
         # plain numpy payload: torch tensors travel through a multiprocessing queue as shared-memory handles that die with this process
         to_np = lambda v: {k: to_np(x) for k, x in v.items()} if isinstance(v, dict) else (v.numpy() if torch.is_tensor(v) else v)
         q.put((rank, to_np(res)))
@@ -280,6 +289,13 @@ def test_two_real_ranks_on_one_gpu_global_loss_and_trainer_accumulation(tmp_path
             err = (got[r]["ga_grads"][k] - acc[k]).norm().item()
             assert err < 0.06 * acc[k].norm().item() + 1e-4, (k, err, acc[k].norm().item())
     assert torch.allclose(got[0]["ga_param"], got[1]["ga_param"], rtol=0, atol=1e-7)      # replicas stay in lock-step
+    # sharded recall == the oracle's rank rule on the concatenated corpus (exact integer counts), identical on both ranks
+    gg = torch.Generator().manual_seed(123)
+    img = torch.nn.functional.normalize(torch.randn(world * 700, 128, generator=gg), dim=-1)
+    txt = torch.nn.functional.normalize(img + 0.9 * torch.randn(world * 700, 128, generator=gg), dim=-1)
+    r = O.rank_of_match(txt.double(), img.double())
+    want = [int((r < k).sum()) for k in (1, 5, 10)] + [world * 700]
+    assert got[0]["recall"] == want and got[1]["recall"] == want, (got[0]["recall"], want)
 
 
 # ------------------------------------------------------------------------------------------------ predictor image rows
