@@ -75,6 +75,15 @@ def _declare(L):
     L.clipk_adamw_step.argtypes = [vp, vp, vp, vp, vp, ll, f, f, f, f, f, i, vp, vp, vp]
     L.clipk_adam_schedule.argtypes = [vp, vp, f, i, i, f, f, vp]
     L.clipk_counter_add.argtypes = [vp, i, vp]
+    L.clipk_peer_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.clipk_peer_free.argtypes = [vp]
+    L.clipk_peer_export.argtypes = [vp, C.c_char_p]
+    L.clipk_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.clipk_peer_close.argtypes = [vp]
+    L.clipk_l2norm_allgather.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
+    L.clipk_peer_signal.argtypes = [vp, i, i, i, C.c_uint, vp]
+    L.clipk_peer_wait.argtypes = [vp, i, i, C.c_uint, vp]
+    L.clipk_peer_reduce_rows.argtypes = [vp, i, i, vp, i, i, i, vp]
     L.clipk_position_ids.argtypes = [vp, vp, i, i, i, vp]
     L.clipk_embed_gather.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     L.clipk_embed_gather_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]

@@ -115,3 +115,98 @@ class OverlappedGradReducer:
             for w in self.works:
                 w.wait()
         self.done, self.works = [], []
+
+
+class PeerGroup:
+    """CUDA-IPC mapped peer buffers of the contrastive head (csrc/peer.cu): every rank owns one buffer
+        [ gallery_image G x E | gallery_text G x E | dgallery_image G x E | dgallery_text G x E | flags 4 x world ]      (fp32 / uint32)
+    and maps every other rank's buffer.  The embedding all-gather then is the l2-normalise kernel storing straight into all peers'
+    galleries, the gradient reduce-scatter a kernel that pulls this rank's rows from all peers.  Construction is collective (handles are
+    exchanged with all_gather_object); `PeerGroup.create` returns None where peer mapping is impossible (the caller keeps the
+    torch.distributed collectives)."""
+
+    CH_GALLERY, CH_GRADS = 0, 1
+
+    def __init__(self, local_rows: int, E: int, device):
+        import ctypes as C
+        from . import _lib as L
+        self.L = L; self.C = C
+        self.world, self.rank = world_size(), get_rank()
+        self.rows, self.E = int(local_rows), int(E)
+        self.G = self.world * self.rows
+        self.dev = torch.device(device)
+        self.region = self.G * self.E * 4                      # bytes of one [G, E] fp32 region
+        self.flag_off = 4 * self.region
+        nbytes = self.flag_off + 4 * self.world * 4 + 256
+        base = C.c_void_p()
+        L.check(L.lib().clipk_peer_alloc(C.byref(base), nbytes), "peer_alloc")
+        self.base = base.value
+        handle = C.create_string_buffer(64)
+        L.check(L.lib().clipk_peer_export(C.c_void_p(self.base), handle), "peer_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        self.bases = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.bases.append(self.base)
+            else:
+                ptr = C.c_void_p()
+                L.check(L.lib().clipk_peer_open(C.c_char_p(h), C.byref(ptr)), "peer_open")
+                self.bases.append(ptr.value)
+        tab = lambda off: torch.tensor([b + off for b in self.bases], dtype=torch.int64, device=self.dev)
+        self.gi_ptrs, self.gt_ptrs = tab(0), tab(self.region)
+        self.dgi_ptrs, self.dgt_ptrs = tab(2 * self.region), tab(3 * self.region)
+        self.flag_ptrs = tab(self.flag_off)
+        self.epoch = 0
+        dist.barrier()
+
+    @classmethod
+    def create(cls, local_rows, E, device):
+        if world_size() == 1 or not torch.cuda.is_available() or os.environ.get("CLIPK_PEER", "1") == "0":
+            return None
+        try:
+            ok = torch.ones(1, device=device)
+            try:
+                pg = cls(local_rows, E, device)
+            except Exception as ex:      # every rank must learn that SOME rank failed, or the others would wait forever later
+                pg = None; ok.zero_()
+                print(f"easynlp_b200: peer-memory collectives unavailable on rank {get_rank()}: {ex!r}", flush=True)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            return pg if ok.item() > 0 else None
+        except Exception:
+            return None
+
+    def _view(self, off_regions):
+        """torch view [G, E] fp32 of a region of the LOCAL buffer (device memory owned by the library, not by torch's allocator)"""
+        class _Mem:
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (self.G, self.E), "typestr": "<f4", "data": (self.base + off_regions * self.region, False), "version": 2}
+        return torch.as_tensor(m, device=self.dev)
+
+    def gallery_views(self):
+        return self._view(0), self._view(1)
+
+    def grad_views(self):
+        return self._view(2), self._view(3)
+
+    # ---- collectives (all asynchronous on the current stream)
+    def l2norm_allgather(self, x, y_local, norm, which):
+        from .ops import _stream
+        ptrs = self.gi_ptrs if which == "image" else self.gt_ptrs
+        self.L.check(self.L.lib().clipk_l2norm_allgather(self.C.c_void_p(x.data_ptr()), self.C.c_void_p(y_local.data_ptr()), self.C.c_void_p(norm.data_ptr()),
+                                                         self.C.c_void_p(ptrs.data_ptr()), self.world, self.rank, self.rows, self.E, _stream()), "l2norm_allgather")
+
+    def sync(self, channel):
+        """every rank's writes issued so far are visible to every other rank once this returns (on the stream)"""
+        from .ops import _stream
+        if channel == self.CH_GALLERY:
+            self.epoch += 1
+        self.L.check(self.L.lib().clipk_peer_signal(self.C.c_void_p(self.flag_ptrs.data_ptr()), self.world, self.rank, channel, self.epoch, _stream()), "peer_signal")
+        self.L.check(self.L.lib().clipk_peer_wait(self.C.c_void_p(self.base + self.flag_off), self.world, channel, self.epoch, _stream()), "peer_wait")
+
+    def reduce_rows(self, which, out, accumulate=True):
+        from .ops import _stream
+        ptrs = self.dgi_ptrs if which == "image" else self.dgt_ptrs
+        self.L.check(self.L.lib().clipk_peer_reduce_rows(self.C.c_void_p(ptrs.data_ptr()), self.world, self.rank, self.C.c_void_p(out.data_ptr()), self.rows, self.E,
+                                                         int(accumulate), _stream()), "peer_reduce_rows")

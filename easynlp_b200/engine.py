@@ -125,6 +125,7 @@ class ClipEngine:
         self.dropout_seed = 0x5EED_C11B
         self._drops = {}
         self._conv_pad = None; self._conv_pad_version = -1
+        self._peer = None; self._peer_key = None; self._peer_on = False      # peer-memory collectives of the contrastive head (distributed.PeerGroup)
 
     # ------------------------------------------------------------------ buffers
     def buf(self, name, shape, dtype):
@@ -227,7 +228,10 @@ class ClipEngine:
         else:
             ops.gemm(st["pooled"], P_.w("visual.proj"), st["feat"], b_mn_major=1)
         st["embeds"] = self.f32("v.embeds", B, self.E); st["norm"] = self.f32("v.norm", B)
-        ops.l2norm_fwd(st["feat"], st["embeds"], st["norm"], B, self.E)
+        if self._peer_on:      # fused normalise + all-gather: the embeddings land in every rank's image gallery (csrc/peer.cu)
+            self._peer.l2norm_allgather(st["feat"], st["embeds"], st["norm"], "image")
+        else:
+            ops.l2norm_fwd(st["feat"], st["embeds"], st["norm"], B, self.E)
         return st
 
     def vit_head_backward_hf(self, st, d_embeds: torch.Tensor):
@@ -373,7 +377,10 @@ class ClipEngine:
         else:
             ops.gemm(cls_rows, P_.w("text_projection"), st["feat"], b_mn_major=1)
         st["embeds"] = self.f32("t.embeds", B, self.E); st["norm"] = self.f32("t.norm", B)
-        ops.l2norm_fwd(st["feat"], st["embeds"], st["norm"], B, self.E)
+        if self._peer_on:
+            self._peer.l2norm_allgather(st["feat"], st["embeds"], st["norm"], "text")
+        else:
+            ops.l2norm_fwd(st["feat"], st["embeds"], st["norm"], B, self.E)
         return st
 
     def bert_backward(self, st, d_embeds: torch.Tensor):
@@ -493,7 +500,10 @@ class ClipEngine:
             ops.gemm(dS_t[:, :G], hi(st["Ts"]), dI, a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
             ops.gemm(dS_i[:, :G], hi(st["Is"]), dT, a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
             return dT, dI, None, None
-        dGI = self.f32("l.dGI", G, E); dGT = self.f32("l.dGT", G, E)
+        if st.get("peer"):      # gallery gradients go straight into the peer buffer, from where their owners pull them
+            dGI, dGT = self._peer.grad_views()
+        else:
+            dGI = self.f32("l.dGI", G, E); dGT = self.f32("l.dGT", G, E)
         ops.gemm(dS_t[:, :G], hi(st["Ts"]), dGI, a_mn_major=1, b_mn_major=1)
         ops.gemm(dS_i[:, :G], hi(st["Is"]), dGT, a_mn_major=1, b_mn_major=1)
         return dT, dI, dGI, dGT
@@ -517,17 +527,32 @@ class ClipEngine:
             train = save           # training step <=> activations are kept; dropout is active only then
         if train and (self.p_hidden > 0.0 or self.p_attn > 0.0):
             ops.counter_add(self._dev_pass, 1)       # new dropout masks for this pass (its backward sees the same value)
+        dist_on = bool(distributed) and D.world_size() > 1
+        B = pixels.shape[0]
+        # Training steps on several GPUs exchange the embedding shards through peer memory: the l2-normalise kernel of each tower stores
+        # its rows straight into every rank's gallery (fused producer + all-gather over NVLink), backward pulls the gallery gradients
+        # (distributed.PeerGroup, csrc/peer.cu).  Forward-only calls and backends without peer access use torch.distributed collectives.
+        self._peer_on = False
+        if dist_on and save:
+            if self._peer_key != (B, self.E):
+                self._peer = D.PeerGroup.create(B, self.E, self.dev); self._peer_key = (B, self.E)
+            self._peer_on = self._peer is not None
         v = self.vit_forward(pixels, save and not self.hf)       # huggingface_clip: the image tower is frozen -> no activations kept
         t = self.bert_forward(ids, save, train=train, token_type_ids=token_type_ids, attention_mask=attention_mask)
-        if distributed and D.world_size() > 1:
-            B = pixels.shape[0]; Wd = D.world_size()
-            gi = D.gather_rows(v["embeds"], self.f32("l.gi", Wd * B, self.E))
-            gt = D.gather_rows(t["embeds"], self.f32("l.gt", Wd * B, self.E))
+        if dist_on:
+            Wd = D.world_size()
+            if self._peer_on:
+                self._peer.sync(D.PeerGroup.CH_GALLERY)
+                gi, gt = self._peer.gallery_views()
+            else:
+                gi = D.gather_rows(v["embeds"], self.f32("l.gi", Wd * B, self.E))
+                gt = D.gather_rows(t["embeds"], self.f32("l.gt", Wd * B, self.E))
             l = self.loss_forward(t["embeds"], v["embeds"], gi, gt, label_offset=D.get_rank() * B, want_logits=want_logits)
-            l["dist"] = True
+            l["dist"] = True; l["peer"] = self._peer_on
         else:
             l = self.loss_forward(t["embeds"], v["embeds"], want_logits=want_logits)
-            l["dist"] = False
+            l["dist"] = False; l["peer"] = False
+        self._peer_on = False
         self._saved = (v, t, l) if save else None
         return {"image_embeds": v["embeds"], "text_embeds": t["embeds"], "logits_per_text": l["logits"], "logits_per_image": l["logits_img"],
                 "loss": l["loss_sum"], "distributed": l["dist"]}
@@ -544,8 +569,13 @@ class ClipEngine:
             from . import distributed as D
             dT, dI, dGI, dGT = self.loss_backward(l, grad_scale, local_gallery=False)
             B = dT.shape[0]
-            ops.axpy(D.reduce_scatter_rows(dGI, self.f32("l.rsI", B, self.E)), dI)
-            ops.axpy(D.reduce_scatter_rows(dGT, self.f32("l.rsT", B, self.E)), dT)
+            if l.get("peer"):      # reduce-scatter by peer loads: this rank's rows of every rank's gallery gradient, summed onto dI / dT
+                self._peer.sync(D.PeerGroup.CH_GRADS)
+                self._peer.reduce_rows("image", dI, accumulate=True)
+                self._peer.reduce_rows("text", dT, accumulate=True)
+            else:
+                ops.axpy(D.reduce_scatter_rows(dGI, self.f32("l.rsI", B, self.E)), dI)
+                ops.axpy(D.reduce_scatter_rows(dGT, self.f32("l.rsT", B, self.E)), dT)
         else:
             dT, dI, _, _ = self.loss_backward(l, grad_scale, local_gallery=True)
         self.bert_backward(t, dT)

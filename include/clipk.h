@@ -223,6 +223,26 @@ int clipk_adamw_step(float* p, const float* g, float* m, float* v, void* w_bf16,
 int clipk_adam_schedule(int* step_dev, float* hyper_dev, float base_lr, int warmup_steps, int t_total, float beta1,
                         float beta2, cudaStream_t stream);
 
+/* -------------------------------------------------------------------------------------------- peer-memory collectives (multi-GPU head)
+ * One process per GPU; every rank allocates ONE peer buffer (galleries + gallery gradients + flags), exports its CUDA-IPC handle, opens
+ * the others' (easynlp_b200/distributed.py: PeerGroup).  gallery_ptrs / flag_ptrs / src_ptrs are DEVICE arrays of `world` pointers, entry p
+ * = the corresponding region in rank p's buffer (p == rank: the local pointer).  See csrc/peer.cu for the protocol.                     */
+int clipk_peer_alloc(void** dev_ptr, size_t bytes);                 /* cudaMalloc'd (IPC-exportable), zero-filled */
+int clipk_peer_free(void* dev_ptr);
+int clipk_peer_export(const void* dev_ptr, unsigned char* handle64); /* 64-byte cudaIpcMemHandle_t */
+int clipk_peer_open(const unsigned char* handle64, void** dev_ptr);
+int clipk_peer_close(void* dev_ptr);
+/* y = x / ||x|| (modeling_chineseclip.py:360,363) stored locally AND into row block `rank` of every rank's gallery: the fused
+ * producer + all-gather of the embedding shards (replaces all_gather_into_tensor of distributed.py) */
+int clipk_l2norm_allgather(const float* x, float* y_local, float* norm, float* const* gallery_ptrs, int world, int rank, int rows, int d,
+                           cudaStream_t stream);
+/* flags[p][channel * world + rank] = epoch on every peer p (after a system-scope fence) / wait until all `world` flags of the channel in
+ * MY flag array reached epoch (bounded spin, traps on timeout).  Epochs increase monotonically per channel. */
+int clipk_peer_signal(unsigned int* const* flag_ptrs, int world, int rank, int channel, unsigned int epoch, cudaStream_t stream);
+int clipk_peer_wait(const unsigned int* my_flags, int world, int channel, unsigned int epoch, cudaStream_t stream);
+/* out[r, :] (+)= sum over peers p of src_ptrs[p][(rank * rows + r), :]: reduce-scatter of the gallery gradients by peer loads */
+int clipk_peer_reduce_rows(float* const* src_ptrs, int world, int rank, float* out, int rows, int d, int accumulate, cudaStream_t stream);
+
 /* counter_dev[0] += value on the stream: the device-resident dropout stream position (one per training forward pass, so that a
  * replayed CUDA graph and every micro-batch of a gradient-accumulation window draw fresh nn.Dropout masks, modeling_bert.py:128,238) */
 int clipk_counter_add(int* counter_dev, int value, cudaStream_t stream);

@@ -181,6 +181,18 @@ def _two_rank_worker(rank, world, port, tmp, q):
         torch.cuda.synchronize()
         share = out["loss"].clone(); D.allreduce_sum_(share)
         res["loss_global"] = share.item()
+        res["peer"] = eng._peer is not None      # CUDA-IPC peer-memory collectives in use (else torch.distributed fallbacks)
+        # the same step once more through the torch.distributed collectives: both exchange paths must agree
+        os.environ["CLIPK_PEER"] = "0"
+        eng2 = ClipEngine(cfg, device="cuda:0")
+        eng2.params.load_state_dict(sd)
+        out2 = eng2.forward(pixels[sl].cuda(), ids[sl].cuda(), distributed=True)
+        eng2.zero_grad(); eng2.backward(); eng2.allreduce_grads()
+        torch.cuda.synchronize()
+        del os.environ["CLIPK_PEER"]
+        assert eng2._peer is None
+        res["peer_vs_nccl_grad"] = (eng.params.grad - eng2.params.grad).abs().max().item() / (eng2.params.grad.abs().max().item() + 1e-30)
+        res["peer_vs_nccl_loss"] = abs(out["loss"].item() - out2["loss"].item())
         res["lpt"] = out["logits_per_text"].cpu(); res["lpi"] = out["logits_per_image"].cpu()
         res["grads"] = {k: eng.params.g(k).detach().cpu().clone() for k in ("visual.proj", "text_projection", "logit_scale",
                         "bert.encoder.layer.0.attention.self.query.weight", "visual.transformer.resblocks.1.mlp.c_fc.weight")}
@@ -261,8 +273,11 @@ def test_two_real_ranks_on_one_gpu_global_loss_and_trainer_accumulation(tmp_path
     ref = O.clip_forward(full, cfg, pixels, ids)
     loss = O.clip_loss(ref["logits_per_text"])
     grads = dict(zip(names, torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)))
+    print("peer-memory collectives used:", [got[r]["peer"] for r in range(world)], "peer vs torch.distributed grad diff", [got[r]["peer_vs_nccl_grad"] for r in range(world)])
     for r in range(world):
         res = got[r]
+        # fused-store all-gather + pulled reduce-scatter == torch.distributed gather / reduce-scatter (fp32 sums in a different order only)
+        assert res["peer_vs_nccl_grad"] < 1e-5 and res["peer_vs_nccl_loss"] < 1e-6, (res["peer_vs_nccl_grad"], res["peer_vs_nccl_loss"])
         assert abs(res["loss_global"] - loss.item()) < 5e-3 * loss.item(), (res["loss_global"], loss.item())
         sl = slice(r * b, (r + 1) * b)
         assert max_err(res["lpt"], ref["logits_per_text"][sl].detach()) < 0.08        # rank r's rows of text->image logits
