@@ -533,7 +533,7 @@ class ClipEngine:
         # its rows straight into every rank's gallery (fused producer + all-gather over NVLink), backward pulls the gallery gradients
         # (distributed.PeerGroup, csrc/peer.cu).  Forward-only calls and backends without peer access use torch.distributed collectives.
         self._peer_on = False
-        if dist_on and save:
+        if dist_on and save and not getattr(self, "_no_peer", False):
             if self._peer_key != (B, self.E):
                 self._peer = D.PeerGroup.create(B, self.E, self.dev); self._peer_key = (B, self.E)
             self._peer_on = self._peer is not None
@@ -675,6 +675,9 @@ class ClipEngine:
         hp = {"token_type_ids": tt, "attention_mask": am, "lr": lr, "weight_decay": weight_decay, "max_grad_norm": max_grad_norm, "warmup_steps": warmup_steps, "t_total": t_total,
               "distributed": distributed, "want_logits": want_logits, "grad_scale": grad_scale, "allreduce": allreduce,
               "overlap": bool(allreduce) and not use_graph and os.environ.get("CLIPK_NO_OVERLAP", "0") != "1"}
+        # the flag epochs of the peer-memory exchange are host-side launch arguments: a replayed graph would reuse them, so a captured
+        # multi-GPU step takes the torch.distributed collectives instead
+        self._no_peer = bool(use_graph)
         if not use_graph or st["calls"] < 2:
             st["calls"] += 1
             return self._step_body(st["pixels"], st["ids"], hp)
