@@ -84,6 +84,11 @@ def _declare(L):
     L.clipk_peer_signal.argtypes = [vp, i, i, i, C.c_uint, vp]
     L.clipk_peer_wait.argtypes = [vp, i, i, C.c_uint, vp]
     L.clipk_peer_reduce_rows.argtypes = [vp, i, i, vp, i, i, i, vp]
+    L.clipk_attention_causal_fwd.argtypes = [vp, vp, vp, i, i, i, i, vp]
+    L.clipk_attention_causal_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
+    L.clipk_argmax_rows.argtypes = [vp, vp, i, i, vp]
+    L.clipk_gather_rows_bf16.argtypes = [vp, vp, vp, i, i, i, vp]
+    L.clipk_scatter_rows_f32.argtypes = [vp, vp, vp, i, i, i, vp]
     L.clipk_position_ids.argtypes = [vp, vp, i, i, i, vp]
     L.clipk_embed_gather.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     L.clipk_embed_gather_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]

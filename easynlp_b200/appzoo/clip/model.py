@@ -1,7 +1,8 @@
-"""CLIPApp -- drop-in for easynlp/appzoo/clip/model.py:40-164 whose math runs in the clipk sm_100a kernels.  Two of the reference's
-three branches are implemented: model_type == "chinese_clip" (ViT + BertModel, model.py:64-72) and the default "huggingface_clip"
-branch (CLIPVisionModel, frozen by `.detach()`, + RobertaModel with its tanh pooler and biased projections, model.py:73-104,128-144);
-"open_clip" raises.  Same constructor / from_pretrained / forward(inputs, feat) / compute_loss contract, same `.config` wrapper, same
+"""CLIPApp -- drop-in for easynlp/appzoo/clip/model.py:40-164 whose math runs in the clipk sm_100a kernels.  All three branches of the
+reference are implemented: model_type == "chinese_clip" (ViT + BertModel, model.py:64-72), "open_clip" (ViT + causal text transformer
+with EOT pooling, model.py:56-63) and the default "huggingface_clip" branch (CLIPVisionModel, frozen by `.detach()`, + RobertaModel
+with its tanh pooler and biased projections, model.py:73-104,128-144); ModifiedResNet visual towers raise.  Same constructor /
+from_pretrained / forward(inputs, feat) / compute_loss contract, same `.config` wrapper, same
 state_dict key names (`chinese_clip.` prefix resp. `text_encoder.` / `vision_encoder.` / `*_projection.`), so Trainer /
 CLIPEvaluator / CLIPPredictor written against the reference keep working.  There is no CPU or PyTorch fallback."""
 import json
@@ -60,11 +61,14 @@ class CLIPApp(Application):
             self.raw_config = json.load(f)
         mt = self.raw_config.get("model_type")
         ckpt = os.path.join(path, "pytorch_model.bin")
-        if mt == "open_clip":
-            raise NotImplementedError("model_type='open_clip' (causal text tower, model.py:56-63 of the reference) is not implemented by the B200 path")
         self.config = Config_Wrapper(self.raw_config)
         checkpoint = torch.load(ckpt, map_location="cpu")
-        if mt == "chinese_clip":
+        if mt == "open_clip":
+            # OPEN_CLIP(**config) with a ViT visual tower and the causal text transformer (model.py:56-63, modeling_openclip.py:255-383)
+            self.model_type = "open_clip"
+            self.prefix = "open_clip."
+            cfg = {k: v for k, v in self.raw_config.items()}
+        elif mt == "chinese_clip":
             self.model_type = "chinese_clip"
             self.prefix = PREFIX
             cfg = {k: v for k, v in self.raw_config.items()}

@@ -574,7 +574,7 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(m + 4 * j) = *reinterpret_cast<const float4*>(smask + c0 + 4 * j);
       tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) pv[j] = qvalid ? exp2f(fmaf(__uint_as_float(rs[j]), sc, m[j] - lse2)) : 0.f;
+      for (int j = 0; j < 16; ++j) pv[j] = (qvalid && !(p.causal && c0 + j > row)) ? exp2f(fmaf(__uint_as_float(rs[j]), sc, m[j] - lse2)) : 0.f;
       if (dc.on) {
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
@@ -663,11 +663,33 @@ static int check_shapes(const char* who, int B, int L, int H, int d, int lmax = 
 
 using namespace clipk;
 
+static int attention_fwd_impl(const void* qkv, const float* key_mask, void* ctx, float* lse, int B, int L, int H, int d, const clipk_dropout_t* drop,
+                              int causal, cudaStream_t stream);
+static int attention_bwd_impl(const void* qkv, const float* key_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv, float* dqkv_colsum,
+                              int B, int L, int H, int d, const clipk_dropout_t* drop, int causal, cudaStream_t stream);
+
 extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void* ctx, float* lse, int B, int L, int H, int d,
                                    const clipk_dropout_t* drop, cudaStream_t stream) {
+  return attention_fwd_impl(qkv, key_mask, ctx, lse, B, L, H, d, drop, 0, stream);
+}
+extern "C" int clipk_attention_causal_fwd(const void* qkv, void* ctx, float* lse, int B, int L, int H, int d, cudaStream_t stream) {
+  return attention_fwd_impl(qkv, nullptr, ctx, lse, B, L, H, d, nullptr, 1, stream);
+}
+extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
+                                   float* dqkv_colsum, int B, int L, int H, int d, const clipk_dropout_t* drop, cudaStream_t stream) {
+  return attention_bwd_impl(qkv, key_mask, ctx, lse, dctx, dqkv, dqkv_colsum, B, L, H, d, drop, 0, stream);
+}
+extern "C" int clipk_attention_causal_bwd(const void* qkv, const void* ctx, const float* lse, const void* dctx, void* dqkv, float* dqkv_colsum, int B,
+                                          int L, int H, int d, cudaStream_t stream) {
+  return attention_bwd_impl(qkv, nullptr, ctx, lse, dctx, dqkv, dqkv_colsum, B, L, H, d, nullptr, 1, stream);
+}
+
+static int attention_fwd_impl(const void* qkv, const float* key_mask, void* ctx, float* lse, int B, int L, int H, int d, const clipk_dropout_t* drop,
+                              int causal, cudaStream_t stream) {
   int rc = check_shapes("attention_fwd", B, L, H, d, 272);
   if (rc) return rc;
   AttnParams p{};
+  p.causal = causal;
   p.B = B; p.L = L; p.H = H; p.d = d;
   p.lk_pad = (L + 15) & ~15;
   p.q_tiles = (L + 127) / 128;
@@ -677,7 +699,7 @@ extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void*
   // default: the persistent warp-specialised pipeline (attention_fwd2.cu); CLIPK_ATTN_V1=1 selects the first-generation kernel (A/B runs)
   { const char* ev = getenv("CLIPK_ATTN_DBG_PTR"); if (ev) p.dbg = reinterpret_cast<long long*>(strtoull(ev, nullptr, 0)); }
   { const char* ev = getenv("CLIPK_ATTN_V1"); if (!(ev && ev[0] == '1')) return attention_fwd2(qkv, p, stream); }
-  if (L > 256) { set_error("attention_fwd: the first-generation kernel handles L <= 256 (L=%d)", L); return CLIPK_ERR_UNSUPPORTED; }
+  if (L > 256 || causal) { set_error("attention_fwd: the first-generation kernel handles L <= 256 without a causal mask (L=%d)", L); return CLIPK_ERR_UNSUPPORTED; }
   CUtensorMap tQ, tKV;
   if ((rc = make_tmap_2d_bf16(&tQ, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tKV, qkv, 3ull * d, (uint64_t)B * L, 3ull * d, 64, p.lk_pad))) return rc;
@@ -696,11 +718,13 @@ extern "C" int clipk_attention_fwd(const void* qkv, const float* key_mask, void*
   return 0;
 }
 
-extern "C" int clipk_attention_bwd(const void* qkv, const float* key_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
-                                   float* dqkv_colsum, int B, int L, int H, int d, const clipk_dropout_t* drop, cudaStream_t stream) {
+static int attention_bwd_impl(const void* qkv, const float* key_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv, float* dqkv_colsum,
+                              int B, int L, int H, int d, const clipk_dropout_t* drop, int causal, cudaStream_t stream) {
   int rc = check_shapes("attention_bwd", B, L, H, d);
   if (rc) return rc;
+  if (causal && L > 128) { set_error("attention_bwd: the causal variant covers L <= 128 (text towers)"); return CLIPK_ERR_UNSUPPORTED; }
   AttnParams p{};
+  p.causal = causal;
   p.B = B; p.L = L; p.H = H; p.d = d;
   p.lk_pad = (L + 15) & ~15;
   p.q_tiles = (L + 127) / 128;

@@ -20,6 +20,7 @@ struct AttnParams {
   const bf16* dctx;    // bwd in  [B*L, d]
   bf16* dqkv;          // bwd out [B*L, 3d]
   float* dqkv_colsum;  // bwd out (optional) [3d] += column sums of dqkv = gradient of the QKV projection bias
+  int causal;          // 1: key j attends only to queries i >= j (additive -inf above the diagonal; OPEN_CLIP.build_attention_mask, modeling_openclip.py:346-352)
   int flags;           // experiment switches (CLIPK_ATTN_FLAGS): bit 0 = issue the gradient MMA chains one after the other instead of interleaved
   long long* dbg;      // optional (diagnostics, CLIPK_ATTN_DBG_PTR): per-role clock64 timestamps of CTA 0, [64 tiles][16 events]
   DropArg drop;        // dropout on the attention probabilities (modeling_bert.py:238); element (b,h,q,j): row = (b*H+h)*L+q, quad = j/4

@@ -195,8 +195,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // plain: no key mask and every column of the slice is a real key.  tail: no key mask and the padding keys all sit in the last 16
     // columns of the slice (the usual case: L rounded up to a multiple of 16) -> they are set to -inf in registers, then as plain.
     const int n_valid = p.L - cq * CPT;               // valid columns of this thread's slice (may be <= 0 or >= CPT)
-    const bool tail = (p.mask == nullptr) && n_valid < CPT && n_valid >= CPT - 16 && n_valid > 0;
-    const bool plain = (p.mask == nullptr) && (n_valid >= CPT || tail);
+    const bool tail = (p.mask == nullptr) && !p.causal && n_valid < CPT && n_valid >= CPT - 16 && n_valid > 0;
+    const bool plain = (p.mask == nullptr) && !p.causal && (n_valid >= CPT || tail);
     int i = 0, j = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
       const int stage = j % NST;
@@ -234,6 +234,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const float a2 = fmaf(__uint_as_float(s[c + 2]), sc, mm.z), a3 = fmaf(__uint_as_float(s[c + 3]), sc, mm.w);
             s[c] = __float_as_uint(a0); s[c + 1] = __float_as_uint(a1); s[c + 2] = __float_as_uint(a2); s[c + 3] = __float_as_uint(a3);
             mx = fmax3(mx, a0, a1); mx = fmax3(mx, a2, a3);
+          }
+          if (p.causal) {        // keys after the query position are masked out (the diagonal itself is kept: a row is never empty)
+            const int qpos = t * 128 + row;
+            mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+              if (cq * CPT + c > qpos) s[c] = 0xff800000u;
+              mx = fmaxf(mx, __uint_as_float(s[c]));
+            }
           }
           k1 = 1.0f;
         }

@@ -1,6 +1,7 @@
 // HBM-bound kernels of the CLIP towers: LayerNorm fwd/bwd, patch im2col, ViT token assembly, BERT embedding
 // gather/scatter, column sums (bias grads), L2 normalisation.  One warp owns one row; a lane owns the float4
 // column groups {lane + 32 i}, so per-column reductions over rows (dgamma, dbeta, dbias) stay in registers.
+#include <limits.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "../../include/clipk.h"
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(const long long* __re
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   long long id = ids[row];
-  if (id < 0 || id >= vocab) id = pad;
+  if (id < 0 || id >= vocab) id = pad >= 0 ? pad : 0;
   int pi = pos_ids[row]; if (pi < 0 || pi >= npos) pi = 0;
   long long ti = type_ids ? type_ids[row] : 0; if (ti < 0 || ti >= ntype) ti = 0;
   if (key_mask && lane == 0) key_mask[row] = attn_mask ? (1.0f - (float)attn_mask[row]) * -10000.0f : (id == pad ? -10000.0f : 0.0f);
@@ -338,6 +339,33 @@ __global__ void __launch_bounds__(256) embed_gather_bwd_kernel(const long long* 
     atomicAdd(reinterpret_cast<float4*>(dtype + ti * H + c), v);
   }
 }
+// idx[b] = argmax_l ids[b, l] (first maximum): OPEN_CLIP.encode_text pools the features at the EOT token, the highest id of each
+// sequence (modeling_openclip.py:367-369).  One warp per sequence.
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const long long* __restrict__ ids, int* __restrict__ idx, int B, int L) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  long long best = LLONG_MIN; int bi = 0;
+  for (int l = lane; l < L; l += 32) { const long long v = ids[(long long)b * L + l]; if (v > best) { best = v; bi = l; } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) idx[b] = bi;
+}
+// out[b, :] = x[b * L + idx[b], :] (bf16 rows) ; dst[b * L + idx[b], :] = src[b, :] (f32 rows; dst zero-filled by the caller)
+__global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const bf16* __restrict__ x, const int* __restrict__ idx, bf16* __restrict__ out, int B, int L, int W) {
+  const int b = blockIdx.x;
+  const bf16* src = x + ((long long)b * L + idx[b]) * W;
+  for (int c = threadIdx.x * 8; c < W; c += blockDim.x * 8) *reinterpret_cast<uint4*>(out + (long long)b * W + c) = *reinterpret_cast<const uint4*>(src + c);
+}
+__global__ void __launch_bounds__(256) scatter_rows_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst, int B, int L, int W) {
+  const int b = blockIdx.x;
+  float* d = dst + ((long long)b * L + idx[b]) * W;
+  for (int c = threadIdx.x * 4; c < W; c += blockDim.x * 4) st_f4(d + c, ld_f4(src + (long long)b * W + c));
+}
+
 // y = tanh(x) (BertPooler / RobertaPooler activation, modeling_bert.py:529-541); dx = dy * (1 - y^2)
 __global__ void __launch_bounds__(256) tanh_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, bf16* __restrict__ y_bf16, long long n4) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
@@ -564,6 +592,30 @@ extern "C" int clipk_embed_gather_bwd(const long long* ids, const int* pos_ids, 
                                       cudaStream_t stream) {
   if (H % 4) { set_error("embed_gather_bwd: H %% 4 != 0"); return CLIPK_ERR_ARG; }
   embed_gather_bwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, pos_ids, type_ids, de, dword, dpos, dtype, rows, H, vocab, npos, ntype, pad_id);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_argmax_rows(const long long* ids, int* idx, int B, int L, cudaStream_t stream) {
+  if (B <= 0 || L <= 0) return 0;
+  argmax_rows_kernel<<<(B + 7) / 8, 256, 0, stream>>>(ids, idx, B, L);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int clipk_gather_rows_bf16(const void* x, const int* idx, void* out, int B, int L, int W, cudaStream_t stream) {
+  if (W % 8) { set_error("gather_rows: W %% 8 != 0"); return CLIPK_ERR_ARG; }
+  if (B <= 0) return 0;
+  gather_rows_bf16_kernel<<<B, 128, 0, stream>>>((const bf16*)x, idx, (bf16*)out, B, L, W);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int clipk_scatter_rows_f32(const float* src, const int* idx, float* dst, int B, int L, int W, cudaStream_t stream) {
+  if (W % 4) { set_error("scatter_rows: W %% 4 != 0"); return CLIPK_ERR_ARG; }
+  if (B <= 0) return 0;
+  scatter_rows_f32_kernel<<<B, 128, 0, stream>>>(src, idx, dst, B, L, W);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

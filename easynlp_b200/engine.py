@@ -66,8 +66,14 @@ class ClipEngine:
         self.cfg = cfg
         self.kind = cfg.get("model_type", "chinese_clip")
         self.hf = self.kind == "huggingface_clip"
-        if self.kind not in ("chinese_clip", "huggingface_clip"):
+        self.oc = self.kind == "open_clip"
+        if self.kind not in ("chinese_clip", "huggingface_clip", "open_clip"):
             raise NotImplementedError(f"model_type {self.kind!r}")
+        if self.oc:      # OPEN_CLIP ctor arguments (modeling_openclip.py:256-271) -> the text-tower keys this engine uses
+            cfg = dict(cfg, text_hidden_size=cfg["transformer_width"], text_intermediate_size=4 * cfg["transformer_width"],
+                       text_num_attention_heads=cfg["transformer_heads"], text_num_hidden_layers=cfg["transformer_layers"],
+                       text_max_position_embeddings=cfg["context_length"])
+            self.cfg = cfg
         self.dev = torch.device(device)
         self.W = cfg["vision_width"]; self.P = cfg["vision_patch_size"]; self.R = cfg["image_resolution"]
         self.E = cfg["embed_dim"]; self.g = self.R // self.P; self.Lv = self.g * self.g + 1
@@ -107,6 +113,9 @@ class ClipEngine:
                        "ln2": "ln_2", "qkv_w": "attn.in_proj_weight", "qkv_b": "attn.in_proj_bias", "out": "attn.out_proj",
                        "fc1": "mlp.c_fc", "fc2": "mlp.c_proj"}
             self.tp = "bert."
+        # OPEN_CLIP's text tower: the same residual block as the ViT, under `transformer.resblocks.{i}.` (modeling_openclip.py:296-301)
+        self.on = {"layer": "transformer.resblocks.{}.", "ln1": "ln_1", "ln2": "ln_2", "qkv_w": "attn.in_proj_weight", "qkv_b": "attn.in_proj_bias",
+                   "out": "attn.out_proj", "fc1": "mlp.c_fc", "fc2": "mlp.c_proj"}
         self.params = ParamStore(cfg, device, with_optimizer_state)
         self._buf: Dict[tuple, torch.Tensor] = {}
         self._saved = None
@@ -152,6 +161,80 @@ class ClipEngine:
         return self.buf(name, shape, torch.float32)
 
     # ------------------------------------------------------------------ ViT
+    # ------------------------------------------------------------------ pre-LN residual blocks (ViT towers, OPEN_CLIP's text tower)
+    def _blocks_forward(self, x, nm, n_layers, B, Ltok, W, I, Hh, save, tg, act, causal):
+        """ResidualAttentionBlock stack (modeling_chineseclip.py:184-216 / modeling_openclip.py:123-160 / CLIPEncoderLayer
+        modeling_clip.py:283-334): x + attn(ln_1(x)), then + mlp(ln_2(.)).  Every projection GEMM writes its branch output as bf16 (plain
+        epilogue); the fp32 residual add is fused into the LayerNorm that follows it (x_new = x + branch is stored by that kernel for
+        backward / the next residual).  Returns (saved layer dicts, pending residual, last stored x, branch buffer): the caller's final
+        LayerNorm performs the last pending add."""
+        P_ = self.params; M = B * Ltok
+        ybr = self.bf(tg + "ybr", M, W)              # branch output (attention out-proj / MLP c_proj), reused
+        pending = None                               # residual stream owed to the next LayerNorm
+        layers = []
+        for i in range(n_layers):
+            p = nm["layer"].format(i)
+            tag = f"{tg}{i}." if save else tg + "t."
+            ly = {}
+            ly["h"] = self.bf(tag + "h", M, W); ly["m1"] = self.f32(tag + "m1", M); ly["r1"] = self.f32(tag + "r1", M)
+            g1, b1 = P_.p(p + nm["ln1"] + ".weight"), P_.p(p + nm["ln1"] + ".bias")
+            if pending is None:
+                ops.layernorm_fwd(x, g1, b1, 1e-5, ly["h"], None, ly["m1"], ly["r1"])
+            else:       # x = x1_prev + c_proj(...) of the previous block
+                x_new = self.f32(f"{tg}x.{i}" if save else f"{tg}x.t{i % 2}", M, W)
+                ops.layernorm_fwd(pending, g1, b1, 1e-5, ly["h"], None, ly["m1"], ly["r1"], add=ybr, x_out=x_new)
+                x = x_new
+            ly["x_in"] = x
+            ly["qkv"] = self.bf(tag + "qkv", M, 3 * W)
+            ops.gemm(ly["h"], P_.w(p + nm["qkv_w"], (3 * W, W)), ly["qkv"], bias=P_.p(p + nm["qkv_b"], (3 * W,)))
+            ly["ctx"] = self.bf(tag + "ctx", M, W); ly["lse"] = self.f32(tag + "lse", B * Hh * Ltok)
+            ops.attention_fwd(ly["qkv"], None, ly["ctx"], ly["lse"], B, Ltok, Hh, causal=causal)
+            ops.gemm(ly["ctx"], P_.w(p + nm["out"] + ".weight"), ybr, bias=P_.p(p + nm["out"] + ".bias"))
+            ly["x1"] = self.f32(tag + "x1", M, W)
+            ly["h2"] = self.bf(tag + "h2", M, W); ly["m2"] = self.f32(tag + "m2", M); ly["r2"] = self.f32(tag + "r2", M)
+            ops.layernorm_fwd(x, P_.p(p + nm["ln2"] + ".weight"), P_.p(p + nm["ln2"] + ".bias"), 1e-5, ly["h2"], None, ly["m2"], ly["r2"],
+                              add=ybr, x_out=ly["x1"])
+            # "z" holds act'(z) (the activation's derivative) saved for backward, "a" the activation
+            ly["z"] = self.bf(tag + "z", M, I); ly["a"] = self.bf(tag + "a", M, I)
+            ops.gemm(ly["h2"], P_.w(p + nm["fc1"] + ".weight"), ly["z"], bias=P_.p(p + nm["fc1"] + ".bias"), mode=act, out2=ly["a"])
+            ops.gemm(ly["a"], P_.w(p + nm["fc2"] + ".weight"), ybr, bias=P_.p(p + nm["fc2"] + ".bias"))
+            pending = ly["x1"]
+            layers.append(ly)
+        return layers, pending, x, ybr
+
+    def _blocks_backward(self, layers, dX, dXb, nm, n_layers, B, Ltok, W, I, Hh, tg, causal):
+        """backward of _blocks_forward.  In: dX (fp32) / dXb (bf16) = gradient of the stack's output (its bias-gradient of the last c_proj
+        already taken by the caller's LayerNorm backward).  Out: dX = gradient of the stack's input."""
+        P_ = self.params; M = B * Ltok
+        dz = self.bf(tg + "dz", M, I); dh = self.bf(tg + "dh", M, W); dctx = self.bf(tg + "dctx", M, W); dqkv = self.bf(tg + "dqkv", M, 3 * W)
+        for i in reversed(range(n_layers)):
+            p = nm["layer"].format(i)
+            ly = layers[i]
+            # MLP
+            ops.gemm(dXb, ly["a"], P_.g(p + nm["fc2"] + ".weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+                     splits=_splits_for(W, I, M))
+            ops.gemm(dXb, P_.w(p + nm["fc2"] + ".weight"), dz, b_mn_major=1, mode=L.EPI_MUL_AUX, aux=ly["z"],
+                     colsum=P_.g(p + nm["fc1"] + ".bias"))            # dz = (dX W) o act'(z); its column sums = d(c_fc.bias)
+            ops.gemm(dz, ly["h2"], P_.g(p + nm["fc1"] + ".weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+                     splits=_splits_for(I, W, M))
+            ops.gemm(dz, P_.w(p + nm["fc1"] + ".weight"), dh, b_mn_major=1)
+            dX1 = self.f32(tg + "dX.b", M, W); dX1b = self.bf(tg + "dXb.b", M, W)
+            ops.layernorm_bwd(dh, ly["x1"], P_.p(p + nm["ln2"] + ".weight"), ly["m2"], ly["r2"], dx_add=dX, dx_f32=dX1, dx_bf16=dX1b,
+                              dgamma=P_.g(p + nm["ln2"] + ".weight"), dbeta=P_.g(p + nm["ln2"] + ".bias"), dbias=P_.g(p + nm["out"] + ".bias"))
+            # attention
+            ops.gemm(dX1b, ly["ctx"], P_.g(p + nm["out"] + ".weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+                     splits=_splits_for(W, W, M))
+            ops.gemm(dX1b, P_.w(p + nm["out"] + ".weight"), dctx, b_mn_major=1)
+            ops.attention_bwd(ly["qkv"], None, ly["ctx"], ly["lse"], dctx, dqkv, B, Ltok, Hh, dqkv_colsum=P_.g(p + nm["qkv_b"], (3 * W,)), causal=causal)
+            ops.gemm(dqkv, ly["h"], P_.g(p + nm["qkv_w"], (3 * W, W)), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
+                     splits=_splits_for(3 * W, W, M))
+            ops.gemm(dqkv, P_.w(p + nm["qkv_w"], (3 * W, W)), dh, b_mn_major=1)
+            bias_prev = P_.g(nm["layer"].format(i - 1) + nm["fc2"] + ".bias") if i > 0 else None
+            ops.layernorm_bwd(dh, ly["x_in"], P_.p(p + nm["ln1"] + ".weight"), ly["m1"], ly["r1"], dx_add=dX1, dx_f32=dX, dx_bf16=dXb,
+                              dgamma=P_.g(p + nm["ln1"] + ".weight"), dbeta=P_.g(p + nm["ln1"] + ".bias"), dbias=bias_prev)
+            self._grads_ready(p)
+        return dX
+
     def _conv_operand(self):
         """patch-embedding weight as the [W, kdim_pad] bf16 GEMM operand (zero-padded copy when 3*P*P is not a multiple of 8)"""
         P_ = self.params
@@ -180,38 +263,8 @@ class ClipEngine:
         x = self.f32("v.x.0", M, W)
         st = {"B": B, "mean0": self.f32("v.mean0", M), "rstd0": self.f32("v.rstd0", M), "layers": []}
         ops.layernorm_fwd(x0, P_.p(vn["ln_pre"] + ".weight"), P_.p(vn["ln_pre"] + ".bias"), 1e-5, None, x, st["mean0"], st["rstd0"])
-        # Residual stream: every projection GEMM writes its branch output as bf16 (plain epilogue); the fp32 residual add is fused
-        # into the LayerNorm that follows it (x_new = x + branch is stored by that kernel for backward / the next residual).
-        ybr = self.bf("v.ybr", M, W)                 # branch output (attention out-proj / MLP c_proj), reused
-        pending = None                               # (x_res, add): residual add owed to the next LayerNorm
-        for i in range(self.nv):
-            p = vn["layer"].format(i)
-            tag = f"v.{i}." if save else "v.t."
-            ly = {}
-            ly["h"] = self.bf(tag + "h", M, W); ly["m1"] = self.f32(tag + "m1", M); ly["r1"] = self.f32(tag + "r1", M)
-            g1, b1 = P_.p(p + vn["ln1"] + ".weight"), P_.p(p + vn["ln1"] + ".bias")
-            if pending is None:
-                ops.layernorm_fwd(x, g1, b1, 1e-5, ly["h"], None, ly["m1"], ly["r1"])
-            else:       # x = x1_prev + c_proj(...) of the previous block
-                x_new = self.f32(f"v.x.{i}" if save else f"v.x.t{i % 2}", M, W)
-                ops.layernorm_fwd(pending, g1, b1, 1e-5, ly["h"], None, ly["m1"], ly["r1"], add=ybr, x_out=x_new)
-                x = x_new
-            ly["x_in"] = x
-            ly["qkv"] = self.bf(tag + "qkv", M, 3 * W)
-            ops.gemm(ly["h"], P_.w(p + vn["qkv_w"], (3 * W, W)), ly["qkv"], bias=P_.p(p + vn["qkv_b"], (3 * W,)))
-            ly["ctx"] = self.bf(tag + "ctx", M, W); ly["lse"] = self.f32(tag + "lse", B * Hh * Lv)
-            ops.attention_fwd(ly["qkv"], None, ly["ctx"], ly["lse"], B, Lv, Hh)
-            ops.gemm(ly["ctx"], P_.w(p + vn["out"] + ".weight"), ybr, bias=P_.p(p + vn["out"] + ".bias"))
-            ly["x1"] = self.f32(tag + "x1", M, W)
-            ly["h2"] = self.bf(tag + "h2", M, W); ly["m2"] = self.f32(tag + "m2", M); ly["r2"] = self.f32(tag + "r2", M)
-            ops.layernorm_fwd(x, P_.p(p + vn["ln2"] + ".weight"), P_.p(p + vn["ln2"] + ".bias"), 1e-5, ly["h2"], None, ly["m2"], ly["r2"],
-                              add=ybr, x_out=ly["x1"])
-            # "z" holds act'(z) (the activation's derivative) saved for backward, "a" the activation
-            ly["z"] = self.bf(tag + "z", M, Iv); ly["a"] = self.bf(tag + "a", M, Iv)
-            ops.gemm(ly["h2"], P_.w(p + vn["fc1"] + ".weight"), ly["z"], bias=P_.p(p + vn["fc1"] + ".bias"), mode=self.vit_act, out2=ly["a"])
-            ops.gemm(ly["a"], P_.w(p + vn["fc2"] + ".weight"), ybr, bias=P_.p(p + vn["fc2"] + ".bias"))
-            pending = ly["x1"]
-            st["layers"].append(ly)
+        layers, pending, x, ybr = self._blocks_forward(x, vn, self.nv, B, Lv, W, Iv, Hh, save, "v.", self.vit_act, causal=False)
+        st["layers"] = layers
         # ln_post on the CLS rows of x_final = x1_last + c_proj(...): the add is fused here too; x_cls [B, W] is kept for backward
         st["x_cls"] = self.f32("v.x_cls", B, W)
         st["pooled"] = self.bf("v.pooled", B, W); st["mp"] = self.f32("v.mp", B); st["rp"] = self.f32("v.rp", B)
@@ -262,33 +315,7 @@ class ClipEngine:
                           dgamma=P_.g(vn["ln_post"] + ".weight"), dbeta=P_.g(vn["ln_post"] + ".bias"), dbias=bias_prev,
                           rows=B, ldx=ld_post, lddx=Lv * W)
         ops.cast_bf16(dX, dXb)
-        dz = self.bf("v.dz", M, Iv); dh = self.bf("v.dh", M, W); dctx = self.bf("v.dctx", M, W); dqkv = self.bf("v.dqkv", M, 3 * W)
-        for i in reversed(range(self.nv)):
-            p = vn["layer"].format(i)
-            ly = st["layers"][i]
-            # MLP
-            ops.gemm(dXb, ly["a"], P_.g(p + vn["fc2"] + ".weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
-                     splits=_splits_for(W, Iv, M))
-            ops.gemm(dXb, P_.w(p + vn["fc2"] + ".weight"), dz, b_mn_major=1, mode=L.EPI_MUL_AUX, aux=ly["z"],
-                     colsum=P_.g(p + vn["fc1"] + ".bias"))            # dz = (dX W) o act'(z); its column sums = d(c_fc.bias)
-            ops.gemm(dz, ly["h2"], P_.g(p + vn["fc1"] + ".weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
-                     splits=_splits_for(Iv, W, M))
-            ops.gemm(dz, P_.w(p + vn["fc1"] + ".weight"), dh, b_mn_major=1)
-            dX1 = self.f32("v.dX.b", M, W); dX1b = self.bf("v.dXb.b", M, W)
-            ops.layernorm_bwd(dh, ly["x1"], P_.p(p + vn["ln2"] + ".weight"), ly["m2"], ly["r2"], dx_add=dX, dx_f32=dX1, dx_bf16=dX1b,
-                              dgamma=P_.g(p + vn["ln2"] + ".weight"), dbeta=P_.g(p + vn["ln2"] + ".bias"), dbias=P_.g(p + vn["out"] + ".bias"))
-            # attention
-            ops.gemm(dX1b, ly["ctx"], P_.g(p + vn["out"] + ".weight"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
-                     splits=_splits_for(W, W, M))
-            ops.gemm(dX1b, P_.w(p + vn["out"] + ".weight"), dctx, b_mn_major=1)
-            ops.attention_bwd(ly["qkv"], None, ly["ctx"], ly["lse"], dctx, dqkv, B, Lv, Hh, dqkv_colsum=P_.g(p + vn["qkv_b"], (3 * W,)))
-            ops.gemm(dqkv, ly["h"], P_.g(p + vn["qkv_w"], (3 * W, W)), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD,
-                     splits=_splits_for(3 * W, W, M))
-            ops.gemm(dqkv, P_.w(p + vn["qkv_w"], (3 * W, W)), dh, b_mn_major=1)
-            bias_prev = P_.g(vn["layer"].format(i - 1) + vn["fc2"] + ".bias") if i > 0 else None
-            ops.layernorm_bwd(dh, ly["x_in"], P_.p(p + vn["ln1"] + ".weight"), ly["m1"], ly["r1"], dx_add=dX1, dx_f32=dX, dx_bf16=dXb,
-                              dgamma=P_.g(p + vn["ln1"] + ".weight"), dbeta=P_.g(p + vn["ln1"] + ".bias"), dbias=bias_prev)
-            self._grads_ready(p)
+        dX = self._blocks_backward(st["layers"], dX, dXb, vn, self.nv, B, Lv, W, Iv, Hh, "v.", causal=False)
         # ln_pre, token assembly, patch embedding
         dx0 = self.f32("v.dx0", M, W)
         ops.layernorm_bwd(dX, self.f32("v.x0", M, W), P_.p(vn["ln_pre"] + ".weight"), st["mean0"], st["rstd0"], dx_f32=dx0,
@@ -313,9 +340,65 @@ class ClipEngine:
             self._drops[key] = d
         return d
 
+    # ------------------------------------------------------------------ OPEN_CLIP text tower
+    def octext_forward(self, ids: torch.Tensor, save: bool):
+        """OPEN_CLIP.encode_text (modeling_openclip.py:358-371): token + positional embedding -> causal pre-LN transformer -> ln_final ->
+        features of the EOT token (the highest id of each sequence) @ text_projection"""
+        P_ = self.params; W = self.H; B, Lt = ids.shape; M = B * Lt; Hh = self.Ht
+        if Lt != self.cfg["context_length"]:
+            raise ValueError(f"open_clip texts must be padded to context_length={self.cfg['context_length']} (got {Lt})")
+        st = {"B": B, "Lt": Lt, "ids": ids}
+        st["pos_ids"] = self.buf("o.pos_ids", (B, Lt), torch.int32)
+        st["pos_ids"].copy_(torch.arange(Lt, device=self.dev, dtype=torch.int32).expand(B, Lt))
+        ztype = self.zbuf("o.ztype", (1, W), torch.float32)                       # no token-type table on this tower
+        x = self.f32("o.x.0", M, W)
+        ops.embed_gather(ids, st["pos_ids"], None, None, P_.p("token_embedding.weight"), P_.p("positional_embedding"), ztype, x, None, -1)
+        layers, pending, x, ybr = self._blocks_forward(x, self.on, self.nt, B, Lt, W, 4 * W, Hh, save, "o.", L.EPI_QUICK_GELU, causal=True)
+        st["layers"] = layers
+        # ln_final on every row of x_final = x1_last + c_proj(...), then the EOT rows are gathered for the projection
+        st["x_fin"] = self.f32("o.x_fin", M, W); st["hf"] = self.bf("o.hfin", M, W); st["mf"] = self.f32("o.mf", M); st["rf"] = self.f32("o.rf", M)
+        g, b = P_.p("ln_final.weight"), P_.p("ln_final.bias")
+        if pending is None:
+            ops.layernorm_fwd(x, g, b, 1e-5, st["hf"], None, st["mf"], st["rf"]); st["x_fin"] = x
+        else:
+            ops.layernorm_fwd(pending, g, b, 1e-5, st["hf"], None, st["mf"], st["rf"], add=ybr, x_out=st["x_fin"])
+        st["eot"] = self.buf("o.eot", (B,), torch.int32)
+        ops.argmax_rows(ids, st["eot"])
+        st["pooled"] = self.bf("o.pooled", B, W)
+        ops.gather_rows_bf16(st["hf"], st["eot"], st["pooled"], B, Lt, W)
+        st["feat"] = self.f32("t.feat", B, self.E)
+        ops.gemm(st["pooled"], P_.w("text_projection"), st["feat"], b_mn_major=1)
+        st["embeds"] = self.f32("t.embeds", B, self.E); st["norm"] = self.f32("t.norm", B)
+        if self._peer_on:
+            self._peer.l2norm_allgather(st["feat"], st["embeds"], st["norm"], "text")
+        else:
+            ops.l2norm_fwd(st["feat"], st["embeds"], st["norm"], B, self.E)
+        return st
+
+    def octext_backward(self, st, d_embeds: torch.Tensor):
+        P_ = self.params; W = self.H; B = st["B"]; Lt = st["Lt"]; M = B * Lt; Hh = self.Ht; E = self.E
+        dfeat_b = self.bf("t.dfeat_b", B, E)
+        ops.l2norm_bwd(d_embeds, st["embeds"], st["norm"], None, dfeat_b, B, E)
+        ops.gemm(st["pooled"], dfeat_b, P_.g("text_projection"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
+        dpooled = self.f32("o.dpooled", B, W)
+        ops.gemm(dfeat_b, P_.w("text_projection"), dpooled)
+        dhf = self.f32("o.dhf", M, W)
+        dhf.zero_()
+        ops.scatter_rows_f32(dpooled, st["eot"], dhf, B, Lt, W)                    # only the EOT rows carry a gradient into ln_final
+        dX = self.f32("o.dX.a", M, W); dXb = self.bf("o.dXb.a", M, W)
+        bias_prev = P_.g(self.on["layer"].format(self.nt - 1) + self.on["fc2"] + ".bias") if self.nt else None
+        ops.layernorm_bwd(dhf, st["x_fin"], P_.p("ln_final.weight"), st["mf"], st["rf"], dx_f32=dX, dx_bf16=dXb,
+                          dgamma=P_.g("ln_final.weight"), dbeta=P_.g("ln_final.bias"), dbias=bias_prev)
+        dX = self._blocks_backward(st["layers"], dX, dXb, self.on, self.nt, B, Lt, W, 4 * W, Hh, "o.", causal=True)
+        ztype_g = self.zbuf("o.ztype_g", (1, W), torch.float32)
+        ops.embed_gather_bwd(st["ids"], st["pos_ids"], None, dX, P_.g("token_embedding.weight"), P_.g("positional_embedding"), ztype_g, -1)
+        self._grads_ready("token_embedding."); self._grads_ready("positional_embedding"); self._grads_ready("ln_final.")
+
     def bert_forward(self, ids: torch.Tensor, save: bool, train: bool = False, token_type_ids=None, attention_mask=None):
         """BertModel (chinese_clip: mask = ids != 0, modeling_chineseclip.py:347-349) or RobertaModel (huggingface_clip: pad-aware
         position ids, the batch's token_type_ids / attention_mask, tanh pooler; appzoo/clip/model.py:128-137)"""
+        if self.oc:
+            return self.octext_forward(ids, save)
         P_ = self.params; H = self.H; I = self.I; B, Lt = ids.shape; M = B * Lt; Hh = self.Ht; tp = self.tp
         assert ids.dtype == torch.int64 and ids.is_contiguous()
         if Lt > self.cfg["text_max_position_embeddings"] - (self.pad_id + 1 if self.hf else 0):
@@ -384,6 +467,8 @@ class ClipEngine:
         return st
 
     def bert_backward(self, st, d_embeds: torch.Tensor):
+        if self.oc:
+            return self.octext_backward(st, d_embeds)
         P_ = self.params; H = self.H; I = self.I; B = st["B"]; Lt = st["Lt"]; M = B * Lt; Hh = self.Ht; E = self.E; tp = self.tp
         train = st.get("train", False)
         dfeat_b = self.bf("t.dfeat_b", B, E)

@@ -121,21 +121,30 @@ def _b16(t):
 
 
 @_op
-def attention_fwd(qkv, key_mask, ctx, lse, B, L, H, drop=None):
+def attention_fwd(qkv, key_mask, ctx, lse, B, L, H, drop=None, causal=False):
     d = H * 64
     assert qkv.shape == (B * L, 3 * d) and qkv.is_contiguous() and ctx.shape == (B * L, d) and ctx.is_contiguous()
     assert lse.numel() == B * H * L
     with _traced(f"attention_fwd|L{L}", 4.0 * B * H * L * L * 64):
-        L_.check(L_.lib().clipk_attention_fwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), B, L, H, d, _dp(drop), _stream()), "attention_fwd")
+        if causal:
+            assert key_mask is None and drop is None
+            L_.check(L_.lib().clipk_attention_causal_fwd(_b16(qkv), _b16(ctx), _f32(lse), B, L, H, d, _stream()), "attention_causal_fwd")
+        else:
+            L_.check(L_.lib().clipk_attention_fwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), B, L, H, d, _dp(drop), _stream()), "attention_fwd")
 
 
 @_op
-def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H, drop=None, dqkv_colsum=None):
+def attention_bwd(qkv, key_mask, ctx, lse, dctx, dqkv, B, L, H, drop=None, dqkv_colsum=None, causal=False):
     """dqkv_colsum: optional f32 [3d], += column sums of dqkv (the QKV projection's bias gradient), fused into the kernel"""
     d = H * 64
     assert dqkv.shape == (B * L, 3 * d) and dqkv.is_contiguous() and dctx.shape == (B * L, d) and dctx.is_contiguous()
     assert dqkv_colsum is None or (dqkv_colsum.numel() == 3 * d and dqkv_colsum.is_contiguous())
     with _traced(f"attention_bwd|L{L}", 10.0 * B * H * L * L * 64):
+        if causal:
+            assert key_mask is None and drop is None
+            L_.check(L_.lib().clipk_attention_causal_bwd(_b16(qkv), _b16(ctx), _f32(lse), _b16(dctx), _b16(dqkv), _f32(dqkv_colsum), B, L, H, d, _stream()),
+                     "attention_causal_bwd")
+            return
         L_.check(L_.lib().clipk_attention_bwd(_b16(qkv), _f32(key_mask), _b16(ctx), _f32(lse), _b16(dctx), _b16(dqkv), _f32(dqkv_colsum),
                                               B, L, H, d, _dp(drop), _stream()), "attention_bwd")
 
@@ -226,6 +235,23 @@ def embed_gather_bwd(ids, pos_ids, type_ids, de, dword, dpos, dtype_, pad_id):
     rows = ids.numel(); H = dword.shape[1]
     L_.check(L_.lib().clipk_embed_gather_bwd(_i64(ids), _ptr(pos_ids), _i64(type_ids), _f32(de), _f32(dword), _f32(dpos), _f32(dtype_), rows, H,
                                              dword.shape[0], dpos.shape[0], dtype_.shape[0], int(pad_id), _stream()), "embed_gather_bwd")
+
+
+@_op
+def argmax_rows(ids, idx):
+    B, Lt = ids.shape
+    assert idx.dtype == torch.int32 and idx.numel() == B
+    L_.check(L_.lib().clipk_argmax_rows(_i64(ids), _ptr(idx), B, Lt, _stream()), "argmax_rows")
+
+
+@_op
+def gather_rows_bf16(x, idx, out, B, Lt, W):
+    L_.check(L_.lib().clipk_gather_rows_bf16(_b16(x), _ptr(idx), _b16(out), B, Lt, W, _stream()), "gather_rows_bf16")
+
+
+@_op
+def scatter_rows_f32(src, idx, dst, B, Lt, W):
+    L_.check(L_.lib().clipk_scatter_rows_f32(_f32(src), _ptr(idx), _f32(dst), B, Lt, W, _stream()), "scatter_rows_f32")
 
 
 @_op

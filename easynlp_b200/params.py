@@ -109,6 +109,37 @@ def hf_param_schema(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
     return s
 
 
+def openclip_param_schema(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
+    """(name -> shape) of model_type == open_clip (OPEN_CLIP, modelzoo/models/clip/modeling_openclip.py:255-312): the same
+    VisualTransformer under `visual.*` and a pre-LN text Transformer with a causal mask under `transformer.*`; checkpoint keys carry the
+    `open_clip.` prefix (appzoo/clip/model.py:61-62)."""
+    W = cfg["vision_width"]; P = cfg["vision_patch_size"]; E = cfg["embed_dim"]
+    n_tok = (cfg["image_resolution"] // P) ** 2 + 1
+    Wt = cfg["transformer_width"]; Lc = cfg["context_length"]
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    s["positional_embedding"] = (Lc, Wt)
+    s["text_projection"] = (Wt, E)
+    s["logit_scale"] = ()
+    s["visual.class_embedding"] = (W,)
+    s["visual.positional_embedding"] = (n_tok, W)
+    s["visual.proj"] = (W, E)
+    s["visual.conv1.weight"] = (W, 3, P, P)
+    s["visual.ln_pre.weight"] = (W,); s["visual.ln_pre.bias"] = (W,)
+    for pre, n, w in (("visual.transformer.resblocks.", cfg["vision_layers"], W), ("transformer.resblocks.", cfg["transformer_layers"], Wt)):
+        for i in range(n):
+            p = f"{pre}{i}."
+            s[p + "attn.in_proj_weight"] = (3 * w, w); s[p + "attn.in_proj_bias"] = (3 * w,)
+            s[p + "attn.out_proj.weight"] = (w, w); s[p + "attn.out_proj.bias"] = (w,)
+            s[p + "ln_1.weight"] = (w,); s[p + "ln_1.bias"] = (w,)
+            s[p + "mlp.c_fc.weight"] = (4 * w, w); s[p + "mlp.c_fc.bias"] = (4 * w,)
+            s[p + "mlp.c_proj.weight"] = (w, 4 * w); s[p + "mlp.c_proj.bias"] = (w,)
+            s[p + "ln_2.weight"] = (w,); s[p + "ln_2.bias"] = (w,)
+    s["visual.ln_post.weight"] = (W,); s["visual.ln_post.bias"] = (W,)
+    s["token_embedding.weight"] = (cfg["vocab_size"], Wt)
+    s["ln_final.weight"] = (Wt,); s["ln_final.bias"] = (Wt,)
+    return s
+
+
 # the pooler is computed-but-unused by chinese_clip (modeling_chineseclip.py:349 takes [0]); its parameters never get a
 # gradient, so the reference optimizer skips them (optimizers.py:420-421) -- they sit outside the updated range.
 NO_GRAD = ("bert.pooler.dense.weight", "bert.pooler.dense.bias")
@@ -135,9 +166,14 @@ class ParamStore:
             self.no_grad = tuple(n for n in self.schema if n.startswith("vision_encoder."))
             self.buffers = {"text_encoder.embeddings.position_ids": cfg["text_max_position_embeddings"],
                             "vision_encoder.vision_model.embeddings.position_ids": (cfg["image_resolution"] // cfg["vision_patch_size"]) ** 2 + 1}
+        elif self.kind == "open_clip":
+            self.schema = openclip_param_schema(cfg)
+            self.no_grad = ()
+            self.buffers = {}
         else:
             self.schema = param_schema(cfg)
             self.no_grad = NO_GRAD
+        if self.kind not in ("huggingface_clip", "open_clip"):
             # buffer exported by the reference BertEmbeddings (modeling_bert.py:87)
             self.buffers = {"bert.embeddings.position_ids": cfg["text_max_position_embeddings"]}
         NO_GRAD_ = set(self.no_grad)

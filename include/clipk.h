@@ -107,6 +107,12 @@ int clipk_attention_bwd(const void* qkv, const float* key_mask, const void* ctx,
                         void* dqkv, float* dqkv_colsum, int B, int L, int H, int d,
                         const clipk_dropout_t* drop /* same as forward; L <= 128 */, cudaStream_t stream);
 
+/* Causal self-attention of OPEN_CLIP's text tower (additive -inf above the diagonal, modeling_openclip.py:296-301,346-352); same layout
+ * and outputs as above, no key mask / dropout; forward L <= 272, backward L <= 128. */
+int clipk_attention_causal_fwd(const void* qkv, void* ctx, float* lse, int B, int L, int H, int d, cudaStream_t stream);
+int clipk_attention_causal_bwd(const void* qkv, const void* ctx, const float* lse, const void* dctx, void* dqkv, float* dqkv_colsum, int B, int L,
+                               int H, int d, cudaStream_t stream);
+
 /* -------------------------------------------------------------------------------------------- LayerNorm
  * y = (x - mean) * rstd * gamma + beta over the last dim d (d % 128 == 0, d <= 1024), fp32 statistics
  * (modeling_chineseclip.py:170-176 eps 1e-5; nn.LayerNorm eps 1e-12 in modeling_bert.py:84,266,344).
@@ -157,6 +163,11 @@ int clipk_embed_gather(const long long* ids, const int* pos_ids, const long long
                        float* key_mask /* optional */, int rows, int H, int vocab, int npos, int ntype, int pad_id, cudaStream_t stream);
 int clipk_embed_gather_bwd(const long long* ids, const int* pos_ids, const long long* type_ids, const float* de, float* dword,
                            float* dpos, float* dtype, int rows, int H, int vocab, int npos, int ntype, int pad_id, cudaStream_t stream);
+/* EOT pooling of OPEN_CLIP.encode_text (modeling_openclip.py:367-369: x[arange(B), text.argmax(-1)]): idx[b] = first argmax of ids[b, :];
+ * out[b, :] = x[b*L + idx[b], :] (bf16 rows, W % 8 == 0); backward: dst[b*L + idx[b], :] = src[b, :] into a zero-filled fp32 [B*L, W] */
+int clipk_argmax_rows(const long long* ids, int* idx, int B, int L, cudaStream_t stream);
+int clipk_gather_rows_bf16(const void* x_bf16, const int* idx, void* out_bf16, int B, int L, int W, cudaStream_t stream);
+int clipk_scatter_rows_f32(const float* src, const int* idx, float* dst, int B, int L, int W, cudaStream_t stream);
 /* pooler activation (RobertaPooler: tanh(dense(h[:,0])), modeling_roberta.py:559-575; used as the text feature by the
  * huggingface_clip branch, appzoo/clip/model.py:135): y = tanh(x) (+ bf16 copy); dx = dy * (1 - y^2) */
 int clipk_tanh_fwd(const float* x, float* y, void* y_bf16 /* optional */, long long n, cudaStream_t stream);

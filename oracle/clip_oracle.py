@@ -505,3 +505,76 @@ def hf_clip_forward(sd: Dict[str, Tensor], raw_cfg: dict, pixels: Optional[Tenso
         lpt = (text_embeds @ image_embeds.t()) * sd["logit_scale"].exp()
         out["logits_per_text"] = lpt; out["logits_per_image"] = lpt.T
     return out
+
+
+# =========================================================================== open_clip branch
+# appzoo/clip/model.py:56-63: OPEN_CLIP (modelzoo/models/clip/modeling_openclip.py:255-383) = the same VisualTransformer + a pre-LN text
+# Transformer with a causal mask (:346-352), token + positional embeddings, ln_final and EOT-argmax pooling (:358-371).
+def openclip_tiny_config() -> dict:
+    return dict(model_type="open_clip", embed_dim=128, image_resolution=64, vision_layers=2, vision_width=128, vision_patch_size=16,
+                context_length=24, vocab_size=512, transformer_width=128, transformer_heads=2, transformer_layers=2)
+
+
+def openclip_init_state_dict(cfg: dict, seed: int = 1234, scale_boost: float = 1.0) -> Dict[str, Tensor]:
+    g = torch.Generator().manual_seed(seed)
+
+    def randn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    sd: Dict[str, Tensor] = {}
+    W = cfg["vision_width"]; P = cfg["vision_patch_size"]; E = cfg["embed_dim"]; Wt = cfg["transformer_width"]
+    n_tok = (cfg["image_resolution"] // P) ** 2 + 1
+    sd["logit_scale"] = torch.tensor(math.log(1 / 0.07))
+    sd["positional_embedding"] = randn(cfg["context_length"], Wt, std=0.01)
+    sd["text_projection"] = randn(Wt, E, std=Wt ** -0.5)
+    sd["token_embedding.weight"] = randn(cfg["vocab_size"], Wt, std=0.02)
+    sd["visual.class_embedding"] = randn(W, std=W ** -0.5)
+    sd["visual.positional_embedding"] = randn(n_tok, W, std=W ** -0.5)
+    sd["visual.proj"] = randn(W, E, std=W ** -0.5)
+    sd["visual.conv1.weight"] = randn(W, 3, P, P, std=(3 * P * P) ** -0.5)
+
+    def ln(prefix, d):
+        sd[prefix + ".weight"] = 1.0 + 0.1 * randn(d); sd[prefix + ".bias"] = 0.1 * randn(d)
+
+    ln("visual.ln_pre", W); ln("visual.ln_post", W); ln("ln_final", Wt)
+    for pre, n, w in (("visual.transformer.resblocks.", cfg["vision_layers"], W), ("transformer.resblocks.", cfg["transformer_layers"], Wt)):
+        for i in range(n):
+            p = f"{pre}{i}."
+            sd[p + "attn.in_proj_weight"] = randn(3 * w, w, std=w ** -0.5) * scale_boost; sd[p + "attn.in_proj_bias"] = 0.02 * randn(3 * w)
+            sd[p + "attn.out_proj.weight"] = randn(w, w, std=w ** -0.5 * (2 * n) ** -0.5); sd[p + "attn.out_proj.bias"] = 0.02 * randn(w)
+            ln(p + "ln_1", w); ln(p + "ln_2", w)
+            sd[p + "mlp.c_fc.weight"] = randn(4 * w, w, std=(2 * w) ** -0.5); sd[p + "mlp.c_fc.bias"] = 0.02 * randn(4 * w)
+            sd[p + "mlp.c_proj.weight"] = randn(w, 4 * w, std=w ** -0.5 * (2 * n) ** -0.5); sd[p + "mlp.c_proj.bias"] = 0.02 * randn(w)
+    return sd
+
+
+def openclip_text_forward(sd: Dict[str, Tensor], cfg: dict, ids: Tensor) -> Tensor:
+    """OPEN_CLIP.encode_text (modeling_openclip.py:358-371) -> [B, embed_dim] (un-normalised)"""
+    Wt = cfg["transformer_width"]; heads = cfg["transformer_heads"]
+    B, L = ids.shape
+    x = sd["token_embedding.weight"][ids] + sd["positional_embedding"]
+    causal = torch.full((L, L), float("-inf")).triu_(1)
+    for i in range(cfg["transformer_layers"]):
+        p = f"transformer.resblocks.{i}."
+        h = _ln(x, sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], 1e-5)
+        x = x + _mha(h, sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"], sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"], heads, causal)
+        h = _ln(x, sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], 1e-5)
+        h = quick_gelu(h @ sd[p + "mlp.c_fc.weight"].t() + sd[p + "mlp.c_fc.bias"])
+        x = x + (h @ sd[p + "mlp.c_proj.weight"].t() + sd[p + "mlp.c_proj.bias"])
+    x = _ln(x, sd["ln_final.weight"], sd["ln_final.bias"], 1e-5)
+    return x[torch.arange(B), ids.argmax(dim=-1)] @ sd["text_projection"]
+
+
+def openclip_forward(sd: Dict[str, Tensor], cfg: dict, pixels: Optional[Tensor], ids: Optional[Tensor]) -> dict:
+    image_embeds = text_embeds = None
+    if pixels is not None:
+        f = vit_forward(sd, cfg, pixels)
+        image_embeds = f / f.norm(dim=-1, keepdim=True)
+    if ids is not None:
+        t = openclip_text_forward(sd, cfg, ids)
+        text_embeds = t / t.norm(dim=-1, keepdim=True)
+    out = {"image_embeds": image_embeds, "text_embeds": text_embeds}
+    if image_embeds is not None and text_embeds is not None:
+        lpt = (text_embeds @ image_embeds.t()) * sd["logit_scale"].exp()
+        out["logits_per_text"] = lpt; out["logits_per_image"] = lpt.T
+    return out

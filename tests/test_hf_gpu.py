@@ -138,3 +138,51 @@ def test_hf_patch14_257_tokens_forward_vs_oracle():
     e, y = max_err(out, ref), max_err(yard, ref)
     print(f"PARITY hf patch14 L=257 fwd: image embeds max err {e:.2e} (PyTorch bf16 yardstick {y:.2e})")
     assert e < 1.5 * y + 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ open_clip branch
+def test_openclip_tiny_forward_backward_vs_reference_golden(tmp_path):
+    """model_type == open_clip (appzoo/clip/model.py:56-63): ViT + causal pre-LN text transformer + EOT-argmax pooling -- the causal variants of
+    the attention kernels, the EOT row gather / scatter, and every gradient against the fixture written by the unmodified reference."""
+    from easynlp_b200.appzoo import get_application_model
+    z = np.load(os.path.join(GOLD, "openclip_tiny_fwd_bwd.npz"))
+    cfg = json.loads(bytes(z["cfg_json"]).decode())
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w.")}
+    d = str(tmp_path / "oc"); os.makedirs(d)
+    json.dump(cfg, open(os.path.join(d, "config.json"), "w"))
+    torch.save({"open_clip." + k: v for k, v in sd.items()}, os.path.join(d, "pytorch_model.bin"))
+    model = get_application_model("clip", d, user_defined_parameters={"app_parameters": {}})
+    assert model.model_type == "open_clip" and all(n.startswith("open_clip.") for n, _ in model.named_parameters())
+    eng = model.engine
+    pixels = torch.from_numpy(z["pixels"]); ids = torch.from_numpy(z["ids"])
+    out = eng.forward(pixels.cuda(), ids.cuda())
+    torch.cuda.synchronize()
+    ref = {k: torch.from_numpy(z["out." + k]) for k in ("image_embeds", "text_embeds", "logits_per_text")}
+    names = list(sd)
+    params = {k: sd[k].clone().requires_grad_(True) for k in names}
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        yo = O.openclip_forward(params, cfg, pixels, ids)
+    yo = {k: v.float() for k, v in yo.items()}
+    yl = O.clip_loss(yo["logits_per_text"])
+    yg = dict(zip(names, torch.autograd.grad(yl, [params[k] for k in names], allow_unused=True)))
+    e = {k: max_err(out[k], ref[k]) for k in ref}; y = {k: max_err(yo[k], ref[k]) for k in ref}
+    loss_ref = float(z["out.loss"]); loss = out["loss"].item()
+    print(f"PARITY open_clip tiny fwd: err {e} (PyTorch bf16 yardstick {y}); loss {loss:.6f} vs {loss_ref:.6f}")
+    assert e["image_embeds"] < 1.5 * y["image_embeds"] + 1e-4 and e["text_embeds"] < 1.5 * y["text_embeds"] + 1e-4
+    assert e["logits_per_text"] < 1.5 * y["logits_per_text"] + 1e-3
+    assert abs(loss - loss_ref) < max(2e-3 * abs(loss_ref), 2.0 * abs(yl.item() - loss_ref))
+    eng.zero_grad(); eng.backward()
+    torch.cuda.synchronize()
+    refg = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("g.")}
+    gnorm = math.sqrt(sum(float(v.double().norm()) ** 2 for v in refg.values()))
+    worst = (0.0, None)
+    for k, r in refg.items():
+        got = eng.params.g(k).detach().float().cpu().view_as(r)
+        err = (got - r).norm().item(); yerr = (yg[k].float() - r).norm().item()
+        tol = max(0.03 * r.norm().item(), 1.5 * yerr) + 1e-4 * gnorm
+        worst = max(worst, (err / (r.norm().item() + 1e-4 * gnorm), k))
+        assert err <= tol, f"grad {k}: err {err:.3e} > tol {tol:.3e} (|ref| {r.norm().item():.3e}, yardstick {yerr:.3e})"
+    print(f"PARITY open_clip tiny bwd: worst per-tensor relative gradient error {worst[0]:.3e} ({worst[1]})")
+    eng.optimizer_step(lr=1e-3)
+    torch.cuda.synchronize()
+    assert torch.isfinite(eng.params.master).all()

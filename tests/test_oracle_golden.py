@@ -123,3 +123,24 @@ def test_hf_oracle_matches_reference_golden():
     m = ids.ne(0).int()
     pos = torch.cumsum(m, 1) * m
     assert pos[3].tolist()[:3] == [1, 2, 0] and pos.max().item() == 16
+
+
+def test_openclip_oracle_matches_reference_golden():
+    """open_clip branch (OPEN_CLIP: ViT + causal text transformer + EOT pooling, modeling_openclip.py:255-383) against the fixture written
+    by the UNMODIFIED reference (oracle/make_golden_openclip.py): forward and all 62 gradient tensors."""
+    import json
+    z = np.load(os.path.join(GOLD, "openclip_tiny_fwd_bwd.npz"))
+    cfg = json.loads(bytes(z["cfg_json"]).decode())
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w.")}
+    names = list(sd)
+    params = {k: sd[k].clone().requires_grad_(True) for k in names}
+    out = O.openclip_forward(params, cfg, torch.from_numpy(z["pixels"]), torch.from_numpy(z["ids"]))
+    for k in ("image_embeds", "text_embeds", "logits_per_text"):
+        assert torch.allclose(out[k], torch.from_numpy(z["out." + k]), rtol=2e-4, atol=2e-5), k
+    loss = O.clip_loss(out["logits_per_text"])
+    assert abs(loss.item() - float(z["out.loss"])) < 1e-5
+    grads = dict(zip(names, torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)))
+    ref = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("g.")}
+    assert len(ref) == 62
+    for k, r in ref.items():
+        assert torch.allclose(grads[k], r, rtol=2e-3, atol=2e-6), k
