@@ -89,6 +89,8 @@ def _declare(L):
     L.clipk_argmax_rows.argtypes = [vp, vp, i, i, vp]
     L.clipk_gather_rows_bf16.argtypes = [vp, vp, vp, i, i, i, vp]
     L.clipk_scatter_rows_f32.argtypes = [vp, vp, vp, i, i, i, vp]
+    L.clipk_frame_pool_fwd.argtypes = [vp, vp, vp, i, i, i, vp]
+    L.clipk_frame_pool_bwd.argtypes = [vp, vp, vp, i, i, i, vp]
     L.clipk_position_ids.argtypes = [vp, vp, i, i, i, vp]
     L.clipk_embed_gather.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     L.clipk_embed_gather_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]

@@ -1,5 +1,7 @@
-"""AppZoo registry for the one application on the hot path -- same call signatures as easynlp/appzoo/api.py:281-468
-(prefix match on app_name, NotImplementedError for unknown apps, extra kwargs tolerated)."""
+"""AppZoo registry for the applications on the hot path -- same call signatures as easynlp/appzoo/api.py:281-468 (prefix match on
+app_name in the reference's dictionary order: 'clip4clip' before 'clip'; NotImplementedError for unknown apps, extra kwargs tolerated).
+'clip' is complete (model, dataset, evaluator, predictor); 'clip4clip' (Text2VideoRetrieval, a sibling app sharing the encoders) registers
+its model."""
 
 
 def _clip_classes():
@@ -11,19 +13,25 @@ def _clip_classes():
 
 
 def _match(app_name):
-    if app_name is not None and app_name.startswith("clip"):
+    if app_name is not None and app_name.startswith("clip") and not app_name.startswith("clip4clip"):
         return True
     raise NotImplementedError(f"application {app_name!r} is outside the B200 hot path (only 'clip' is registered)")
 
 
-def get_application_model(app_name, pretrained_model_name_or_path, user_defined_parameters=None, **kwargs):
+def _model_cls(app_name):
+    if app_name is not None and app_name.startswith("clip4clip"):
+        from .text2video_retrieval.model import Text2VideoRetrieval
+        return Text2VideoRetrieval
     _match(app_name)
-    return _clip_classes()[0](pretrained_model_name_or_path, user_defined_parameters=user_defined_parameters, **kwargs)
+    return _clip_classes()[0]
+
+
+def get_application_model(app_name, pretrained_model_name_or_path, user_defined_parameters=None, **kwargs):
+    return _model_cls(app_name)(pretrained_model_name_or_path, user_defined_parameters=user_defined_parameters, **kwargs)
 
 
 def get_application_model_for_evaluation(app_name, pretrained_model_name_or_path, user_defined_parameters=None, **kwargs):
-    _match(app_name)
-    return _clip_classes()[0].from_pretrained(pretrained_model_name_or_path, user_defined_parameters=user_defined_parameters or {}, **kwargs)
+    return _model_cls(app_name).from_pretrained(pretrained_model_name_or_path, user_defined_parameters=user_defined_parameters or {}, **kwargs)
 
 
 def get_application_evaluator(app_name, valid_dataset, user_defined_parameters=None, **kwargs):

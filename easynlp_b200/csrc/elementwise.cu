@@ -366,6 +366,39 @@ __global__ void __launch_bounds__(256) scatter_rows_f32_kernel(const float* __re
   for (int c = threadIdx.x * 4; c < W; c += blockDim.x * 4) st_f4(d + c, ld_f4(src + (long long)b * W + c));
 }
 
+// masked mean over the T frames of a video (Text2VideoRetrieval._mean_pooling_for_similarity_visual, appzoo/text2video_retrieval/model.py:98-104):
+// out[b, :] = sum_t mask[b,t] * x[b,t,:] / max(sum_t mask[b,t], 1) ; backward: dx[b,t,:] = mask[b,t] * dout[b,:] / count
+__global__ void __launch_bounds__(256) frame_pool_fwd_kernel(const float* __restrict__ x, const long long* __restrict__ mask, float* __restrict__ out,
+                                                             int B, int T, int E) {
+  const int b = blockIdx.x;
+  float cnt = 0.f;
+  for (int t = 0; t < T; ++t) cnt += (float)mask[(long long)b * T + t];
+  const float inv = 1.0f / (cnt == 0.f ? 1.f : cnt);
+  for (int c = threadIdx.x * 4; c < E; c += blockDim.x * 4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) {
+      const float m = (float)mask[(long long)b * T + t];
+      const float4 v = ld_f4(x + ((long long)b * T + t) * E + c);
+      a.x += m * v.x; a.y += m * v.y; a.z += m * v.z; a.w += m * v.w;
+    }
+    st_f4(out + (long long)b * E + c, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
+  }
+}
+__global__ void __launch_bounds__(256) frame_pool_bwd_kernel(const float* __restrict__ dout, const long long* __restrict__ mask, float* __restrict__ dx,
+                                                             int B, int T, int E) {
+  const int b = blockIdx.x;
+  float cnt = 0.f;
+  for (int t = 0; t < T; ++t) cnt += (float)mask[(long long)b * T + t];
+  const float inv = 1.0f / (cnt == 0.f ? 1.f : cnt);
+  for (int c = threadIdx.x * 4; c < E; c += blockDim.x * 4) {
+    const float4 g = ld_f4(dout + (long long)b * E + c);
+    for (int t = 0; t < T; ++t) {
+      const float m = (float)mask[(long long)b * T + t] * inv;
+      st_f4(dx + ((long long)b * T + t) * E + c, make_float4(m * g.x, m * g.y, m * g.z, m * g.w));
+    }
+  }
+}
+
 // y = tanh(x) (BertPooler / RobertaPooler activation, modeling_bert.py:529-541); dx = dy * (1 - y^2)
 __global__ void __launch_bounds__(256) tanh_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, bf16* __restrict__ y_bf16, long long n4) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
@@ -616,6 +649,23 @@ extern "C" int clipk_scatter_rows_f32(const float* src, const int* idx, float* d
   if (W % 4) { set_error("scatter_rows: W %% 4 != 0"); return CLIPK_ERR_ARG; }
   if (B <= 0) return 0;
   scatter_rows_f32_kernel<<<B, 128, 0, stream>>>(src, idx, dst, B, L, W);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int clipk_frame_pool_fwd(const float* x, const long long* mask, float* out, int B, int T, int E, cudaStream_t stream) {
+  if (E % 4) { set_error("frame_pool: E %% 4 != 0"); return CLIPK_ERR_ARG; }
+  if (B <= 0) return 0;
+  frame_pool_fwd_kernel<<<B, 128, 0, stream>>>(x, mask, out, B, T, E);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int clipk_frame_pool_bwd(const float* dout, const long long* mask, float* dx, int B, int T, int E, cudaStream_t stream) {
+  if (E % 4) { set_error("frame_pool: E %% 4 != 0"); return CLIPK_ERR_ARG; }
+  if (B <= 0) return 0;
+  frame_pool_bwd_kernel<<<B, 128, 0, stream>>>(dout, mask, dx, B, T, E);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

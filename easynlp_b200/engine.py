@@ -603,7 +603,19 @@ class ClipEngine:
             out["text_embeds"] = self.bert_forward(ids, save=False, token_type_ids=token_type_ids, attention_mask=attention_mask)["embeds"]
         return out
 
-    def forward(self, pixels, ids, save=True, want_logits=True, distributed=False, train=None, token_type_ids=None, attention_mask=None):
+    def _video_pool(self, v, video_masks, B, T):
+        """frame embeddings [B*T, E] (each l2-normalised) -> masked mean over the frames -> l2-normalised video embeddings [B, E]
+        (appzoo/text2video_retrieval/model.py:82-88)"""
+        E = self.E
+        vm = video_masks.to(self.dev).long().contiguous()
+        vf = self.f32("vd.feat", B, E)
+        ops.frame_pool_fwd(v["embeds"], vm, vf, B, T, E)
+        ve = self.f32("vd.embeds", B, E); vn_ = self.f32("vd.norm", B)
+        ops.l2norm_fwd(vf, ve, vn_, B, E)
+        return {"mask": vm, "T": T, "embeds": ve, "norm": vn_}
+
+    def forward(self, pixels, ids, save=True, want_logits=True, distributed=False, train=None, token_type_ids=None, attention_mask=None,
+                video_masks=None):
         """Both towers + the contrastive head.  distributed=True: all-gather the embedding shards over the default process
         group and take the loss over the GLOBAL batch (labels offset by rank * local_B); 'loss' is then this rank's share
         (sum over ranks = global loss) and 'logits_per_text' the local [b, G] strip."""
@@ -622,7 +634,16 @@ class ClipEngine:
             if self._peer_key != (B, self.E):
                 self._peer = D.PeerGroup.create(B, self.E, self.dev); self._peer_key = (B, self.E)
             self._peer_on = self._peer is not None
-        v = self.vit_forward(pixels, save and not self.hf)       # huggingface_clip: the image tower is frozen -> no activations kept
+        if video_masks is not None:      # Text2VideoRetrieval: [B, T, 3, R, R] frames through the image tower, masked mean over the frames
+            if dist_on:
+                raise NotImplementedError("video batches use the single-process loss")
+            Bv, T = pixels.shape[0], pixels.shape[1]
+            v = self.vit_forward(pixels.reshape(Bv * T, *pixels.shape[2:]).contiguous(), save and not self.hf)
+            v["video"] = self._video_pool(v, video_masks, Bv, T)
+            img_embeds = v["video"]["embeds"]
+        else:
+            v = self.vit_forward(pixels, save and not self.hf)       # huggingface_clip: the image tower is frozen -> no activations kept
+            img_embeds = v["embeds"]
         t = self.bert_forward(ids, save, train=train, token_type_ids=token_type_ids, attention_mask=attention_mask)
         if dist_on:
             Wd = D.world_size()
@@ -635,10 +656,13 @@ class ClipEngine:
             l = self.loss_forward(t["embeds"], v["embeds"], gi, gt, label_offset=D.get_rank() * B, want_logits=want_logits)
             l["dist"] = True; l["peer"] = self._peer_on
         else:
-            l = self.loss_forward(t["embeds"], v["embeds"], want_logits=want_logits)
+            l = self.loss_forward(t["embeds"], img_embeds, want_logits=want_logits)
             l["dist"] = False; l["peer"] = False
         self._peer_on = False
         self._saved = (v, t, l) if save else None
+        if video_masks is not None:
+            return {"video_embeds": v["video"]["embeds"], "text_embeds": t["embeds"], "logits_per_text": l["logits"], "logits_per_image": l["logits_img"],
+                    "loss": l["loss_sum"], "distributed": l["dist"]}
         return {"image_embeds": v["embeds"], "text_embeds": t["embeds"], "logits_per_text": l["logits"], "logits_per_image": l["logits_img"],
                 "loss": l["loss_sum"], "distributed": l["dist"]}
 
@@ -664,6 +688,12 @@ class ClipEngine:
         else:
             dT, dI, _, _ = self.loss_backward(l, grad_scale, local_gallery=True)
         self.bert_backward(t, dT)
+        if v.get("video") is not None:      # video embeds <- l2norm <- masked frame mean <- per-frame l2-normalised image embeds
+            vd = v["video"]; Bv = vd["embeds"].shape[0]; T = vd["T"]
+            dvf = self.f32("vd.dfeat", Bv, self.E); dframe = self.f32("vd.dframe", Bv * T, self.E)
+            ops.l2norm_bwd(dI, vd["embeds"], vd["norm"], dvf, None, Bv, self.E)
+            ops.frame_pool_bwd(dvf, vd["mask"], dframe, Bv, T, self.E)
+            dI = dframe
         self.vit_backward(v, dI)
         self._saved = None
 

@@ -255,6 +255,16 @@ def scatter_rows_f32(src, idx, dst, B, Lt, W):
 
 
 @_op
+def frame_pool_fwd(x, mask, out, B, T, E):
+    L_.check(L_.lib().clipk_frame_pool_fwd(_f32(x), _i64(mask), _f32(out), B, T, E, _stream()), "frame_pool_fwd")
+
+
+@_op
+def frame_pool_bwd(dout, mask, dx, B, T, E):
+    L_.check(L_.lib().clipk_frame_pool_bwd(_f32(dout), _i64(mask), _f32(dx), B, T, E, _stream()), "frame_pool_bwd")
+
+
+@_op
 def tanh_fwd(x, y, y_bf16=None):
     L_.check(L_.lib().clipk_tanh_fwd(_f32(x), _f32(y), _b16(y_bf16), x.numel(), _stream()), "tanh_fwd")
 

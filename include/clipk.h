@@ -168,6 +168,10 @@ int clipk_embed_gather_bwd(const long long* ids, const int* pos_ids, const long 
 int clipk_argmax_rows(const long long* ids, int* idx, int B, int L, cudaStream_t stream);
 int clipk_gather_rows_bf16(const void* x_bf16, const int* idx, void* out_bf16, int B, int L, int W, cudaStream_t stream);
 int clipk_scatter_rows_f32(const float* src, const int* idx, float* dst, int B, int L, int W, cudaStream_t stream);
+/* masked mean over the T frame embeddings of a video and its backward (Text2VideoRetrieval._mean_pooling_for_similarity_visual,
+ * appzoo/text2video_retrieval/model.py:98-104): x f32 [B, T, E], mask int64 [B, T] */
+int clipk_frame_pool_fwd(const float* x, const long long* mask, float* out, int B, int T, int E, cudaStream_t stream);
+int clipk_frame_pool_bwd(const float* dout, const long long* mask, float* dx, int B, int T, int E, cudaStream_t stream);
 /* pooler activation (RobertaPooler: tanh(dense(h[:,0])), modeling_roberta.py:559-575; used as the text feature by the
  * huggingface_clip branch, appzoo/clip/model.py:135): y = tanh(x) (+ bf16 copy); dx = dy * (1 - y^2) */
 int clipk_tanh_fwd(const float* x, float* y, void* y_bf16 /* optional */, long long n, cudaStream_t stream);

@@ -186,3 +186,33 @@ def test_openclip_tiny_forward_backward_vs_reference_golden(tmp_path):
     eng.optimizer_step(lr=1e-3)
     torch.cuda.synchronize()
     assert torch.isfinite(eng.params.master).all()
+
+
+def test_text2video_retrieval_vs_reference_golden(tmp_path):
+    """'clip4clip' sibling application (appzoo/text2video_retrieval/model.py:38-120): T frames per video through the open_clip image tower,
+    masked mean over the frames, InfoNCE against the texts -- forward and a sample of gradients against the unmodified reference."""
+    from easynlp_b200.appzoo import get_application_model
+    zc = np.load(os.path.join(GOLD, "openclip_tiny_fwd_bwd.npz")); z = np.load(os.path.join(GOLD, "t2v_tiny.npz"))
+    cfg = json.loads(bytes(zc["cfg_json"]).decode())
+    sd = {k[2:]: torch.from_numpy(zc[k]) for k in zc.files if k.startswith("w.")}
+    d = str(tmp_path / "t2v"); os.makedirs(d)
+    json.dump(cfg, open(os.path.join(d, "config.json"), "w"))
+    torch.save({"open_clip." + k: v for k, v in sd.items()}, os.path.join(d, "pytorch_model.bin"))
+    model = get_application_model("clip4clip", d, user_defined_parameters={"app_parameters": {}})
+    assert type(model).__name__ == "Text2VideoRetrieval"
+    model.train()
+    batch = {"pixel_values": torch.from_numpy(z["pixels"]), "video_masks": torch.from_numpy(z["video_masks"]), "input_ids": torch.from_numpy(z["ids"])}
+    out = model(batch)
+    assert set(out) == {"logits_per_text", "logits_per_video", "video_embeds", "text_embeds"} and batch["pixel_values"].shape[0] == 15
+    assert max_err(out["video_embeds"], torch.from_numpy(z["out.video_embeds"])) < 6e-3
+    assert max_err(out["text_embeds"], torch.from_numpy(z["out.text_embeds"])) < 6e-3
+    loss = model.compute_loss(out, [])["loss"]
+    assert abs(loss.item() - float(z["out.loss"])) < 5e-3 * float(z["out.loss"]) + 2e-3
+    model.zero_grad(); loss.backward()
+    for k in [f[2:] for f in z.files if f.startswith("g.")]:
+        r = torch.from_numpy(z["g." + k]); got = model.engine.params.g(k).detach().float().cpu().view_as(r)
+        assert (got - r).norm().item() < 0.08 * r.norm().item() + 1e-4, (k, (got - r).norm().item(), r.norm().item())
+    model.eval()
+    with torch.no_grad():
+        f = model({"pixel_values": torch.from_numpy(z["pixels"]), "video_masks": torch.from_numpy(z["video_masks"])}, feat=True)
+    assert f["text_embeds"] is None and max_err(f["video_embeds"], torch.from_numpy(z["out.video_embeds"])) < 6e-3
