@@ -91,6 +91,12 @@ def _declare(L):
     L.clipk_scatter_rows_f32.argtypes = [vp, vp, vp, i, i, i, vp]
     L.clipk_frame_pool_fwd.argtypes = [vp, vp, vp, i, i, i, vp]
     L.clipk_frame_pool_bwd.argtypes = [vp, vp, vp, i, i, i, vp]
+    L.clipk_wp_create.argtypes = [C.c_char_p, C.c_char_p, i]
+    L.clipk_wp_create.restype = vp
+    L.clipk_wp_destroy.argtypes = [vp]
+    L.clipk_wp_destroy.restype = None
+    L.clipk_wp_encode.argtypes = [vp, C.c_char_p, i, vp, vp]
+    L.clipk_wp_encode_batch.argtypes = [vp, C.POINTER(C.c_char_p), i, i, vp, vp, vp, i]
     L.clipk_position_ids.argtypes = [vp, vp, i, i, i, vp]
     L.clipk_embed_gather.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     L.clipk_embed_gather_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]

@@ -26,7 +26,7 @@ def _sources():
 def _digest():
     h = hashlib.sha256()
     for f in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(CSRC, "*.h"))) + \
-            [os.path.join(PKG, "..", "include", "clipk.h")]:
+            [os.path.join(PKG, "..", "include", "clipk.h"), os.path.join(PKG, "..", "tools", "gen_unicode_table.py")]:
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -37,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "libclipk.sha256")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+    if not force and os.path.exists(LIB) and os.path.exists(os.path.join(LIBDIR, "unicode_bmp.bin")) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
@@ -60,6 +60,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("clipk build failed")
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
+    # per-code-point tables of the native WordPiece tokenizer, from the same Python unicodedata the reference's tokenizer evaluates
+    subprocess.check_call([sys.executable, os.path.join(PKG, "..", "tools", "gen_unicode_table.py"), os.path.join(LIBDIR, "unicode_bmp.bin")],
+                          stdout=subprocess.DEVNULL)
     with open(stamp, "w") as f:
         f.write(dig)
     return LIB

@@ -2,7 +2,12 @@
 (easynlp/modelzoo/models/bert/tokenization_bert.py:67-504: BasicTokenizer + WordpieceTokenizer, do_lower_case=True,
 tokenize_chinese_chars=True) for the one call pattern the CLIP app uses (appzoo/clip/data.py:262-264,
 appzoo/clip/predictor.py): `tokenizer([text], padding='max_length', truncation=True, max_length=L)`.
-Pinned against the reference tokenizer by tests/golden/tokenizer.json."""
+Pinned against the reference tokenizer by tests/golden/tokenizer.json.
+
+Two implementations with identical results: this Python restatement and the NATIVE one behind the C ABI (clipk_wp_*,
+easynlp_b200/csrc/wordpiece.cu: multi-threaded batches, per-code-point tables generated from the same Python unicodedata).  `__call__`
+uses the native encoder when the library is present; a text holding a code point outside the native tables (supplementary planes other
+than the CJK extensions, capital sigma) is tokenized here."""
 import collections
 import unicodedata
 from typing import Dict, List
@@ -49,6 +54,43 @@ class BertTokenizer:
         self.unk_token, self.sep_token, self.pad_token, self.cls_token, self.mask_token = unk_token, sep_token, pad_token, cls_token, mask_token
         self.never_split = {unk_token, sep_token, pad_token, cls_token, mask_token}
         self.max_input_chars_per_word = 100
+        self.vocab_file = vocab_file
+        self._native = None          # handle of the native encoder (created lazily; False = unavailable)
+        self.native_threads = 8
+        self.native_stats = {"native": 0, "fallback": 0}
+
+    def _native_handle(self):
+        if self._native is None:
+            self._native = False
+            defaults = (self.unk_token, self.sep_token, self.pad_token, self.cls_token, self.mask_token) == ("[UNK]", "[SEP]", "[PAD]", "[CLS]", "[MASK]")
+            try:
+                import os
+                from . import _lib as L
+                table = os.path.join(os.path.dirname(L.LIB_PATH), "unicode_bmp.bin")
+                if defaults and os.path.exists(L.LIB_PATH) and os.path.exists(table):
+                    h = L.lib().clipk_wp_create(self.vocab_file.encode(), table.encode(), int(self.do_lower_case))
+                    if h:
+                        self._native = h
+            except Exception:
+                self._native = False
+        return self._native
+
+    def encode_native(self, texts, max_length):
+        """(ids [n, L] int64, mask [n, L] int64, status [n]) from the native encoder, or None when it is unavailable"""
+        h = self._native_handle()
+        if not h:
+            return None
+        import ctypes as C
+        import numpy as np
+        from . import _lib as L
+        n = len(texts)
+        ids = np.zeros((n, max_length), dtype=np.int64); mask = np.zeros((n, max_length), dtype=np.int64); status = np.zeros(n, dtype=np.int32)
+        arr = (C.c_char_p * n)(*[t.encode("utf-8", "surrogatepass") if isinstance(t, str) else t for t in texts])
+        rc = L.lib().clipk_wp_encode_batch(C.c_void_p(h), arr, n, int(max_length), ids.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p),
+                                           status.ctypes.data_as(C.c_void_p), int(self.native_threads))
+        if rc != 0:
+            return None
+        return ids, mask, status
 
     @classmethod
     def from_pretrained(cls, path, **kwargs):
@@ -135,6 +177,28 @@ class BertTokenizer:
         if isinstance(texts, str):
             texts = [texts]
         cls_id, sep_id, pad_id = self.vocab[self.cls_token], self.vocab[self.sep_token], self.vocab.get(self.pad_token, 0)
+        if padding == "max_length" and truncation and max_length >= 2 and all(isinstance(t, str) and "\x00" not in t for t in texts):
+            nat = self.encode_native(texts, max_length)
+            if nat is not None:
+                ids_np, mask_np, status = nat
+                for i, t in enumerate(texts):
+                    if status[i] < 0:                      # code point outside the native tables: the Python restatement takes this text
+                        one = self._encode_python([t], padding, truncation, max_length, cls_id, sep_id, pad_id)
+                        ids_np[i] = one[0][0]; mask_np[i] = one[1][0]
+                        self.native_stats["fallback"] += 1
+                    else:
+                        self.native_stats["native"] += 1
+                if return_tensors == "pt":
+                    return {"input_ids": torch.from_numpy(ids_np.copy()), "token_type_ids": torch.zeros(len(texts), max_length, dtype=torch.long),
+                            "attention_mask": torch.from_numpy(mask_np.copy())}
+                return {"input_ids": ids_np.tolist(), "token_type_ids": [[0] * max_length for _ in texts], "attention_mask": mask_np.tolist()}
+        ids_all, mask_all = self._encode_python(texts, padding, truncation, max_length, cls_id, sep_id, pad_id)
+        if return_tensors == "pt":
+            return {"input_ids": torch.tensor(ids_all, dtype=torch.long), "token_type_ids": torch.zeros(len(ids_all), len(ids_all[0]), dtype=torch.long),
+                    "attention_mask": torch.tensor(mask_all, dtype=torch.long)}
+        return {"input_ids": ids_all, "token_type_ids": [[0] * len(x) for x in ids_all], "attention_mask": mask_all}
+
+    def _encode_python(self, texts, padding, truncation, max_length, cls_id, sep_id, pad_id):
         ids_all, mask_all = [], []
         for t in texts:
             ids = self.convert_tokens_to_ids(self.tokenize(t))
@@ -146,7 +210,4 @@ class BertTokenizer:
                 pad = max_length - len(ids)
                 ids = ids + [pad_id] * pad; mask = mask + [0] * pad
             ids_all.append(ids); mask_all.append(mask)
-        if return_tensors == "pt":
-            return {"input_ids": torch.tensor(ids_all, dtype=torch.long), "token_type_ids": torch.zeros(len(ids_all), len(ids_all[0]), dtype=torch.long),
-                    "attention_mask": torch.tensor(mask_all, dtype=torch.long)}
-        return {"input_ids": ids_all, "token_type_ids": [[0] * len(x) for x in ids_all], "attention_mask": mask_all}
+        return ids_all, mask_all

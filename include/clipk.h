@@ -258,6 +258,19 @@ int clipk_peer_wait(const unsigned int* my_flags, int world, int channel, unsign
 /* out[r, :] (+)= sum over peers p of src_ptrs[p][(rank * rows + r), :]: reduce-scatter of the gallery gradients by peer loads */
 int clipk_peer_reduce_rows(float* const* src_ptrs, int world, int rank, float* out, int rows, int d, int accumulate, cudaStream_t stream);
 
+/* -------------------------------------------------------------------------------------------- native WordPiece (host code)
+ * BertTokenizer of the reference (modelzoo/models/bert/tokenization_bert.py:67-504) for the call the CLIP application makes
+ * (appzoo/clip/data.py:262-264): [CLS] + wordpieces (truncated to max_length - 2) + [SEP] + [PAD]s, attention mask 1/0.
+ * unicode_table_path: the table written by tools/gen_unicode_table.py (Python unicodedata predicates for the BMP).
+ * encode returns the number of non-padding positions, CLIPK_WP_FALLBACK when the text holds a code point outside the supported set
+ * (the caller tokenizes that text with the Python restatement), or a negative CLIPK_ERR_*.  HOST pointers throughout.          */
+#define CLIPK_WP_FALLBACK (-100)
+void* clipk_wp_create(const char* vocab_path, const char* unicode_table_path, int do_lower_case);
+void clipk_wp_destroy(void* handle);
+int clipk_wp_encode(void* handle, const char* utf8_text, int max_length, long long* host_input_ids, long long* host_attention_mask);
+int clipk_wp_encode_batch(void* handle, const char* const* utf8_texts, int n, int max_length, long long* host_input_ids,
+                          long long* host_attention_mask, int* host_status, int threads);
+
 /* counter_dev[0] += value on the stream: the device-resident dropout stream position (one per training forward pass, so that a
  * replayed CUDA graph and every micro-batch of a gradient-accumulation window draw fresh nn.Dropout masks, modeling_bert.py:128,238) */
 int clipk_counter_add(int* counter_dev, int value, cudaStream_t stream);
