@@ -87,6 +87,7 @@ def _declare(L):
     L.clipk_attention_causal_fwd.argtypes = [vp, vp, vp, i, i, i, i, vp]
     L.clipk_attention_causal_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
     L.clipk_argmax_rows.argtypes = [vp, vp, i, i, vp]
+    L.clipk_find_token_rows.argtypes = [vp, ll, vp, vp, i, i, vp]
     L.clipk_gather_rows_bf16.argtypes = [vp, vp, vp, i, i, i, vp]
     L.clipk_scatter_rows_f32.argtypes = [vp, vp, vp, i, i, i, vp]
     L.clipk_frame_pool_fwd.argtypes = [vp, vp, vp, i, i, i, vp]

@@ -1,7 +1,7 @@
 """AppZoo registry for the applications on the hot path -- same call signatures as easynlp/appzoo/api.py:281-468 (prefix match on
 app_name in the reference's dictionary order: 'clip4clip' before 'clip'; NotImplementedError for unknown apps, extra kwargs tolerated).
-'clip' is complete (model, dataset, evaluator, predictor); 'clip4clip' (Text2VideoRetrieval, a sibling app sharing the encoders) registers
-its model."""
+'clip' and 'wukong_clip' are complete (model, dataset, evaluator, predictor); 'clip4clip' (Text2VideoRetrieval, a sibling app sharing the
+encoders) registers its model."""
 
 
 def _clip_classes():
@@ -12,18 +12,28 @@ def _clip_classes():
     return CLIPApp, CLIPEvaluator, CLIPPredictor, CLIPDataset
 
 
-def _match(app_name):
+def _wukong_classes():
+    from .wukong_clip.model import WukongCLIP
+    from .wukong_clip.evaluator import WukongCLIPEvaluator
+    from .wukong_clip.predictor import WukongCLIPPredictor
+    from .wukong_clip.data import WukongCLIPDataset
+    return WukongCLIP, WukongCLIPEvaluator, WukongCLIPPredictor, WukongCLIPDataset
+
+
+def _classes(app_name):
+    """(model, evaluator, predictor, dataset) classes of a fully registered application"""
+    if app_name is not None and app_name.startswith("wukong_clip"):
+        return _wukong_classes()
     if app_name is not None and app_name.startswith("clip") and not app_name.startswith("clip4clip"):
-        return True
-    raise NotImplementedError(f"application {app_name!r} is outside the B200 hot path (only 'clip' is registered)")
+        return _clip_classes()
+    raise NotImplementedError(f"application {app_name!r} is outside the B200 hot path (registered: 'clip', 'wukong_clip', model of 'clip4clip')")
 
 
 def _model_cls(app_name):
     if app_name is not None and app_name.startswith("clip4clip"):
         from .text2video_retrieval.model import Text2VideoRetrieval
         return Text2VideoRetrieval
-    _match(app_name)
-    return _clip_classes()[0]
+    return _classes(app_name)[0]
 
 
 def get_application_model(app_name, pretrained_model_name_or_path, user_defined_parameters=None, **kwargs):
@@ -35,17 +45,14 @@ def get_application_model_for_evaluation(app_name, pretrained_model_name_or_path
 
 
 def get_application_evaluator(app_name, valid_dataset, user_defined_parameters=None, **kwargs):
-    _match(app_name)
-    return _clip_classes()[1](valid_dataset=valid_dataset, user_defined_parameters=user_defined_parameters, **kwargs)
+    return _classes(app_name)[1](valid_dataset=valid_dataset, user_defined_parameters=user_defined_parameters, **kwargs)
 
 
 def get_application_predictor(app_name, model_dir, user_defined_parameters=None, **kwargs):
-    _match(app_name)
-    cls = _clip_classes()
+    cls = _classes(app_name)
     return cls[2](model_dir=model_dir, model_cls=cls[0], user_defined_parameters=user_defined_parameters, **kwargs)
 
 
 def get_application_dataset(app_name, pretrained_model_name_or_path, data_file, max_seq_length, user_defined_parameters=None, **kwargs):
-    _match(app_name)
-    return _clip_classes()[3](pretrained_model_name_or_path=pretrained_model_name_or_path, data_file=data_file,
-                              max_seq_length=max_seq_length, user_defined_parameters=user_defined_parameters, **kwargs)
+    return _classes(app_name)[3](pretrained_model_name_or_path=pretrained_model_name_or_path, data_file=data_file,
+                                 max_seq_length=max_seq_length, user_defined_parameters=user_defined_parameters, **kwargs)

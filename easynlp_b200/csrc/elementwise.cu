@@ -354,6 +354,20 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const long long* __res
   }
   if (lane == 0) idx[b] = bi;
 }
+// idx[b] = first l with ids[b, l] == token (0 when there is none), count[b] (optional) = number of matches: Wukong's TextTransformer pools
+// the [SEP] position, `x[(ids == 102).nonzero()]` (modeling_wukong.py:349,359), which needs exactly one per sequence.  One warp per sequence.
+__global__ void __launch_bounds__(256) find_token_rows_kernel(const long long* __restrict__ ids, long long token, int* __restrict__ idx,
+                                                              int* __restrict__ count, int B, int L) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  int first = INT_MAX, n = 0;
+  for (int l = lane; l < L; l += 32)
+    if (ids[(long long)b * L + l] == token) { first = min(first, l); ++n; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { first = min(first, __shfl_xor_sync(0xffffffffu, first, o)); n += __shfl_xor_sync(0xffffffffu, n, o); }
+  if (lane == 0) { idx[b] = first == INT_MAX ? 0 : first; if (count) count[b] = n; }
+}
 // out[b, :] = x[b * L + idx[b], :] (bf16 rows) ; dst[b * L + idx[b], :] = src[b, :] (f32 rows; dst zero-filled by the caller)
 __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const bf16* __restrict__ x, const int* __restrict__ idx, bf16* __restrict__ out, int B, int L, int W) {
   const int b = blockIdx.x;
@@ -633,6 +647,13 @@ extern "C" int clipk_embed_gather_bwd(const long long* ids, const int* pos_ids, 
 extern "C" int clipk_argmax_rows(const long long* ids, int* idx, int B, int L, cudaStream_t stream) {
   if (B <= 0 || L <= 0) return 0;
   argmax_rows_kernel<<<(B + 7) / 8, 256, 0, stream>>>(ids, idx, B, L);
+  note_launch();
+  CLIPK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int clipk_find_token_rows(const long long* ids, long long token, int* idx, int* count, int B, int L, cudaStream_t stream) {
+  if (B <= 0 || L <= 0) return 0;
+  find_token_rows_kernel<<<(B + 7) / 8, 256, 0, stream>>>(ids, token, idx, count, B, L);
   note_launch();
   CLIPK_CUDA(cudaGetLastError());
   return 0;

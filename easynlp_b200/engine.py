@@ -59,6 +59,19 @@ def hf_engine_config(raw: dict, embed_dim: int) -> dict:
                 text_initializer_range=t.get("initializer_range", 0.02))
 
 
+def wukong_engine_config(raw: dict) -> dict:
+    """flat engine config from a Wukong `config.json` ({"model": {"visual": {...}, "text": {...}}}: the constructor arguments of
+    VisualTransformer / TextTransformer, modeling_wukong.py:269-277,312-319; appzoo/wukong_clip/model.py:51-55)"""
+    v = raw["model"]["visual"]; t = raw["model"]["text"]
+    if v["heads"] * 64 != v["width"] or t["heads"] * 64 != t["width"]:
+        raise NotImplementedError("clipk attention needs head_dim 64 in both Wukong towers")
+    if v["output_dim"] != t["output_dim"]:
+        raise ValueError("Wukong towers must project to the same output_dim")
+    return dict(model_type="wukong", embed_dim=v["output_dim"], image_resolution=v["input_resolution"], vision_layers=v["layers"],
+                vision_width=v["width"], vision_patch_size=v["patch_size"], vocab_size=t["vocab_size"], context_length=t["context_length"],
+                transformer_width=t["width"], transformer_heads=t["heads"], transformer_layers=t["layers"])
+
+
 class ClipEngine:
     def __init__(self, cfg: dict, device="cuda", with_optimizer_state: bool = True):
         if isinstance(cfg.get("vision_layers"), (tuple, list)):
@@ -66,8 +79,9 @@ class ClipEngine:
         self.cfg = cfg
         self.kind = cfg.get("model_type", "chinese_clip")
         self.hf = self.kind == "huggingface_clip"
-        self.oc = self.kind == "open_clip"
-        if self.kind not in ("chinese_clip", "huggingface_clip", "open_clip"):
+        self.wk = self.kind == "wukong"
+        self.oc = self.kind in ("open_clip", "wukong")          # pre-LN causal text transformer (OPEN_CLIP; Wukong's TextTransformer)
+        if self.kind not in ("chinese_clip", "huggingface_clip", "open_clip", "wukong"):
             raise NotImplementedError(f"model_type {self.kind!r}")
         if self.oc:      # OPEN_CLIP ctor arguments (modeling_openclip.py:256-271) -> the text-tower keys this engine uses
             cfg = dict(cfg, text_hidden_size=cfg["transformer_width"], text_intermediate_size=4 * cfg["transformer_width"],
@@ -87,8 +101,6 @@ class ClipEngine:
             raise NotImplementedError("clipk attention needs head_dim 64 in the vision tower")
         self.kdim = 3 * self.P * self.P
         self.kdim_pad = (self.kdim + 7) // 8 * 8                 # ViT-L/14: 588 -> 592 (TMA rows are 16-byte multiples)
-        if self.kdim_pad != self.kdim and not self.hf:
-            raise NotImplementedError("patch dim 3*P*P % 8 != 0 is supported for frozen (forward-only) image towers only")
         if cfg.get("text_hidden_act", "gelu") != "gelu":
             raise NotImplementedError("text tower activation must be erf-GELU")
         self.vit_act = L.EPI_QUICK_GELU
@@ -98,6 +110,9 @@ class ClipEngine:
                 raise NotImplementedError(f"vision hidden_act {va!r}")
             self.vit_act = L.EPI_QUICK_GELU if va == "quick_gelu" else L.EPI_ERF_GELU
         self.text_eps = float(cfg.get("text_layer_norm_eps", 1e-12))   # modeling_chineseclip.py:311 / CLIPTextConfig.layer_norm_eps
+        # eps of the pre-LN blocks: nn.LayerNorm default 1e-5 (modeling_chineseclip.py:170-176, modeling_openclip.py:108-121),
+        # CLIPVisionConfig.layer_norm_eps (configuration_clip.py:211), 1e-7 in the Wukong towers (modeling_wukong.py:242-248,284-288,329)
+        self.ln_eps = float(cfg.get("vision_layer_norm_eps", 1e-5)) if self.hf else (1e-7 if self.wk else 1e-5)
         self.pad_id = int(cfg.get("text_pad_token_id", 0))
         # parameter names of the two branches
         if self.hf:
@@ -108,14 +123,19 @@ class ClipEngine:
                        "qkv_b": "self_attn.q_proj.bias", "out": "self_attn.out_proj", "fc1": "mlp.fc1", "fc2": "mlp.fc2"}
             self.tp = "text_encoder."
         else:
-            self.vn = {"conv": "visual.conv1.weight", "cls": "visual.class_embedding", "pos": "visual.positional_embedding",
-                       "ln_pre": "visual.ln_pre", "ln_post": "visual.ln_post", "layer": "visual.transformer.resblocks.{}.", "ln1": "ln_1",
+            v = "visual_encoder." if self.wk else "visual."
+            self.vn = {"conv": v + "conv1.weight", "cls": v + "class_embedding", "pos": v + "positional_embedding",
+                       "ln_pre": v + "ln_pre", "ln_post": v + "ln_post", "layer": v + "transformer.resblocks.{}.", "ln1": "ln_1",
                        "ln2": "ln_2", "qkv_w": "attn.in_proj_weight", "qkv_b": "attn.in_proj_bias", "out": "attn.out_proj",
-                       "fc1": "mlp.c_fc", "fc2": "mlp.c_proj"}
+                       "fc1": "mlp.c_fc", "fc2": "mlp.c_proj", "proj": v + "proj"}
             self.tp = "bert."
-        # OPEN_CLIP's text tower: the same residual block as the ViT, under `transformer.resblocks.{i}.` (modeling_openclip.py:296-301)
-        self.on = {"layer": "transformer.resblocks.{}.", "ln1": "ln_1", "ln2": "ln_2", "qkv_w": "attn.in_proj_weight", "qkv_b": "attn.in_proj_bias",
-                   "out": "attn.out_proj", "fc1": "mlp.c_fc", "fc2": "mlp.c_proj"}
+        # OPEN_CLIP's text tower: the same residual block as the ViT, under `transformer.resblocks.{i}.` (modeling_openclip.py:296-301);
+        # Wukong's TextTransformer keeps it under `text_encoder.` with an `embedding_table` parameter (modeling_wukong.py:311-336)
+        t = "text_encoder." if self.wk else ""
+        self.on = {"layer": t + "transformer.resblocks.{}.", "ln1": "ln_1", "ln2": "ln_2", "qkv_w": "attn.in_proj_weight", "qkv_b": "attn.in_proj_bias",
+                   "out": "attn.out_proj", "fc1": "mlp.c_fc", "fc2": "mlp.c_proj", "tok": t + ("embedding_table" if self.wk else "token_embedding.weight"),
+                   "pos": t + "positional_embedding", "ln_final": t + "ln_final", "proj": t + "text_projection"}
+        self.sep_id = int(cfg.get("sep_token_id", 102))          # Wukong pools the [SEP] position: `(x == 102).nonzero()` (modeling_wukong.py:349)
         self.params = ParamStore(cfg, device, with_optimizer_state)
         self._buf: Dict[tuple, torch.Tensor] = {}
         self._saved = None
@@ -179,10 +199,10 @@ class ClipEngine:
             ly["h"] = self.bf(tag + "h", M, W); ly["m1"] = self.f32(tag + "m1", M); ly["r1"] = self.f32(tag + "r1", M)
             g1, b1 = P_.p(p + nm["ln1"] + ".weight"), P_.p(p + nm["ln1"] + ".bias")
             if pending is None:
-                ops.layernorm_fwd(x, g1, b1, 1e-5, ly["h"], None, ly["m1"], ly["r1"])
+                ops.layernorm_fwd(x, g1, b1, self.ln_eps, ly["h"], None, ly["m1"], ly["r1"])
             else:       # x = x1_prev + c_proj(...) of the previous block
                 x_new = self.f32(f"{tg}x.{i}" if save else f"{tg}x.t{i % 2}", M, W)
-                ops.layernorm_fwd(pending, g1, b1, 1e-5, ly["h"], None, ly["m1"], ly["r1"], add=ybr, x_out=x_new)
+                ops.layernorm_fwd(pending, g1, b1, self.ln_eps, ly["h"], None, ly["m1"], ly["r1"], add=ybr, x_out=x_new)
                 x = x_new
             ly["x_in"] = x
             ly["qkv"] = self.bf(tag + "qkv", M, 3 * W)
@@ -192,7 +212,7 @@ class ClipEngine:
             ops.gemm(ly["ctx"], P_.w(p + nm["out"] + ".weight"), ybr, bias=P_.p(p + nm["out"] + ".bias"))
             ly["x1"] = self.f32(tag + "x1", M, W)
             ly["h2"] = self.bf(tag + "h2", M, W); ly["m2"] = self.f32(tag + "m2", M); ly["r2"] = self.f32(tag + "r2", M)
-            ops.layernorm_fwd(x, P_.p(p + nm["ln2"] + ".weight"), P_.p(p + nm["ln2"] + ".bias"), 1e-5, ly["h2"], None, ly["m2"], ly["r2"],
+            ops.layernorm_fwd(x, P_.p(p + nm["ln2"] + ".weight"), P_.p(p + nm["ln2"] + ".bias"), self.ln_eps, ly["h2"], None, ly["m2"], ly["r2"],
                               add=ybr, x_out=ly["x1"])
             # "z" holds act'(z) (the activation's derivative) saved for backward, "a" the activation
             ly["z"] = self.bf(tag + "z", M, I); ly["a"] = self.bf(tag + "a", M, I)
@@ -262,7 +282,7 @@ class ClipEngine:
         ops.vit_assemble(patch_out, P_.p(vn["cls"]), P_.p(vn["pos"]), x0, B, Lv, W)
         x = self.f32("v.x.0", M, W)
         st = {"B": B, "mean0": self.f32("v.mean0", M), "rstd0": self.f32("v.rstd0", M), "layers": []}
-        ops.layernorm_fwd(x0, P_.p(vn["ln_pre"] + ".weight"), P_.p(vn["ln_pre"] + ".bias"), 1e-5, None, x, st["mean0"], st["rstd0"])
+        ops.layernorm_fwd(x0, P_.p(vn["ln_pre"] + ".weight"), P_.p(vn["ln_pre"] + ".bias"), self.ln_eps, None, x, st["mean0"], st["rstd0"])
         layers, pending, x, ybr = self._blocks_forward(x, vn, self.nv, B, Lv, W, Iv, Hh, save, "v.", self.vit_act, causal=False)
         st["layers"] = layers
         # ln_post on the CLS rows of x_final = x1_last + c_proj(...): the add is fused here too; x_cls [B, W] is kept for backward
@@ -270,16 +290,16 @@ class ClipEngine:
         st["pooled"] = self.bf("v.pooled", B, W); st["mp"] = self.f32("v.mp", B); st["rp"] = self.f32("v.rp", B)
         gp, bp = P_.p(vn["ln_post"] + ".weight"), P_.p(vn["ln_post"] + ".bias")
         if pending is None:      # zero-layer tower (degenerate configs): no pending residual
-            ops.layernorm_fwd(x, gp, bp, 1e-5, st["pooled"], None, st["mp"], st["rp"], rows=B, ldx=Lv * W)
+            ops.layernorm_fwd(x, gp, bp, self.ln_eps, st["pooled"], None, st["mp"], st["rp"], rows=B, ldx=Lv * W)
             st["x_cls"] = None; st["x_final"] = x
         else:
-            ops.layernorm_fwd(pending, gp, bp, 1e-5, st["pooled"], None, st["mp"], st["rp"],
+            ops.layernorm_fwd(pending, gp, bp, self.ln_eps, st["pooled"], None, st["mp"], st["rp"],
                               rows=B, ldx=Lv * W, add=ybr, ldadd=Lv * W, x_out=st["x_cls"])
         st["feat"] = self.f32("v.feat", B, self.E)
         if self.hf:   # image_embeds = vision_projection(pooled.detach())  (appzoo/clip/model.py:142-143)
             ops.gemm(st["pooled"], P_.w("vision_projection.weight"), st["feat"], bias=P_.p("vision_projection.bias"))
         else:
-            ops.gemm(st["pooled"], P_.w("visual.proj"), st["feat"], b_mn_major=1)
+            ops.gemm(st["pooled"], P_.w(vn["proj"]), st["feat"], b_mn_major=1)
         st["embeds"] = self.f32("v.embeds", B, self.E); st["norm"] = self.f32("v.norm", B)
         if self._peer_on:      # fused normalise + all-gather: the embeddings land in every rank's image gallery (csrc/peer.cu)
             self._peer.l2norm_allgather(st["feat"], st["embeds"], st["norm"], "image")
@@ -303,9 +323,9 @@ class ClipEngine:
         dfeat_b = self.bf("v.dfeat_b", B, E)
         ops.l2norm_bwd(d_embeds, st["embeds"], st["norm"], None, dfeat_b, B, E)
         # d proj[W,E] += pooled^T dfeat ; dpooled = dfeat proj^T
-        ops.gemm(st["pooled"], dfeat_b, P_.g("visual.proj"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
+        ops.gemm(st["pooled"], dfeat_b, P_.g(vn["proj"]), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
         dpooled = self.f32("v.dpooled", B, W)
-        ops.gemm(dfeat_b, P_.w("visual.proj"), dpooled)
+        ops.gemm(dfeat_b, P_.w(vn["proj"]), dpooled)
         dX = self.f32("v.dX.a", M, W); dXb = self.bf("v.dXb.a", M, W)
         dX.zero_()
         last = st["layers"][-1] if self.nv else None
@@ -325,8 +345,14 @@ class ClipEngine:
         npatch = B * self.g * self.g; kdim = 3 * self.P * self.P
         dpatch = self.bf("v.dpatch", npatch, W)
         ops.vit_assemble_bwd(dx0, dpatch, B, Lv, W)
-        ops.gemm(dpatch, self.zbuf("v.patches", (npatch, self.kdim_pad), torch.bfloat16), P_.g(vn["conv"], (W, kdim)), a_mn_major=1, b_mn_major=1,
-                 mode=L.EPI_ATOMIC_ADD, splits=_splits_for(W, kdim, npatch))
+        patches = self.zbuf("v.patches", (npatch, self.kdim_pad), torch.bfloat16)
+        if self.kdim_pad == kdim:
+            ops.gemm(dpatch, patches, P_.g(vn["conv"], (W, kdim)), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD, splits=_splits_for(W, kdim, npatch))
+        else:       # ViT-*/14: the operand rows are padded 588 -> 592; the weight gradient goes through a padded scratch tile
+            dpad = self.f32("v.dconv_pad", W, self.kdim_pad)
+            dpad.zero_()
+            ops.gemm(dpatch, patches, dpad, a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD, splits=_splits_for(W, self.kdim_pad, npatch))
+            P_.g(vn["conv"], (W, kdim)).add_(dpad[:, :kdim])
 
     # ------------------------------------------------------------------ BERT
     def _drop(self, train: bool, p: float, site: int):
@@ -352,22 +378,25 @@ class ClipEngine:
         st["pos_ids"].copy_(torch.arange(Lt, device=self.dev, dtype=torch.int32).expand(B, Lt))
         ztype = self.zbuf("o.ztype", (1, W), torch.float32)                       # no token-type table on this tower
         x = self.f32("o.x.0", M, W)
-        ops.embed_gather(ids, st["pos_ids"], None, None, P_.p("token_embedding.weight"), P_.p("positional_embedding"), ztype, x, None, -1)
+        ops.embed_gather(ids, st["pos_ids"], None, None, P_.p(self.on["tok"]), P_.p(self.on["pos"]), ztype, x, None, -1)
         layers, pending, x, ybr = self._blocks_forward(x, self.on, self.nt, B, Lt, W, 4 * W, Hh, save, "o.", L.EPI_QUICK_GELU, causal=True)
         st["layers"] = layers
         # ln_final on every row of x_final = x1_last + c_proj(...), then the EOT rows are gathered for the projection
         st["x_fin"] = self.f32("o.x_fin", M, W); st["hf"] = self.bf("o.hfin", M, W); st["mf"] = self.f32("o.mf", M); st["rf"] = self.f32("o.rf", M)
-        g, b = P_.p("ln_final.weight"), P_.p("ln_final.bias")
+        g, b = P_.p(self.on["ln_final"] + ".weight"), P_.p(self.on["ln_final"] + ".bias")
         if pending is None:
-            ops.layernorm_fwd(x, g, b, 1e-5, st["hf"], None, st["mf"], st["rf"]); st["x_fin"] = x
+            ops.layernorm_fwd(x, g, b, self.ln_eps, st["hf"], None, st["mf"], st["rf"]); st["x_fin"] = x
         else:
-            ops.layernorm_fwd(pending, g, b, 1e-5, st["hf"], None, st["mf"], st["rf"], add=ybr, x_out=st["x_fin"])
+            ops.layernorm_fwd(pending, g, b, self.ln_eps, st["hf"], None, st["mf"], st["rf"], add=ybr, x_out=st["x_fin"])
         st["eot"] = self.buf("o.eot", (B,), torch.int32)
-        ops.argmax_rows(ids, st["eot"])
+        if self.wk:
+            ops.find_token_rows(ids, self.sep_id, st["eot"])       # exactly one [SEP] per text (WukongCLIPDataset.tokenize, data.py:180-187)
+        else:
+            ops.argmax_rows(ids, st["eot"])
         st["pooled"] = self.bf("o.pooled", B, W)
         ops.gather_rows_bf16(st["hf"], st["eot"], st["pooled"], B, Lt, W)
         st["feat"] = self.f32("t.feat", B, self.E)
-        ops.gemm(st["pooled"], P_.w("text_projection"), st["feat"], b_mn_major=1)
+        ops.gemm(st["pooled"], P_.w(self.on["proj"]), st["feat"], b_mn_major=1)
         st["embeds"] = self.f32("t.embeds", B, self.E); st["norm"] = self.f32("t.norm", B)
         if self._peer_on:
             self._peer.l2norm_allgather(st["feat"], st["embeds"], st["norm"], "text")
@@ -379,20 +408,20 @@ class ClipEngine:
         P_ = self.params; W = self.H; B = st["B"]; Lt = st["Lt"]; M = B * Lt; Hh = self.Ht; E = self.E
         dfeat_b = self.bf("t.dfeat_b", B, E)
         ops.l2norm_bwd(d_embeds, st["embeds"], st["norm"], None, dfeat_b, B, E)
-        ops.gemm(st["pooled"], dfeat_b, P_.g("text_projection"), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
+        ops.gemm(st["pooled"], dfeat_b, P_.g(self.on["proj"]), a_mn_major=1, b_mn_major=1, mode=L.EPI_ATOMIC_ADD)
         dpooled = self.f32("o.dpooled", B, W)
-        ops.gemm(dfeat_b, P_.w("text_projection"), dpooled)
+        ops.gemm(dfeat_b, P_.w(self.on["proj"]), dpooled)
         dhf = self.f32("o.dhf", M, W)
         dhf.zero_()
         ops.scatter_rows_f32(dpooled, st["eot"], dhf, B, Lt, W)                    # only the EOT rows carry a gradient into ln_final
         dX = self.f32("o.dX.a", M, W); dXb = self.bf("o.dXb.a", M, W)
         bias_prev = P_.g(self.on["layer"].format(self.nt - 1) + self.on["fc2"] + ".bias") if self.nt else None
-        ops.layernorm_bwd(dhf, st["x_fin"], P_.p("ln_final.weight"), st["mf"], st["rf"], dx_f32=dX, dx_bf16=dXb,
-                          dgamma=P_.g("ln_final.weight"), dbeta=P_.g("ln_final.bias"), dbias=bias_prev)
+        ops.layernorm_bwd(dhf, st["x_fin"], P_.p(self.on["ln_final"] + ".weight"), st["mf"], st["rf"], dx_f32=dX, dx_bf16=dXb,
+                          dgamma=P_.g(self.on["ln_final"] + ".weight"), dbeta=P_.g(self.on["ln_final"] + ".bias"), dbias=bias_prev)
         dX = self._blocks_backward(st["layers"], dX, dXb, self.on, self.nt, B, Lt, W, 4 * W, Hh, "o.", causal=True)
         ztype_g = self.zbuf("o.ztype_g", (1, W), torch.float32)
-        ops.embed_gather_bwd(st["ids"], st["pos_ids"], None, dX, P_.g("token_embedding.weight"), P_.g("positional_embedding"), ztype_g, -1)
-        self._grads_ready("token_embedding."); self._grads_ready("positional_embedding"); self._grads_ready("ln_final.")
+        ops.embed_gather_bwd(st["ids"], st["pos_ids"], None, dX, P_.g(self.on["tok"]), P_.g(self.on["pos"]), ztype_g, -1)
+        self._grads_ready(self.on["tok"]); self._grads_ready(self.on["pos"]); self._grads_ready(self.on["ln_final"] + ".")
 
     def bert_forward(self, ids: torch.Tensor, save: bool, train: bool = False, token_type_ids=None, attention_mask=None):
         """BertModel (chinese_clip: mask = ids != 0, modeling_chineseclip.py:347-349) or RobertaModel (huggingface_clip: pad-aware

@@ -245,6 +245,13 @@ def argmax_rows(ids, idx):
 
 
 @_op
+def find_token_rows(ids, token, idx, count=None):
+    B, Lt = ids.shape
+    assert idx.dtype == torch.int32 and idx.numel() == B and (count is None or (count.dtype == torch.int32 and count.numel() == B))
+    L_.check(L_.lib().clipk_find_token_rows(_i64(ids), int(token), _ptr(idx), _ptr(count), B, Lt, _stream()), "find_token_rows")
+
+
+@_op
 def gather_rows_bf16(x, idx, out, B, Lt, W):
     L_.check(L_.lib().clipk_gather_rows_bf16(_b16(x), _ptr(idx), _b16(out), B, Lt, W, _stream()), "gather_rows_bf16")
 

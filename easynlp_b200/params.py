@@ -140,6 +140,38 @@ def openclip_param_schema(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
     return s
 
 
+def wukong_param_schema(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
+    """(name -> shape) of WukongModel (modelzoo/models/wukong/modeling_wukong.py:268-289,311-336,363-380) without the `model.` prefix
+    the application's state dict carries (appzoo/wukong_clip/model.py:55): a VisualTransformer under `visual_encoder.*` and a causal
+    pre-LN TextTransformer under `text_encoder.*` whose token table is the bare parameter `embedding_table`."""
+    W = cfg["vision_width"]; P = cfg["vision_patch_size"]; E = cfg["embed_dim"]
+    n_tok = (cfg["image_resolution"] // P) ** 2 + 1
+    Wt = cfg["transformer_width"]; Lc = cfg["context_length"]
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    s["logit_scale"] = ()
+    v = "visual_encoder."; t = "text_encoder."
+    s[v + "class_embedding"] = (W,)
+    s[v + "positional_embedding"] = (n_tok, W)
+    s[v + "proj"] = (W, E)
+    s[v + "conv1.weight"] = (W, 3, P, P)
+    s[v + "ln_pre.weight"] = (W,); s[v + "ln_pre.bias"] = (W,)
+    for pre, n, w in ((v + "transformer.resblocks.", cfg["vision_layers"], W), (t + "transformer.resblocks.", cfg["transformer_layers"], Wt)):
+        for i in range(n):
+            p = f"{pre}{i}."
+            s[p + "attn.in_proj_weight"] = (3 * w, w); s[p + "attn.in_proj_bias"] = (3 * w,)
+            s[p + "attn.out_proj.weight"] = (w, w); s[p + "attn.out_proj.bias"] = (w,)
+            s[p + "ln_1.weight"] = (w,); s[p + "ln_1.bias"] = (w,)
+            s[p + "mlp.c_fc.weight"] = (4 * w, w); s[p + "mlp.c_fc.bias"] = (4 * w,)
+            s[p + "mlp.c_proj.weight"] = (w, 4 * w); s[p + "mlp.c_proj.bias"] = (w,)
+            s[p + "ln_2.weight"] = (w,); s[p + "ln_2.bias"] = (w,)
+    s[v + "ln_post.weight"] = (W,); s[v + "ln_post.bias"] = (W,)
+    s[t + "text_projection"] = (Wt, E)
+    s[t + "ln_final.weight"] = (Wt,); s[t + "ln_final.bias"] = (Wt,)
+    s[t + "embedding_table"] = (cfg["vocab_size"], Wt)
+    s[t + "positional_embedding"] = (Lc, Wt)
+    return s
+
+
 # the pooler is computed-but-unused by chinese_clip (modeling_chineseclip.py:349 takes [0]); its parameters never get a
 # gradient, so the reference optimizer skips them (optimizers.py:420-421) -- they sit outside the updated range.
 NO_GRAD = ("bert.pooler.dense.weight", "bert.pooler.dense.bias")
@@ -166,14 +198,14 @@ class ParamStore:
             self.no_grad = tuple(n for n in self.schema if n.startswith("vision_encoder."))
             self.buffers = {"text_encoder.embeddings.position_ids": cfg["text_max_position_embeddings"],
                             "vision_encoder.vision_model.embeddings.position_ids": (cfg["image_resolution"] // cfg["vision_patch_size"]) ** 2 + 1}
-        elif self.kind == "open_clip":
-            self.schema = openclip_param_schema(cfg)
+        elif self.kind in ("open_clip", "wukong"):
+            self.schema = openclip_param_schema(cfg) if self.kind == "open_clip" else wukong_param_schema(cfg)
             self.no_grad = ()
             self.buffers = {}
         else:
             self.schema = param_schema(cfg)
             self.no_grad = NO_GRAD
-        if self.kind not in ("huggingface_clip", "open_clip"):
+        if self.kind not in ("huggingface_clip", "open_clip", "wukong"):
             # buffer exported by the reference BertEmbeddings (modeling_bert.py:87)
             self.buffers = {"bert.embeddings.position_ids": cfg["text_max_position_embeddings"]}
         NO_GRAD_ = set(self.no_grad)

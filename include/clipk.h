@@ -166,6 +166,9 @@ int clipk_embed_gather_bwd(const long long* ids, const int* pos_ids, const long 
 /* EOT pooling of OPEN_CLIP.encode_text (modeling_openclip.py:367-369: x[arange(B), text.argmax(-1)]): idx[b] = first argmax of ids[b, :];
  * out[b, :] = x[b*L + idx[b], :] (bf16 rows, W % 8 == 0); backward: dst[b*L + idx[b], :] = src[b, :] into a zero-filled fp32 [B*L, W] */
 int clipk_argmax_rows(const long long* ids, int* idx, int B, int L, cudaStream_t stream);
+/* [SEP] pooling of Wukong's TextTransformer (modelzoo/models/wukong/modeling_wukong.py:349,359: x[(ids == 102).nonzero()]): idx[b] = first
+ * position of `token` in ids[b, :] (0 when absent), count[b] (optional) = number of occurrences */
+int clipk_find_token_rows(const long long* ids, long long token, int* idx, int* count /* optional */, int B, int L, cudaStream_t stream);
 int clipk_gather_rows_bf16(const void* x_bf16, const int* idx, void* out_bf16, int B, int L, int W, cudaStream_t stream);
 int clipk_scatter_rows_f32(const float* src, const int* idx, float* dst, int B, int L, int W, cudaStream_t stream);
 /* masked mean over the T frame embeddings of a video and its backward (Text2VideoRetrieval._mean_pooling_for_similarity_visual,

@@ -188,30 +188,31 @@ def _mha(x: Tensor, w_in: Tensor, b_in: Tensor, w_out: Tensor, b_out: Tensor, he
     return o @ w_out.t() + b_out
 
 
-def vit_forward(sd: Dict[str, Tensor], cfg: dict, pixels: Tensor, taps: Optional[dict] = None) -> Tensor:
-    """VisualTransformer.forward -> [B, embed_dim] (un-normalised)."""
+def vit_forward(sd: Dict[str, Tensor], cfg: dict, pixels: Tensor, taps: Optional[dict] = None, pre: str = "visual.", eps: float = 1e-5) -> Tensor:
+    """VisualTransformer.forward -> [B, embed_dim] (un-normalised).  `pre` / `eps`: Wukong keeps the same tower under
+    `visual_encoder.` with LayerNorm eps 1e-7 (modeling_wukong.py:268-309)."""
     W = cfg["vision_width"]; P = cfg["vision_patch_size"]
     heads = W // 64                                              # modeling_chineseclip.py:289
-    x = F.conv2d(pixels, sd["visual.conv1.weight"], stride=P)   # [B, W, g, g]
+    x = F.conv2d(pixels, sd[pre + "conv1.weight"], stride=P)   # [B, W, g, g]
     B = x.shape[0]
     x = x.reshape(B, W, -1).permute(0, 2, 1)
-    cls = sd["visual.class_embedding"].to(x.dtype).expand(B, 1, W)
-    x = torch.cat([cls, x], dim=1) + sd["visual.positional_embedding"]
-    x = _ln(x, sd["visual.ln_pre.weight"], sd["visual.ln_pre.bias"], 1e-5)
+    cls = sd[pre + "class_embedding"].to(x.dtype).expand(B, 1, W)
+    x = torch.cat([cls, x], dim=1) + sd[pre + "positional_embedding"]
+    x = _ln(x, sd[pre + "ln_pre.weight"], sd[pre + "ln_pre.bias"], eps)
     if taps is not None:
         taps["vit.ln_pre"] = x
     for i in range(cfg["vision_layers"]):
-        p = f"visual.transformer.resblocks.{i}."
-        h = _ln(x, sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], 1e-5)
+        p = f"{pre}transformer.resblocks.{i}."
+        h = _ln(x, sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], eps)
         x = x + _mha(h, sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"],
                      sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"], heads)
-        h = _ln(x, sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], 1e-5)
+        h = _ln(x, sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], eps)
         h = quick_gelu(h @ sd[p + "mlp.c_fc.weight"].t() + sd[p + "mlp.c_fc.bias"])
         x = x + (h @ sd[p + "mlp.c_proj.weight"].t() + sd[p + "mlp.c_proj.bias"])
         if taps is not None:
             taps[f"vit.block{i}"] = x
-    x = _ln(x[:, 0, :], sd["visual.ln_post.weight"], sd["visual.ln_post.bias"], 1e-5)
-    return x @ sd["visual.proj"]
+    x = _ln(x[:, 0, :], sd[pre + "ln_post.weight"], sd[pre + "ln_post.bias"], eps)
+    return x @ sd[pre + "proj"]
 
 
 # --------------------------------------------------------------------------- BERT
@@ -577,4 +578,70 @@ def openclip_forward(sd: Dict[str, Tensor], cfg: dict, pixels: Optional[Tensor],
     if image_embeds is not None and text_embeds is not None:
         lpt = (text_embeds @ image_embeds.t()) * sd["logit_scale"].exp()
         out["logits_per_text"] = lpt; out["logits_per_image"] = lpt.T
+    return out
+
+
+# =========================================================================== Wukong (sibling application wukong_clip)
+# appzoo/wukong_clip/model.py:22-88 + modelzoo/models/wukong/modeling_wukong.py:234-413: the same ViT under `visual_encoder.` and a causal
+# pre-LN TextTransformer under `text_encoder.` (token table = the bare parameter `embedding_table`), LayerNorm eps 1e-7 everywhere,
+# features pooled at the [SEP] (id 102) position (:349,359).  Keys as in the application's checkpoint minus the `model.` prefix.
+def wukong_tiny_config() -> dict:
+    return {"model": {"visual": dict(input_resolution=64, patch_size=16, width=128, layers=2, heads=2, output_dim=128),
+                      "text": dict(context_length=32, vocab_size=512, output_dim=128, width=128, layers=2, heads=2)}}
+
+
+def wukong_flat_config(raw: dict) -> dict:
+    v = raw["model"]["visual"]; t = raw["model"]["text"]
+    return dict(embed_dim=v["output_dim"], image_resolution=v["input_resolution"], vision_layers=v["layers"], vision_width=v["width"],
+                vision_patch_size=v["patch_size"], vocab_size=t["vocab_size"], context_length=t["context_length"],
+                transformer_width=t["width"], transformer_heads=t["heads"], transformer_layers=t["layers"])
+
+
+def wukong_init_state_dict(raw: dict, seed: int = 1234, scale_boost: float = 1.0) -> Dict[str, Tensor]:
+    """the open_clip tiny initialisation under Wukong's key names"""
+    cfg = wukong_flat_config(raw)
+    src = openclip_init_state_dict(cfg, seed, scale_boost)
+    sd: Dict[str, Tensor] = {}
+    for k, v in src.items():
+        if k == "logit_scale":
+            sd[k] = v
+        elif k.startswith("visual."):
+            sd["visual_encoder." + k[len("visual."):]] = v
+        elif k == "token_embedding.weight":
+            sd["text_encoder.embedding_table"] = v
+        else:
+            sd["text_encoder." + k] = v
+    return sd
+
+
+def wukong_text_forward(sd: Dict[str, Tensor], cfg: dict, ids: Tensor, sep_id: int = 102) -> Tensor:
+    """TextTransformer.forward (modeling_wukong.py:347-361) -> [B, output_dim] (un-normalised); one [SEP] per row"""
+    heads = cfg["transformer_heads"]; t = "text_encoder."
+    B, L = ids.shape
+    x = sd[t + "embedding_table"][ids] + sd[t + "positional_embedding"]
+    causal = torch.full((L, L), float("-inf")).triu_(1)
+    for i in range(cfg["transformer_layers"]):
+        p = f"{t}transformer.resblocks.{i}."
+        h = _ln(x, sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], 1e-7)
+        x = x + _mha(h, sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"], sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"], heads, causal)
+        h = _ln(x, sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], 1e-7)
+        h = quick_gelu(h @ sd[p + "mlp.c_fc.weight"].t() + sd[p + "mlp.c_fc.bias"])
+        x = x + (h @ sd[p + "mlp.c_proj.weight"].t() + sd[p + "mlp.c_proj.bias"])
+    x = _ln(x, sd[t + "ln_final.weight"], sd[t + "ln_final.bias"], 1e-7)
+    rows, cols = (ids == sep_id).nonzero(as_tuple=True)
+    return x[rows, cols] @ sd[t + "text_projection"]
+
+
+def wukong_forward(sd: Dict[str, Tensor], raw: dict, pixels: Optional[Tensor], ids: Optional[Tensor]) -> dict:
+    cfg = wukong_flat_config(raw)
+    image_features = text_features = None
+    if pixels is not None:
+        f = vit_forward(sd, cfg, pixels, pre="visual_encoder.", eps=1e-7)
+        image_features = f / f.norm(p=2, dim=-1, keepdim=True)
+    if ids is not None:
+        tx = wukong_text_forward(sd, cfg, ids)
+        text_features = tx / tx.norm(p=2, dim=-1, keepdim=True)
+    out = {"image_features": image_features, "text_features": text_features, "logit_scale": sd["logit_scale"].exp()}
+    if image_features is not None and text_features is not None:
+        out["logits_per_text"] = out["logit_scale"] * text_features @ image_features.t()
     return out

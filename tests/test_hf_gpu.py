@@ -216,3 +216,155 @@ def test_text2video_retrieval_vs_reference_golden(tmp_path):
     with torch.no_grad():
         f = model({"pixel_values": torch.from_numpy(z["pixels"]), "video_masks": torch.from_numpy(z["video_masks"])}, feat=True)
     assert f["text_embeds"] is None and max_err(f["video_embeds"], torch.from_numpy(z["out.video_embeds"])) < 6e-3
+
+
+# ------------------------------------------------------------------------------------------------ wukong_clip sibling application
+def _wukong_dir(tmp_path, z, with_vocab=False):
+    raw = json.loads(bytes(z["cfg_json"]).decode())
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w.")}
+    d = str(tmp_path / "wk"); os.makedirs(d)
+    json.dump(raw, open(os.path.join(d, "config.json"), "w"))
+    torch.save({"model." + k: v for k, v in sd.items()}, os.path.join(d, "pytorch_model.bin"))
+    if with_vocab:     # BERT layout: [PAD] 0, [UNK] 100, [CLS] 101, [SEP] 102 -- the text tower pools the position of id 102
+        words = ["[PAD]"] + [f"[unused{i}]" for i in range(1, 100)] + ["[UNK]", "[CLS]", "[SEP]", "[MASK]", "a", "red", "cat", "dog", "on", "the", "mat", "##s", "猫", "狗"]
+        open(os.path.join(d, "vocab.txt"), "w", encoding="utf-8").write("\n".join(words) + "\n")
+    return d, raw, sd
+
+
+def test_wukong_tiny_forward_backward_vs_reference_golden(tmp_path):
+    """WukongCLIP (appzoo/wukong_clip/model.py:22-88): ViT + causal TextTransformer pooled at [SEP], LayerNorm eps 1e-7 -- tuple output,
+    features / loss / every gradient against the fixture written by the unmodified reference (oracle/make_golden_wukong.py)."""
+    from easynlp_b200.appzoo import get_application_model
+    z = np.load(os.path.join(GOLD, "wukong_tiny.npz"))
+    d, raw, sd = _wukong_dir(tmp_path, z)
+    model = get_application_model("wukong_clip", d, user_defined_parameters={})
+    assert type(model).__name__ == "WukongCLIP" and all(n.startswith("model.") for n, _ in model.named_parameters())
+    assert json.loads(model.config.to_json_string()) == raw
+    assert set(model.state_dict()) == {"model." + k for k in sd}
+    model.train()
+    pixels = torch.from_numpy(z["pixels"]); ids = torch.from_numpy(z["ids"])
+    out, extra = model({"pixel_values": pixels.clone(), "input_ids": ids.clone()})
+    assert extra == [] and set(out) == {"image_features", "text_features", "logit_scale"}
+    ref = {k: torch.from_numpy(z["out." + k]) for k in ("image_features", "text_features")}
+    names = list(sd)
+    params = {k: sd[k].clone().requires_grad_(True) for k in names}
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        yo = O.wukong_forward(params, raw, pixels, ids)
+    yl = O.clip_loss(yo["logits_per_text"].float())
+    yg = dict(zip(names, torch.autograd.grad(yl, [params[k] for k in names], allow_unused=True)))
+    e = {k: max_err(out[k], ref[k]) for k in ref}; y = {k: max_err(yo[k].float(), ref[k]) for k in ref}
+    loss = model.compute_loss((out, extra), [])["loss"]
+    loss_ref = float(z["out.loss"])
+    print(f"PARITY wukong tiny fwd: err {e} (PyTorch bf16 yardstick {y}); loss {loss.item():.6f} vs {loss_ref:.6f}")
+    assert e["image_features"] < 1.5 * y["image_features"] + 1e-4 and e["text_features"] < 1.5 * y["text_features"] + 1e-4
+    assert abs(out["logit_scale"].item() - float(z["out.logit_scale"])) < 1e-4
+    assert abs(loss.item() - loss_ref) < max(2e-3 * abs(loss_ref), 2.0 * abs(yl.item() - loss_ref))
+    model.zero_grad(); loss.backward()
+    torch.cuda.synchronize()
+    refg = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("g.")}
+    gnorm = math.sqrt(sum(float(v.double().norm()) ** 2 for v in refg.values()))
+    worst = (0.0, None)
+    for k, r in refg.items():
+        got = model.engine.params.g(k).detach().float().cpu().view_as(r)
+        err = (got - r).norm().item(); yerr = (yg[k].float() - r).norm().item()
+        tol = max(0.03 * r.norm().item(), 1.5 * yerr) + 1e-4 * gnorm
+        worst = max(worst, (err / (r.norm().item() + 1e-4 * gnorm), k))
+        assert err <= tol, f"grad {k}: err {err:.3e} > tol {tol:.3e} (|ref| {r.norm().item():.3e}, yardstick {yerr:.3e})"
+    print(f"PARITY wukong tiny bwd: worst per-tensor relative gradient error {worst[0]:.3e} ({worst[1]})")
+    # single-modality calls (model.py:58-69) and the [SEP] rule
+    model.eval()
+    with torch.no_grad():
+        o1, _ = model({"input_ids": ids.clone()})
+        o2, _ = model({"pixel_values": pixels.clone()})
+    assert o1["image_features"] is None and max_err(o1["text_features"], ref["text_features"]) < 6e-3
+    assert o2["text_features"] is None and max_err(o2["image_features"], ref["image_features"]) < 6e-3
+    bad = ids.clone(); bad[0, 1] = 102
+    with pytest.raises(ValueError):
+        model({"input_ids": bad})
+    # kernel: position and count of the pooled token
+    from easynlp_b200 import ops
+    idx = torch.empty(ids.shape[0], dtype=torch.int32, device="cuda"); cnt = torch.empty_like(idx)
+    ops.find_token_rows(bad.cuda(), 102, idx, cnt)
+    assert idx.tolist() == [1] + ((ids == 102).int().argmax(1)[1:]).tolist() and cnt.tolist() == [2, 1, 1, 1, 1, 1]
+
+
+def test_wukong_dataset_evaluator_predictor(tmp_path):
+    """the application's data format end to end (appzoo/wukong_clip/data.py, evaluator.py, predictor.py): TSV rows of text + base64 image ->
+    WukongCLIPDataset.batch_fn -> WukongCLIPEvaluator (blocked ranking) and WukongCLIPPredictor rows, checked against the oracle on the
+    same preprocessed tensors"""
+    import base64
+    from io import BytesIO
+    from PIL import Image
+    from easynlp_b200.appzoo import get_application_dataset, get_application_evaluator, get_application_model_for_evaluation, get_application_predictor
+    z = np.load(os.path.join(GOLD, "wukong_tiny.npz"))
+    d, raw, sd = _wukong_dir(tmp_path, z, with_vocab=True)
+    raw["model"]["visual"]["input_resolution"] = 224      # the dataset crops to 224 x 224 (data.py:155-160): positional table for 14 x 14 + 1 tokens
+    g = torch.Generator().manual_seed(5)
+    sd["visual_encoder.positional_embedding"] = torch.randn(197, 128, generator=g) * 128 ** -0.5
+    json.dump(raw, open(os.path.join(d, "config.json"), "w"))
+    torch.save({"model." + k: v for k, v in sd.items()}, os.path.join(d, "pytorch_model.bin"))
+    rng = np.random.RandomState(3)
+    texts = ["a red cat", "the dog on the mat", "猫 on mats", "dogs", "a cat a dog", "红 unknown words", "the the the", "狗"]
+    rows = []
+    for t in texts:
+        buf = BytesIO(); Image.fromarray(rng.randint(0, 256, (240, 300, 3)).astype(np.uint8)).save(buf, format="PNG")
+        rows.append(t + "\t" + base64.urlsafe_b64encode(buf.getvalue()).decode())
+    tsv = str(tmp_path / "valid.tsv"); open(tsv, "w", encoding="utf-8").write("\n".join(rows) + "\n")
+    ds = get_application_dataset("wukong_clip", d, tsv, 32, input_schema="text:str:1,image:str:1", first_sequence="text", second_sequence="image")
+    batch = ds.batch_fn([ds[i] for i in range(len(ds))])
+    assert batch["pixel_values"].shape == (8, 3, 224, 224) and batch["input_ids"].shape == (8, 32)
+    assert batch["input_ids"][0].tolist()[:5] == [101, 104, 105, 106, 102] and (batch["input_ids"] == 102).sum(1).tolist() == [1] * 8
+    model = get_application_model_for_evaluation("wukong_clip", d)
+    ev = get_application_evaluator("wukong_clip", ds, user_defined_parameters={}, eval_batch_size=4)
+    res = ev.evaluate(model)
+    o = O.wukong_forward(sd, raw, batch["pixel_values"], batch["input_ids"])
+    with torch.no_grad():
+        f, _ = model({"pixel_values": batch["pixel_values"].clone(), "input_ids": batch["input_ids"].clone()})
+    assert max_err(f["text_features"], o["text_features"]) < 6e-3 and max_err(f["image_features"], o["image_features"]) < 6e-3
+    r = O.rank_of_match(f["text_features"].double().cpu(), f["image_features"].double().cpu())     # the ranking the evaluator must reproduce
+    want = sum(float((r < k).sum()) / 8 for k in (1, 5, 10)) / 3
+    assert res[0][0] == "mean_recall" and abs(res[0][1] - want) < 1e-9
+    assert get_application_evaluator("wukong_clip", ds, user_defined_parameters={"cosine_similarity": "True"}, eval_batch_size=8).evaluate(model) is None
+    pred = get_application_predictor("wukong_clip", d, first_sequence="text", second_sequence="image")
+    recs = pred.run([{"text": texts[1]}, {"text": texts[2]}])
+    got = np.array([[float(x) for x in rec["text_feat"].split("\t")] for rec in recs])
+    assert np.abs(got - o["text_features"][1:3].numpy()).max() < 6e-3
+    recs = pred.run([{"image": rows[0].split("\t")[1]}])
+    got = np.array([float(x) for x in recs[0]["image_feat"].split("\t")])
+    assert np.abs(got - o["image_features"][0].numpy()).max() < 6e-3
+
+
+def test_patch14_tower_trains(tmp_path):
+    """ViT-*/14 image towers that DO train (chinese_clip / open_clip / Wukong ViT-L/14): the 588-wide patch rows are padded to 592 for TMA;
+    the patch-embedding weight gradient and everything upstream against the oracle's autograd."""
+    from easynlp_b200.appzoo import get_application_model
+    raw = O.wukong_tiny_config()
+    raw["model"]["visual"].update(patch_size=14, input_resolution=56)
+    sd = O.wukong_init_state_dict(raw, seed=31, scale_boost=2.0)
+    assert sd["visual_encoder.conv1.weight"].shape == (128, 3, 14, 14) and sd["visual_encoder.positional_embedding"].shape == (17, 128)
+    d = str(tmp_path / "wk14"); os.makedirs(d)
+    json.dump(raw, open(os.path.join(d, "config.json"), "w"))
+    torch.save({"model." + k: v for k, v in sd.items()}, os.path.join(d, "pytorch_model.bin"))
+    model = get_application_model("wukong_clip", d)
+    assert model.engine.kdim == 588 and model.engine.kdim_pad == 592
+    model.train()
+    g = torch.Generator().manual_seed(31)
+    B = 6
+    pixels = torch.randn(B, 3, 56, 56, generator=g)
+    ids = torch.randint(103, 500, (B, 32), generator=g); ids[:, 0] = 101
+    lens = torch.tensor([32, 4, 11, 20, 7, 16])
+    ids = torch.where(torch.arange(32)[None, :] < lens[:, None], ids, torch.zeros_like(ids)); ids[torch.arange(B), lens - 1] = 102
+    names = list(sd)
+    params = {k: sd[k].clone().requires_grad_(True) for k in names}
+    ref = O.wukong_forward(params, raw, pixels, ids)
+    ref_loss = O.clip_loss(ref["logits_per_text"])
+    rg = dict(zip(names, torch.autograd.grad(ref_loss, [params[k] for k in names])))
+    out, _ = model({"pixel_values": pixels.clone(), "input_ids": ids.clone()})
+    loss = model.compute_loss(out, [])["loss"]
+    assert max_err(out["image_features"], ref["image_features"]) < 6e-3 and abs(loss.item() - ref_loss.item()) < 5e-3 * ref_loss.item() + 2e-3
+    for rep in range(2):      # twice: the padded scratch tile must not carry the first pass over
+        model.zero_grad(); (loss if rep == 0 else model.compute_loss(model({"pixel_values": pixels.clone(), "input_ids": ids.clone()})[0], [])["loss"]).backward()
+        for k in ("visual_encoder.conv1.weight", "visual_encoder.positional_embedding", "visual_encoder.class_embedding", "visual_encoder.proj",
+                  "visual_encoder.transformer.resblocks.0.attn.in_proj_weight"):
+            r = rg[k]; got = model.engine.params.g(k).detach().float().cpu().view_as(r)
+            assert (got - r).norm().item() < 0.05 * r.norm().item() + 1e-5, (rep, k, (got - r).norm().item(), r.norm().item())

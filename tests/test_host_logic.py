@@ -58,7 +58,8 @@ def test_registry_prefix_match_and_unknown_app():
     from easynlp_b200.appzoo import api
     with pytest.raises(NotImplementedError):
         api.get_application_model("sequence_classification", "/tmp/x")
-    assert api._match("clip") and api._match("clip_finetune")
+    assert api._classes("clip")[0].__name__ == "CLIPApp" and api._classes("clip_finetune")[0].__name__ == "CLIPApp"
+    assert api._classes("wukong_clip")[0].__name__ == "WukongCLIP" and api._model_cls("clip4clip").__name__ == "Text2VideoRetrieval"
 
 
 def test_synthetic_batch_layout():

@@ -144,3 +144,38 @@ def test_openclip_oracle_matches_reference_golden():
     assert len(ref) == 62
     for k, r in ref.items():
         assert torch.allclose(grads[k], r, rtol=2e-3, atol=2e-6), k
+
+
+def test_wukong_oracle_matches_reference_golden():
+    """wukong_clip sibling application (WukongModel: ViT + causal TextTransformer pooled at [SEP], eps 1e-7; modeling_wukong.py:234-413)
+    against the fixture written by the UNMODIFIED reference (oracle/make_golden_wukong.py): features, loss and all 62 gradient tensors."""
+    import json
+    z = np.load(os.path.join(GOLD, "wukong_tiny.npz"))
+    raw = json.loads(bytes(z["cfg_json"]).decode())
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w.")}
+    names = list(sd)
+    params = {k: sd[k].clone().requires_grad_(True) for k in names}
+    out = O.wukong_forward(params, raw, torch.from_numpy(z["pixels"]), torch.from_numpy(z["ids"]))
+    for k in ("image_features", "text_features"):
+        assert torch.allclose(out[k], torch.from_numpy(z["out." + k]), rtol=2e-4, atol=2e-5), k
+    loss = O.clip_loss(out["logits_per_text"])
+    assert abs(loss.item() - float(z["out.loss"])) < 1e-5
+    grads = dict(zip(names, torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)))
+    ref = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("g.")}
+    assert len(ref) == 62
+    for k, r in ref.items():
+        assert torch.allclose(grads[k], r, rtol=2e-3, atol=2e-6), k
+
+
+def test_wukong_full_tokenizer_matches_reference_vectors():
+    """FullTokenizer + the dataset's tokenize rule (appzoo/wukong_clip/bert_tokenizer.py:166-396, data.py:166-187): no never_split
+    protection of special tokens, 200-character words, [CLS] ids[:30] [SEP] zero padded to 32"""
+    import json
+    from easynlp_b200.appzoo.wukong_clip.data import FullTokenizer, wukong_tokenize
+    tok = FullTokenizer(os.path.join(GOLD, "tokenizer_vocab.txt"))
+    cases = json.load(open(os.path.join(GOLD, "wukong_tokenizer.json"), encoding="utf-8"))["cases"]
+    assert len(cases) == 10
+    for c in cases:
+        assert tok.tokenize(c["text"]) == c["tokens"], c["text"]
+        assert wukong_tokenize(tok, c["text"])[0].tolist() == c["input_ids"], c["text"]
+    assert wukong_tokenize(tok, [c["text"] for c in cases]).tolist() == [c["input_ids"] for c in cases]
