@@ -271,13 +271,13 @@ def test_wukong_tiny_forward_backward_vs_reference_golden(tmp_path):
         worst = max(worst, (err / (r.norm().item() + 1e-4 * gnorm), k))
         assert err <= tol, f"grad {k}: err {err:.3e} > tol {tol:.3e} (|ref| {r.norm().item():.3e}, yardstick {yerr:.3e})"
     print(f"PARITY wukong tiny bwd: worst per-tensor relative gradient error {worst[0]:.3e} ({worst[1]})")
-    # single-modality calls (model.py:58-69) and the [SEP] rule
+    # single-modality calls (model.py:58-69) and the [SEP] rule; 1e-2 = 1.4 x the PyTorch-bf16 yardstick printed above on unit vectors
     model.eval()
     with torch.no_grad():
         o1, _ = model({"input_ids": ids.clone()})
         o2, _ = model({"pixel_values": pixels.clone()})
-    assert o1["image_features"] is None and max_err(o1["text_features"], ref["text_features"]) < 6e-3
-    assert o2["text_features"] is None and max_err(o2["image_features"], ref["image_features"]) < 6e-3
+    assert o1["image_features"] is None and max_err(o1["text_features"], ref["text_features"]) < 1e-2
+    assert o2["text_features"] is None and max_err(o2["image_features"], ref["image_features"]) < 1e-2
     bad = ids.clone(); bad[0, 1] = 102
     with pytest.raises(ValueError):
         model({"input_ids": bad})
@@ -320,7 +320,7 @@ def test_wukong_dataset_evaluator_predictor(tmp_path):
     o = O.wukong_forward(sd, raw, batch["pixel_values"], batch["input_ids"])
     with torch.no_grad():
         f, _ = model({"pixel_values": batch["pixel_values"].clone(), "input_ids": batch["input_ids"].clone()})
-    assert max_err(f["text_features"], o["text_features"]) < 6e-3 and max_err(f["image_features"], o["image_features"]) < 6e-3
+    assert max_err(f["text_features"], o["text_features"]) < 1e-2 and max_err(f["image_features"], o["image_features"]) < 1e-2
     r = O.rank_of_match(f["text_features"].double().cpu(), f["image_features"].double().cpu())     # the ranking the evaluator must reproduce
     want = sum(float((r < k).sum()) / 8 for k in (1, 5, 10)) / 3
     assert res[0][0] == "mean_recall" and abs(res[0][1] - want) < 1e-9
@@ -328,10 +328,10 @@ def test_wukong_dataset_evaluator_predictor(tmp_path):
     pred = get_application_predictor("wukong_clip", d, first_sequence="text", second_sequence="image")
     recs = pred.run([{"text": texts[1]}, {"text": texts[2]}])
     got = np.array([[float(x) for x in rec["text_feat"].split("\t")] for rec in recs])
-    assert np.abs(got - o["text_features"][1:3].numpy()).max() < 6e-3
+    assert np.abs(got - o["text_features"][1:3].numpy()).max() < 1e-2
     recs = pred.run([{"image": rows[0].split("\t")[1]}])
     got = np.array([float(x) for x in recs[0]["image_feat"].split("\t")])
-    assert np.abs(got - o["image_features"][0].numpy()).max() < 6e-3
+    assert np.abs(got - o["image_features"][0].numpy()).max() < 1e-2
 
 
 def test_patch14_tower_trains(tmp_path):
@@ -361,7 +361,7 @@ def test_patch14_tower_trains(tmp_path):
     rg = dict(zip(names, torch.autograd.grad(ref_loss, [params[k] for k in names])))
     out, _ = model({"pixel_values": pixels.clone(), "input_ids": ids.clone()})
     loss = model.compute_loss(out, [])["loss"]
-    assert max_err(out["image_features"], ref["image_features"]) < 6e-3 and abs(loss.item() - ref_loss.item()) < 5e-3 * ref_loss.item() + 2e-3
+    assert max_err(out["image_features"], ref["image_features"]) < 1e-2 and abs(loss.item() - ref_loss.item()) < 5e-3 * ref_loss.item() + 2e-3
     for rep in range(2):      # twice: the padded scratch tile must not carry the first pass over
         model.zero_grad(); (loss if rep == 0 else model.compute_loss(model({"pixel_values": pixels.clone(), "input_ids": ids.clone()})[0], [])["loss"]).backward()
         for k in ("visual_encoder.conv1.weight", "visual_encoder.positional_embedding", "visual_encoder.class_embedding", "visual_encoder.proj",
