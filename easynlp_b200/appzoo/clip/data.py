@@ -15,6 +15,7 @@ from PIL import Image
 from torch.utils.data import Dataset
 
 from ...tokenization import BertTokenizer
+from ...bpe_tokenizer import SimpleTokenizer, openclip_tokenize
 
 CLIP_MEAN = np.array([0.48145466, 0.4578275, 0.40821073], dtype=np.float32)
 CLIP_STD = np.array([0.26862954, 0.26130258, 0.27577711], dtype=np.float32)
@@ -72,9 +73,8 @@ class CLIPDataset(Dataset):
         with open(os.path.join(pretrained_model_name_or_path, "config.json"), "r") as f:
             self.raw_config = json.load(f)
         mt = self.raw_config.get("model_type")
-        if mt == "open_clip":
-            raise NotImplementedError("model_type == open_clip (BPE SimpleTokenizer, causal text tower) is not on the B200 path")
-        self.model_type = "chinese_clip" if mt == "chinese_clip" else "huggingface_clip"      # both use BertTokenizer (data.py:226-229)
+        # open_clip tokenises with the byte-level BPE SimpleTokenizer, the other two branches with BertTokenizer (data.py:225-229)
+        self.model_type = mt if mt in ("open_clip", "chinese_clip") else "huggingface_clip"
         self.columns = parse_schema(input_schema)
         self.text_col = first_sequence
         self.image_col = second_sequence
@@ -84,7 +84,11 @@ class CLIPDataset(Dataset):
         if skip_first_line:
             lines = lines[1:]
         self.data_rows = [ln for ln in lines if ln]
-        self.tokenizer = BertTokenizer.from_pretrained(os.path.join(pretrained_model_name_or_path, "vocab.txt"))
+        vocab = os.path.join(pretrained_model_name_or_path, "vocab.txt")
+        if self.model_type == "open_clip":
+            self.openclip_tokenizer = SimpleTokenizer(bpe_path=vocab)       # `vocab.txt` is the gzip'd merges file here (data.py:226)
+        else:
+            self.tokenizer = BertTokenizer.from_pretrained(vocab)
         self.max_text_length = max_seq_length
 
     def __len__(self):
@@ -96,13 +100,16 @@ class CLIPDataset(Dataset):
         return self.convert_single_row_to_example(row)
 
     def convert_single_row_to_example(self, row):
-        tk = self.tokenizer([row[self.text_col]], padding="max_length", truncation=True, max_length=self.max_text_length, return_tensors="pt")
+        if self.model_type == "open_clip":      # fixed context length 77 whatever max_seq_length says (data.py:259-261)
+            tk = {"input_ids": openclip_tokenize(texts=[row[self.text_col]], context_length=77, _tokenizer=self.openclip_tokenizer)}
+        else:
+            tk = self.tokenizer([row[self.text_col]], padding="max_length", truncation=True, max_length=self.max_text_length, return_tensors="pt")
         return {"text": tk, "pixel_values": preprocess_image(decode_image(row[self.image_col]))}
 
     def batch_fn(self, features):
         out = {"pixel_values": torch.cat([f["pixel_values"] for f in features], dim=0),
-               "input_ids": torch.cat([f["text"]["input_ids"] for f in features], dim=0),
-               "token_type_ids": torch.cat([f["text"]["token_type_ids"] for f in features], dim=0),
-               "attention_mask": torch.cat([f["text"]["attention_mask"] for f in features], dim=0),
-               "label_ids": []}
+               "input_ids": torch.cat([f["text"]["input_ids"] for f in features], dim=0)}
+        for k in ("token_type_ids", "attention_mask"):      # absent from BPE rows: the reference then leaves an empty list (data.py:276-294)
+            out[k] = torch.cat([f["text"][k] for f in features], dim=0) if all(k in f["text"] for f in features) else []
+        out["label_ids"] = []
         return out

@@ -12,6 +12,7 @@ import torch
 
 from ...core.predictor import Predictor
 from ...tokenization import BertTokenizer
+from ...bpe_tokenizer import SimpleTokenizer, openclip_tokenize
 from .data import decode_image, preprocess_image
 
 
@@ -21,10 +22,11 @@ class CLIPPredictor(Predictor):
         with open(os.path.join(model_dir, "config.json"), "r") as f:
             self.raw_config = json.load(f)
         mt = self.raw_config.get("model_type")
-        if mt == "open_clip":
-            raise NotImplementedError("model_type == open_clip (BPE SimpleTokenizer, causal text tower) is not on the B200 path")
-        self.model_type = "chinese_clip" if mt == "chinese_clip" else "huggingface_clip"      # both use BertTokenizer (data.py:226-229)
-        self.tokenizer = BertTokenizer.from_pretrained(os.path.join(model_dir, "vocab.txt"))
+        self.model_type = mt if mt in ("open_clip", "chinese_clip") else "huggingface_clip"
+        if self.model_type == "open_clip":      # byte-level BPE over the gzip'd merges file `vocab.txt` (predictor.py:54-55)
+            self.openclip_tokenizer = SimpleTokenizer(bpe_path=os.path.join(model_dir, "vocab.txt"))
+        else:
+            self.tokenizer = BertTokenizer.from_pretrained(os.path.join(model_dir, "vocab.txt"))
         if model_cls is None:
             from .model import CLIPApp as model_cls
         self.multi_modal = model_cls.from_pretrained(model_dir, user_defined_parameters=user_defined_parameters or {}).cuda()
@@ -50,7 +52,9 @@ class CLIPPredictor(Predictor):
         for record in in_data:
             text = record.get(self.first_sequence, None)
             image = record.get(self.second_sequence, None)
-            if text is not None:
+            if text is not None and self.model_type == "open_clip":
+                record["input_ids"] = openclip_tokenize(texts=[text], context_length=77, _tokenizer=self.openclip_tokenizer)
+            elif text is not None:
                 tk = self.tokenizer(text, padding="max_length", truncation=True, max_length=max_seq_length, return_tensors="pt")
                 record["input_ids"] = tk["input_ids"]; record["token_type_ids"] = tk["token_type_ids"]; record["attention_mask"] = tk["attention_mask"]
             if image is not None:
@@ -62,9 +66,10 @@ class CLIPPredictor(Predictor):
         if "pixel_values" in in_data[0]:
             output = {"pixel_values": torch.cat([d["pixel_values"] for d in in_data], dim=0)}
         if "input_ids" in in_data[0]:
-            output = {"input_ids": torch.cat([d["input_ids"] for d in in_data], dim=0),
-                      "token_type_ids": torch.cat([d["token_type_ids"] for d in in_data], dim=0),
-                      "attention_mask": torch.cat([d["attention_mask"] for d in in_data], dim=0)}
+            output = {"input_ids": torch.cat([d["input_ids"] for d in in_data], dim=0)}
+            if "token_type_ids" in in_data[0]:
+                output["token_type_ids"] = torch.cat([d["token_type_ids"] for d in in_data], dim=0)
+                output["attention_mask"] = torch.cat([d["attention_mask"] for d in in_data], dim=0)
         with torch.no_grad():
             return self.multi_modal(output, feat=True)
 
