@@ -92,6 +92,11 @@ def _declare(L):
     L.clipk_scatter_rows_f32.argtypes = [vp, vp, vp, i, i, i, vp]
     L.clipk_frame_pool_fwd.argtypes = [vp, vp, vp, i, i, i, vp]
     L.clipk_frame_pool_bwd.argtypes = [vp, vp, vp, i, i, i, vp]
+    L.clipk_preprocess_kmax.argtypes = [i, i, i]
+    L.clipk_preprocess_workspace.argtypes = [i, i, i, ll]
+    L.clipk_preprocess_workspace.restype = C.c_size_t
+    L.clipk_preprocess_images.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, C.c_size_t, ll, vp]
+    L.clipk_preprocess_status.argtypes = [vp, i, i, i, vp]
     L.clipk_wp_create.argtypes = [C.c_char_p, C.c_char_p, i]
     L.clipk_wp_create.restype = vp
     L.clipk_wp_destroy.argtypes = [vp]

@@ -67,6 +67,24 @@ def parse_schema(input_schema):
     return [c.split(":")[0] for c in input_schema.split(",")] if input_schema else []
 
 
+def collate_pixels(features) -> torch.Tensor:
+    """[n, 3, 224, 224] of a batch whose examples carry either host-preprocessed `pixel_values` or a decoded RGB `image` (gpu_preprocess)"""
+    todo = [i for i, f in enumerate(features) if "image" in f]
+    if not todo:
+        return torch.cat([f["pixel_values"] for f in features], dim=0)
+    from ...image_pipeline import preprocess_images
+    batch = preprocess_images([features[i]["image"] for i in todo])
+    if len(todo) == len(features):
+        return batch
+    rows = [None] * len(features)
+    for j, i in enumerate(todo):
+        rows[i] = batch[j:j + 1]
+    for i, f in enumerate(features):
+        if rows[i] is None:
+            rows[i] = f["pixel_values"].to(batch.device)
+    return torch.cat(rows, dim=0)
+
+
 class CLIPDataset(Dataset):
     def __init__(self, pretrained_model_name_or_path, data_file, max_seq_length, input_schema=None, first_sequence=None, label_name=None,
                  second_sequence=None, label_enumerate_values=None, user_defined_parameters=None, skip_first_line=False, *args, **kwargs):
@@ -90,6 +108,11 @@ class CLIPDataset(Dataset):
         else:
             self.tokenizer = BertTokenizer.from_pretrained(vocab)
         self.max_text_length = max_seq_length
+        # gpu_preprocess (kwarg or user_defined_parameters['app_parameters']): examples carry the decoded RGB image and batch_fn runs the
+        # resize / crop / normalise of the whole batch in one GPU call (easynlp_b200/image_pipeline.py, bit-identical to the host chain).
+        # Off by default: batch_fn must then run in the main process (data loader workers = 0).
+        ap = (user_defined_parameters or {}).get("app_parameters", {}) if isinstance(user_defined_parameters, dict) else {}
+        self.gpu_preprocess = str(kwargs.get("gpu_preprocess", ap.get("gpu_preprocess", False))).lower() in ("1", "true", "yes")
 
     def __len__(self):
         return len(self.data_rows)
@@ -104,10 +127,14 @@ class CLIPDataset(Dataset):
             tk = {"input_ids": openclip_tokenize(texts=[row[self.text_col]], context_length=77, _tokenizer=self.openclip_tokenizer)}
         else:
             tk = self.tokenizer([row[self.text_col]], padding="max_length", truncation=True, max_length=self.max_text_length, return_tensors="pt")
-        return {"text": tk, "pixel_values": preprocess_image(decode_image(row[self.image_col]))}
+        image = decode_image(row[self.image_col])
+        if self.gpu_preprocess and image.mode == "RGB":
+            image.load()
+            return {"text": tk, "image": image}
+        return {"text": tk, "pixel_values": preprocess_image(image)}
 
     def batch_fn(self, features):
-        out = {"pixel_values": torch.cat([f["pixel_values"] for f in features], dim=0),
+        out = {"pixel_values": collate_pixels(features),
                "input_ids": torch.cat([f["text"]["input_ids"] for f in features], dim=0)}
         for k in ("token_type_ids", "attention_mask"):      # absent from BPE rows: the reference then leaves an empty list (data.py:276-294)
             out[k] = torch.cat([f["text"][k] for f in features], dim=0) if all(k in f["text"] for f in features) else []

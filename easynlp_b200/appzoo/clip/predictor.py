@@ -35,6 +35,9 @@ class CLIPPredictor(Predictor):
         self.second_sequence = kwargs.pop("second_sequence", "second_sequence")
         self.sequence_length = kwargs.pop("sequence_length", 128)
         self.feature_format = kwargs.pop("feature_format", "text")
+        # decoded RGB images of a batch are resized / cropped / normalised in one GPU call (bit-identical to the host chain,
+        # easynlp_b200/image_pipeline.py); gpu_preprocess=False keeps the per-image PIL + numpy chain of the reference
+        self.gpu_preprocess = bool(kwargs.pop("gpu_preprocess", True))
         if self.feature_format not in ("text", "numpy"):
             raise ValueError(f"feature_format must be 'text' or 'numpy', got {self.feature_format!r}")
 
@@ -49,6 +52,7 @@ class CLIPPredictor(Predictor):
                 break
             max_seq_length = max(max_seq_length, record["sequence_length"])
         max_seq_length = self.sequence_length if max_seq_length == -1 else max_seq_length
+        pending = []
         for record in in_data:
             text = record.get(self.first_sequence, None)
             image = record.get(self.second_sequence, None)
@@ -58,7 +62,20 @@ class CLIPPredictor(Predictor):
                 tk = self.tokenizer(text, padding="max_length", truncation=True, max_length=max_seq_length, return_tensors="pt")
                 record["input_ids"] = tk["input_ids"]; record["token_type_ids"] = tk["token_type_ids"]; record["attention_mask"] = tk["attention_mask"]
             if image is not None:
-                record["pixel_values"] = preprocess_image(decode_image(image))
+                img = decode_image(image)
+                if self.gpu_preprocess and img.mode == "RGB":
+                    pending.append((record, img))
+                else:
+                    record["pixel_values"] = preprocess_image(img)
+        if pending:
+            from ...image_pipeline import preprocess_images
+            batch = preprocess_images([img for _, img in pending])
+            for j, (record, _) in enumerate(pending):
+                record["pixel_values"] = batch[j:j + 1]
+            dev = batch.device
+            for record in in_data:       # host-chain leftovers (palette / grey / alpha images) join the batch on the same device
+                if record.get("pixel_values") is not None and record["pixel_values"].device != dev:
+                    record["pixel_values"] = record["pixel_values"].to(dev)
         return in_data
 
     def predict(self, in_data):

@@ -8,7 +8,7 @@ import torch
 from torch.utils.data import Dataset
 
 from ...tokenization import BertTokenizer
-from ..clip.data import decode_image, parse_schema, preprocess_image
+from ..clip.data import collate_pixels, decode_image, parse_schema, preprocess_image
 
 
 class FullTokenizer(BertTokenizer):
@@ -48,6 +48,8 @@ class WukongCLIPDataset(Dataset):
         self.data_rows = [ln for ln in lines if ln]
         self.tokenizer = FullTokenizer(vocab_file=os.path.join(pretrained_model_name_or_path, "vocab.txt"))
         self.max_text_length = max_seq_length
+        ap = (user_defined_parameters or {}).get("app_parameters", {}) if isinstance(user_defined_parameters, dict) else {}
+        self.gpu_preprocess = str(kwargs.get("gpu_preprocess", ap.get("gpu_preprocess", False))).lower() in ("1", "true", "yes")     # see CLIPDataset
 
     def __len__(self):
         return len(self.data_rows)
@@ -61,8 +63,13 @@ class WukongCLIPDataset(Dataset):
 
     def convert_single_row_to_example(self, row):
         # the reference tokenises with the default context length 32 whatever max_seq_length says (data.py:209)
-        return {"text": {"input_ids": self.tokenize(row[self.text_col])}, "pixel_values": preprocess_image(decode_image(row[self.image_col]))}
+        tk = {"input_ids": self.tokenize(row[self.text_col])}
+        image = decode_image(row[self.image_col])
+        if self.gpu_preprocess and image.mode == "RGB":
+            image.load()
+            return {"text": tk, "image": image}
+        return {"text": tk, "pixel_values": preprocess_image(image)}
 
     def batch_fn(self, features):
-        return {"pixel_values": torch.cat([f["pixel_values"] for f in features], dim=0),
+        return {"pixel_values": collate_pixels(features),
                 "input_ids": torch.cat([f["text"]["input_ids"] for f in features], dim=0)}

@@ -21,6 +21,9 @@ class WukongCLIPPredictor(Predictor):
         self.second_sequence = kwargs.pop("second_sequence", "second_sequence")
         self.sequence_length = kwargs.pop("sequence_length", 128)
         self.feature_format = kwargs.pop("feature_format", "text")
+        # decoded RGB images of a batch are resized / cropped / normalised in one GPU call (bit-identical to the host chain,
+        # easynlp_b200/image_pipeline.py); gpu_preprocess=False keeps the per-image PIL + numpy chain of the reference
+        self.gpu_preprocess = bool(kwargs.pop("gpu_preprocess", True))
         if self.feature_format not in ("text", "numpy"):
             raise ValueError(f"feature_format must be 'text' or 'numpy', got {self.feature_format!r}")
 
@@ -32,13 +35,27 @@ class WukongCLIPPredictor(Predictor):
             raise RuntimeError("Input data should not be None.")
         if not isinstance(in_data, list):
             in_data = [in_data]
+        pending = []
         for record in in_data:
             text = record.get(self.first_sequence, None)
             image = record.get(self.second_sequence, None)
             if text is not None:
                 record["input_ids"] = self.tokenize(text)
             if image is not None:
-                record["pixel_values"] = preprocess_image(decode_image(image))
+                img = decode_image(image)
+                if self.gpu_preprocess and img.mode == "RGB":
+                    pending.append((record, img))
+                else:
+                    record["pixel_values"] = preprocess_image(img)
+        if pending:
+            from ...image_pipeline import preprocess_images
+            batch = preprocess_images([img for _, img in pending])
+            for j, (record, _) in enumerate(pending):
+                record["pixel_values"] = batch[j:j + 1]
+            dev = batch.device
+            for record in in_data:       # host-chain leftovers (palette / grey / alpha images) join the batch on the same device
+                if record.get("pixel_values") is not None and record["pixel_values"].device != dev:
+                    record["pixel_values"] = record["pixel_values"].to(dev)
         return in_data
 
     def predict(self, in_data):

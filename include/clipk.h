@@ -261,6 +261,24 @@ int clipk_peer_wait(const unsigned int* my_flags, int world, int channel, unsign
 /* out[r, :] (+)= sum over peers p of src_ptrs[p][(rank * rows + r), :]: reduce-scatter of the gallery gradients by peer loads */
 int clipk_peer_reduce_rows(float* const* src_ptrs, int world, int rank, float* out, int rows, int d, int accumulate, cudaStream_t stream);
 
+/* -------------------------------------------------------------------------------------------- image preprocessing
+ * Decoded 8-bit RGB images -> the normalised fp32 [n, 3, size, size] batch of the image tower: replaces, per batch, the host chain
+ * _resize(image, 224, BICUBIC) -> _center_crop(224) -> /255 -> (x - mean) / std of CLIPDataset.convert_single_row_to_example and
+ * CLIPPredictor.preprocess (easynlp/appzoo/clip/data.py:29-135,263-272; predictor.py:100-110).  BIT-EXACT with Pillow's 8-bit bicubic
+ * resample (fixed-point taps, uint8 intermediate) and numpy's float32 normalisation.
+ *   pixels   device blob holding every image as interleaved RGB rows (h * w * 3 bytes at desc[i].src)
+ *   desc     device array [n]; `tmp` = byte offset of the image's h * size * 3 byte slot in the scratch part of the workspace
+ *   max_h    largest h of the batch (launch bound); kmax >= clipk_preprocess_kmax(w, h, size) of every image
+ *   workspace_bytes >= clipk_preprocess_workspace(n, size, kmax, scratch_bytes), scratch_bytes = sum of the slots
+ * clipk_preprocess_status reads back (and synchronises on) the overflow flag of the last call: 1 = a kmax too small was passed.      */
+typedef struct clipk_image_desc { long long src; int w, h; long long tmp; } clipk_image_desc;
+int clipk_preprocess_kmax(int w, int h, int size);                                             /* host helper, no CUDA call */
+size_t clipk_preprocess_workspace(int n, int size, int kmax, long long scratch_bytes);        /* host helper, no CUDA call */
+int clipk_preprocess_images(const unsigned char* pixels, const clipk_image_desc* desc, int n, int max_h, int size, int kmax,
+                            const float* mean3 /* host */, const float* std3 /* host */, float* out, void* workspace,
+                            size_t workspace_bytes, long long scratch_bytes, cudaStream_t stream);
+int clipk_preprocess_status(const void* workspace, int n, int size, int kmax, cudaStream_t stream);
+
 /* -------------------------------------------------------------------------------------------- native WordPiece (host code)
  * BertTokenizer of the reference (modelzoo/models/bert/tokenization_bert.py:67-504) for the call the CLIP application makes
  * (appzoo/clip/data.py:262-264): [CLS] + wordpieces (truncated to max_length - 2) + [SEP] + [PAD]s, attention mask 1/0.
