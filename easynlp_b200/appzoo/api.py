@@ -1,7 +1,6 @@
 """AppZoo registry for the applications on the hot path -- same call signatures as easynlp/appzoo/api.py:281-468 (prefix match on
 app_name in the reference's dictionary order: 'clip4clip' before 'clip'; NotImplementedError for unknown apps, extra kwargs tolerated).
-'clip' and 'wukong_clip' are complete (model, dataset, evaluator, predictor); 'clip4clip' (Text2VideoRetrieval, a sibling app sharing the
-encoders) registers its model."""
+'clip', 'wukong_clip' and 'clip4clip' (Text2VideoRetrieval) are registered with model, dataset, evaluator and predictor."""
 
 
 def _clip_classes():
@@ -20,19 +19,26 @@ def _wukong_classes():
     return WukongCLIP, WukongCLIPEvaluator, WukongCLIPPredictor, WukongCLIPDataset
 
 
+def _t2v_classes():
+    from .text2video_retrieval.model import Text2VideoRetrieval
+    from .text2video_retrieval.evaluator import Text2VideoRetrievalEvaluator
+    from .text2video_retrieval.predictor import Text2VideoRetrievalPredictor
+    from .text2video_retrieval.data import Text2VideoRetrievalDataset
+    return Text2VideoRetrieval, Text2VideoRetrievalEvaluator, Text2VideoRetrievalPredictor, Text2VideoRetrievalDataset
+
+
 def _classes(app_name):
     """(model, evaluator, predictor, dataset) classes of a fully registered application"""
     if app_name is not None and app_name.startswith("wukong_clip"):
         return _wukong_classes()
-    if app_name is not None and app_name.startswith("clip") and not app_name.startswith("clip4clip"):
+    if app_name is not None and app_name.startswith("clip4clip"):       # before 'clip': the reference's dictionary order (api.py:141,162)
+        return _t2v_classes()
+    if app_name is not None and app_name.startswith("clip"):
         return _clip_classes()
-    raise NotImplementedError(f"application {app_name!r} is outside the B200 hot path (registered: 'clip', 'wukong_clip', model of 'clip4clip')")
+    raise NotImplementedError(f"application {app_name!r} is outside the B200 hot path (registered: 'clip', 'clip4clip', 'wukong_clip')")
 
 
 def _model_cls(app_name):
-    if app_name is not None and app_name.startswith("clip4clip"):
-        from .text2video_retrieval.model import Text2VideoRetrieval
-        return Text2VideoRetrieval
     return _classes(app_name)[0]
 
 

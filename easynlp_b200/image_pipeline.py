@@ -52,11 +52,10 @@ class ImagePreprocessor:
             setattr(self, name, t)
         return t
 
-    def __call__(self, images: List, check: bool = False) -> torch.Tensor:
+    def stage(self, images: List):
+        """pack the decoded frames + their descriptor table into the pinned blob and start the host->device copy; -> launch plan"""
         lib = L.lib()
         n = len(images); S = self.size
-        if n == 0:
-            return torch.empty(0, 3, S, S, dtype=torch.float32, device=self.dev)
         arrs = [as_rgb_array(im) for im in images]
         desc = np.zeros(n, dtype=DESC)
         desc_bytes = (n * DESC.itemsize + 255) // 256 * 256
@@ -78,16 +77,29 @@ class ImagePreprocessor:
         dev = self._grow("_dev", off)
         dev[:off].copy_(host[:off], non_blocking=True)
         self._copied = torch.cuda.Event(); self._copied.record()
-        ws_bytes = lib.clipk_preprocess_workspace(n, S, kmax, tmp)
+        return {"n": n, "desc_bytes": desc_bytes, "scratch": tmp, "kmax": kmax, "max_h": max_h, "bytes": off,
+                "algorithmic_bytes": sum(a.size for a in arrs) + 2 * sum(a.shape[0] for a in arrs) * S * 3 + n * S * S * 3 * 4}
+
+    def run(self, plan, check: bool = False) -> torch.Tensor:
+        """the three kernel launches over a staged batch (may be repeated: the staged blob is not modified)"""
+        lib = L.lib()
+        n = plan["n"]; S = self.size; kmax = plan["kmax"]
+        dev = self._dev
+        ws_bytes = lib.clipk_preprocess_workspace(n, S, kmax, plan["scratch"])
         ws = self._grow("_ws", ws_bytes)
         out = torch.empty(n, 3, S, S, dtype=torch.float32, device=self.dev)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        L.check(lib.clipk_preprocess_images(C.c_void_p(dev.data_ptr() + desc_bytes), C.c_void_p(dev.data_ptr()), n, max_h, S, kmax,
+        L.check(lib.clipk_preprocess_images(C.c_void_p(dev.data_ptr() + plan["desc_bytes"]), C.c_void_p(dev.data_ptr()), n, plan["max_h"], S, kmax,
                                             self.mean.ctypes.data_as(C.c_void_p), self.std.ctypes.data_as(C.c_void_p), C.c_void_p(out.data_ptr()),
-                                            C.c_void_p(ws.data_ptr()), ws_bytes, tmp, stream), "preprocess_images")
+                                            C.c_void_p(ws.data_ptr()), ws_bytes, plan["scratch"], stream), "preprocess_images")
         if check and lib.clipk_preprocess_status(C.c_void_p(ws.data_ptr()), n, S, kmax, stream) != 0:
             raise RuntimeError("clipk_preprocess_images: tap table overflow (kmax too small)")
         return out
+
+    def __call__(self, images: List, check: bool = False) -> torch.Tensor:
+        if len(images) == 0:
+            return torch.empty(0, 3, self.size, self.size, dtype=torch.float32, device=self.dev)
+        return self.run(self.stage(images), check)
 
 
 _default = {}

@@ -368,3 +368,61 @@ def test_patch14_tower_trains(tmp_path):
                   "visual_encoder.transformer.resblocks.0.attn.in_proj_weight"):
             r = rg[k]; got = model.engine.params.g(k).detach().float().cpu().view_as(r)
             assert (got - r).norm().item() < 0.05 * r.norm().item() + 1e-5, (rep, k, (got - r).norm().item(), r.norm().item())
+
+
+def test_clip4clip_dataset_evaluator_predictor(tmp_path):
+    """Text2VideoRetrieval's data format end to end (appzoo/text2video_retrieval/data.py, evaluator.py, predictor.py): TSV rows of text + a
+    directory of frames -> padded frame stacks + video masks -> evaluator / predictor, against the oracle on the host-preprocessed frames"""
+    import shutil
+    from PIL import Image
+    from easynlp_b200.appzoo import get_application_dataset, get_application_evaluator, get_application_model_for_evaluation, get_application_predictor
+    from easynlp_b200.appzoo.clip.data import preprocess_image
+    zc = np.load(os.path.join(GOLD, "openclip_tiny_fwd_bwd.npz"))
+    cfg = json.loads(bytes(zc["cfg_json"]).decode())
+    sd = {k[2:]: torch.from_numpy(zc[k]) for k in zc.files if k.startswith("w.")}
+    g = torch.Generator().manual_seed(11)
+    cfg.update(image_resolution=224, vocab_size=700, context_length=77)          # frames are cropped to 224 x 224; BPE ids reach 653
+    sd["visual.positional_embedding"] = torch.randn(197, 128, generator=g) * 128 ** -0.5
+    sd["token_embedding.weight"] = torch.randn(700, 128, generator=g) * 0.02
+    sd["positional_embedding"] = torch.randn(77, 128, generator=g) * 0.01
+    d = str(tmp_path / "t2v"); os.makedirs(d)
+    json.dump(cfg, open(os.path.join(d, "config.json"), "w"))
+    torch.save({"open_clip." + k: v for k, v in sd.items()}, os.path.join(d, "pytorch_model.bin"))
+    shutil.copy(os.path.join(GOLD, "bpe_merges.txt.gz"), os.path.join(d, "vocab.txt"))
+    rng = np.random.RandomState(6)
+    texts = ["a photo of a cat", "the red bike", "the dog's ball rolled", "photos of cats and dogs"]
+    rows, frames = [], []
+    for i, t in enumerate(texts):
+        fd = tmp_path / f"video{i}"; fd.mkdir()
+        arrs = [rng.randint(0, 256, (90 + 10 * i, 120, 3)).astype(np.uint8) for _ in range((3, 12, 1, 7)[i])]
+        for j, a in enumerate(arrs):
+            Image.fromarray(a).save(fd / f"frame{j:02d}.png")
+        frames.append(arrs); rows.append(t + "\t" + str(fd))
+    tsv = str(tmp_path / "valid.tsv"); open(tsv, "w", encoding="utf-8").write("\n".join(rows) + "\n")
+    kw = dict(input_schema="text:str:1,image:str:1", first_sequence="text", second_sequence="image")
+    ds = get_application_dataset("clip4clip", d, tsv, 77, user_defined_parameters={"app_parameters": {"gpu_preprocess": True}}, **kw)
+    ds_host = get_application_dataset("clip4clip", d, tsv, 77, **kw)
+    batch = ds.batch_fn([ds[i] for i in range(4)]); bh = ds_host.batch_fn([ds_host[i] for i in range(4)])
+    assert batch["pixel_values"].shape == (4, 12, 3, 224, 224) and batch["video_masks"].sum(1).tolist() == [3, 12, 1, 7] and batch["input_ids"].shape == (4, 77)
+    assert torch.equal(batch["pixel_values"].cpu(), bh["pixel_values"]) and torch.equal(batch["video_masks"], bh["video_masks"])
+    # oracle: per-frame image embeddings -> masked mean -> normalise (text2video_retrieval/model.py:82-88); causal text tower with EOT pooling
+    px = bh["pixel_values"].view(48, 3, 224, 224)
+    f = O.vit_forward(sd, cfg, px); f = f / f.norm(dim=-1, keepdim=True)
+    m = bh["video_masks"].float().unsqueeze(-1)
+    v = (f.view(4, 12, -1) * m).sum(1) / m.sum(1); v = v / v.norm(dim=-1, keepdim=True)
+    t = O.openclip_text_forward(sd, cfg, bh["input_ids"]); t = t / t.norm(dim=-1, keepdim=True)
+    model = get_application_model_for_evaluation("clip4clip", d)
+    model.eval()
+    with torch.no_grad():
+        out = model(dict(batch))
+    assert max_err(out["video_embeds"], v) < 1e-2 and max_err(out["text_embeds"], t) < 1e-2
+    res = get_application_evaluator("clip4clip", ds, user_defined_parameters={}, eval_batch_size=2).evaluate(model)
+    r = O.rank_of_match(out["text_embeds"].double().cpu(), out["video_embeds"].double().cpu())
+    assert res[0][0] == "mean_recall" and abs(res[0][1] - sum(float((r < k).sum()) / 4 for k in (1, 5, 10)) / 3) < 1e-9
+    pred = get_application_predictor("clip4clip", d, first_sequence="image")
+    recs = pred.run([{"image": rows[0].split("\t")[1]}, {"image": rows[3].split("\t")[1]}])
+    got = np.array([[float(x) for x in rec["video_feat"].split("\t")] for rec in recs])
+    assert np.abs(got - v[[0, 3]].numpy()).max() < 1e-2
+    pred = get_application_predictor("clip4clip", d, first_sequence="text")
+    recs = pred.run([{"text": texts[1]}])
+    assert np.abs(np.array([float(x) for x in recs[0]["text_feat"].split("\t")]) - t[1].numpy()).max() < 1e-2
