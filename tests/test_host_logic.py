@@ -109,3 +109,28 @@ def test_predictor_feature_formats_and_npy_sink(tmp_path):
     SimplePredictorManager(Stub("text"), str(src), "idx:str:1,first_sequence:str:1", txt, "text_feat", "idx", batch_size=2).run()
     lines = open(txt).read().splitlines()
     assert len(lines) == 5 and lines[3].split("\t") == ["3.0"] * 4 + ["3"]
+
+
+def test_split_score_error_bound():
+    """Arithmetic of clipk_retrieval_rank_tc / the contrastive logits restated on the host: fp32 unit vectors split into
+    bf16 hi + lo, score = hi.hi + hi.lo + lo.hi accumulated in fp32.  The error against fp64 stays below 3e-6, the hit@K decisions of a
+    retrieval run equal the fp64 ones, and every rank lies inside the band that near-ties of that size allow."""
+    g = torch.Generator().manual_seed(0)
+    N, E, nq = 16384, 512, 512
+    img = torch.nn.functional.normalize(torch.randn(N, E, generator=g), dim=-1)
+    txt = torch.nn.functional.normalize(img + (7.0 / E ** 0.5) * torch.randn(N, E, generator=g), dim=-1)
+    sub = torch.arange(0, N, N // nq)[:nq]
+    q = txt[sub]
+    qh = q.bfloat16().float(); ql = (q - qh).bfloat16().float()
+    kh = img.bfloat16().float(); kl = (img - kh).bfloat16().float()
+    s = qh @ kh.t() + qh @ kl.t() + ql @ kh.t()
+    s64 = q.double() @ img.double().t()
+    assert (s.double() - s64).abs().max().item() < 3e-6
+    other = sub[:, None] != torch.arange(N)[None, :]
+    thr32 = (q * img[sub]).sum(-1, keepdim=True); thr64 = (q.double() * img[sub].double()).sum(-1, keepdim=True)
+    got = ((s > thr32) & other).sum(1)
+    exact = ((s64 > thr64) & other).sum(1)
+    for k in (1, 5, 10):
+        assert torch.equal(got < k, exact < k)
+    lo = ((s64 > thr64 + 4e-6) & other).sum(1); hi = ((s64 > thr64 - 4e-6) & other).sum(1)
+    assert bool(((lo <= got) & (got <= hi)).all()) and 0.05 < (exact < 1).float().mean().item() < 0.95
