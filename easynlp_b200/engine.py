@@ -1,4 +1,4 @@
-"""ClipEngine: host-side schedule of the chinese_clip training / encoding step over the clipk kernels.
+"""ClipEngine: host-side schedule of the CLIP training / encoding step over the clipk kernels.
 
 Everything numerical happens in hand-written sm_100a kernels behind the C ABI (include/clipk.h); this file only owns
 buffers (torch tensors as device memory) and the order of launches, i.e. it is the from-scratch counterpart of the
@@ -8,17 +8,23 @@ autograd graph PyTorch builds for
     CHINESE_CLIP.forward                easynlp/modelzoo/models/clip/modeling_chineseclip.py:343-365
     VisualTransformer / ResidualAttentionBlock   .../modeling_chineseclip.py:170-253   (pre-LN, QuickGELU)
     BertModel (embeddings + post-LN encoder)     easynlp/modelzoo/models/bert/modeling_bert.py:72-541
+    CLIPVisionModel / RobertaModel (huggingface_clip branch)   .../clip/modeling_clip.py:731-838, .../roberta/modeling_roberta.py:65-575
+    OPEN_CLIP (causal text transformer, EOT pooling)           .../clip/modeling_openclip.py:255-383
+    WukongModel (same shape, eps 1e-7, [SEP] pooling)          .../wukong/modeling_wukong.py:234-413
+    Text2VideoRetrieval's frame pooling                        easynlp/appzoo/text2video_retrieval/model.py:82-105
     clip_grad_norm_ + AdamW.step        easynlp/core/trainer.py:315-337, easynlp/core/optimizers.py:405-464
+
+`cfg["model_type"]` picks the kind: "chinese_clip" (default), "huggingface_clip", "open_clip", "wukong".  The towers share the code:
+one pre-LN block stack (`_blocks_forward/_blocks_backward`) serves every ViT and the causal text towers through a parameter-name
+table; `bert_forward/backward` serves BertModel and RobertaModel.
 
 Numerics: bf16 GEMM/attention operands with fp32 accumulation, fp32 residual stream / LayerNorm statistics /
 embeddings / logits / loss, fp32 master weights and gradients.  Layout: token-major [B*L, d] activations.
 BERT-tower dropout (hidden / attention-probs) is fused into the LayerNorm and attention kernels as Philox masks keyed by a
 device-resident forward-pass counter: a training forward draws fresh masks, its backward regenerates them ("dropout").
 """
-import math
-from typing import Dict, Optional
-
 import os
+from typing import Dict, Optional
 
 import torch
 

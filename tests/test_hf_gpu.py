@@ -376,7 +376,6 @@ def test_clip4clip_dataset_evaluator_predictor(tmp_path):
     import shutil
     from PIL import Image
     from easynlp_b200.appzoo import get_application_dataset, get_application_evaluator, get_application_model_for_evaluation, get_application_predictor
-    from easynlp_b200.appzoo.clip.data import preprocess_image
     zc = np.load(os.path.join(GOLD, "openclip_tiny_fwd_bwd.npz"))
     cfg = json.loads(bytes(zc["cfg_json"]).decode())
     sd = {k[2:]: torch.from_numpy(zc[k]) for k in zc.files if k.startswith("w.")}

@@ -1,6 +1,5 @@
 """GPU: the reference-facing plugin surface (get_application_model / CLIPApp / Trainer / CLIPEvaluator / CLIPPredictor) end to end
 on a synthetic checkpoint directory, checked against the oracle and the reference-generated fixtures."""
-import base64
 import io
 import json
 import os

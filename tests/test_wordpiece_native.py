@@ -5,7 +5,6 @@ import json
 import os
 import random
 
-import numpy as np
 import pytest
 
 from easynlp_b200.tokenization import BertTokenizer
