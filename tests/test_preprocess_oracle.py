@@ -50,3 +50,25 @@ def test_pipeline_matches_reference_vectors():
 def test_shape_rules():
     assert R.resized_shape(300, 200) == (336, 224) and R.resized_shape(200, 300) == (224, 336) and R.resized_shape(224, 500) == (224, 500)
     assert R.resized_shape(640, 481) == (298, 224) and R.crop_origin(298, 224) == (37, 0) and R.crop_origin(224, 337) == (0, 57)
+
+
+def test_cabi_host_helpers_agree_with_the_oracle():
+    """clipk_preprocess_kmax / clipk_preprocess_workspace are host-side helpers of the C ABI (no CUDA call): tap-table width per image ==
+    the resampling filter length Pillow allocates (ksize of the longer-filter axis), workspace formula monotone and padded."""
+    from easynlp_b200 import _lib as L
+    lib = L.lib()
+    rng = np.random.RandomState(0)
+    shapes = [(224, 224), (224, 500), (500, 224), (37, 61), (4000, 3000), (64, 900), (225, 223), (1, 1), (223, 4000)]
+    shapes += [(int(rng.randint(1, 3000)), int(rng.randint(1, 3000))) for _ in range(200)]
+    for w, h in shapes:
+        nw, nh = R.resized_shape(w, h, 224)
+        want = 1
+        if nw != w:
+            want = max(want, R.coefficients(w, nw)[0]) if nw > 0 else want
+        if nh != h:
+            want = max(want, R.coefficients(h, nh)[0]) if nh > 0 else want
+        assert lib.clipk_preprocess_kmax(w, h, 224) == want, (w, h, nw, nh)
+    assert lib.clipk_preprocess_kmax(0, 5, 224) == 0
+    a = lib.clipk_preprocess_workspace(4, 224, 9, 1000); b = lib.clipk_preprocess_workspace(8, 224, 9, 1000)
+    assert 0 < a < b and lib.clipk_preprocess_workspace(4, 224, 9, 5000) - a == 4000 and lib.clipk_preprocess_workspace(0, 224, 9, 0) == 0
+    assert a >= 4 * 2 * 224 * (8 + 9 * 4) + 1000
