@@ -167,7 +167,8 @@ class Trainer(object):
         label_ids = batch.pop("label_ids", None)
         dist_loss = bool(getattr(self.model_module, "distributed_loss", False))
         self._micro_step += 1
-        if ga == 1:
+        # video batches (Text2VideoRetrieval: [B, T, 3, R, R] frames + video_masks) go through the application's own forward
+        if ga == 1 and batch.get("video_masks") is None:
             out = self.engine.train_step(batch["pixel_values"], batch["input_ids"], lr=args.learning_rate, weight_decay=args.weight_decay,
                                          max_grad_norm=args.max_grad_norm, warmup_steps=self._warmup_steps, t_total=self._t_total,
                                          distributed=dist_loss, use_graph=self.use_graph,
