@@ -28,6 +28,18 @@ def recall_sharded(text_embeds_local: torch.Tensor, image_embeds_local: torch.Te
     return sharded_recall(text_embeds_local, image_embeds_local, ks)
 
 
+def summarize_recall(hits, query_len: int, seconds: float):
+    """hit counts {1: n1, 5: n5, 10: n10} -> the evaluators' return value [("mean_recall", fraction)]; prints the three report lines in
+    the format of the reference evaluators (appzoo/clip/evaluator.py:62-70, wukong_clip/evaluator.py:69-77, text2video_retrieval/
+    evaluator.py:63-71) -- shared by CLIPEvaluator, WukongCLIPEvaluator and Text2VideoRetrievalEvaluator"""
+    fractions = [hits[k] / query_len for k in (1, 5, 10)]
+    mean_recall = sum(fractions) / 3.0
+    print(" ".join(f"r{k}_num:{hits[k]}" for k in (1, 5, 10)), "query_num:" + str(query_len))
+    print(" ".join(f"r{k}(%):{f * 100}" for k, f in zip((1, 5, 10), fractions)), "mean_recall(%):" + str(mean_recall * 100))
+    print("Inference time = {:.2f}s, [{:.4f} ms / sample] ".format(seconds, seconds * 1000 / max(1, query_len)))
+    return [("mean_recall", mean_recall)]
+
+
 class CLIPEvaluator(Evaluator):
 
     def __init__(self, valid_dataset, **kwargs):
@@ -49,11 +61,4 @@ class CLIPEvaluator(Evaluator):
             text_embeds_all.append(outputs["text_embeds"].clone())
         image_embeds = torch.cat(image_embeds_all, dim=0)
         text_embeds = torch.cat(text_embeds_all, dim=0)
-        query_len = text_embeds.shape[0]
-        hits = recall_from_embeddings(text_embeds, image_embeds)
-        r1, r5, r10 = hits[1] / query_len, hits[5] / query_len, hits[10] / query_len
-        mean_recall = (r1 + r5 + r10) / 3.0
-        print("r1_num:" + str(hits[1]), "r5_num:" + str(hits[5]), "r10_num:" + str(hits[10]), "query_num:" + str(query_len))
-        print("r1(%):" + str(r1 * 100), "r5(%):" + str(r5 * 100), "r10(%):" + str(r10 * 100), "mean_recall(%):" + str(mean_recall * 100))
-        print("Inference time = {:.2f}s, [{:.4f} ms / sample] ".format(total_spent_time, total_spent_time * 1000 / max(1, query_len)))
-        return [("mean_recall", mean_recall)]
+        return summarize_recall(recall_from_embeddings(text_embeds, image_embeds), text_embeds.shape[0], total_spent_time)

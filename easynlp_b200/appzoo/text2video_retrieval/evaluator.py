@@ -5,7 +5,7 @@ import time
 import torch
 
 from ...core.evaluator import Evaluator
-from ..clip.evaluator import recall_from_embeddings
+from ..clip.evaluator import recall_from_embeddings, summarize_recall
 
 
 class Text2VideoRetrievalEvaluator(Evaluator):
@@ -29,10 +29,4 @@ class Text2VideoRetrievalEvaluator(Evaluator):
             video_all.append(outputs["video_embeds"]); text_all.append(outputs["text_embeds"])
         video_embeds = torch.cat(video_all, dim=0); text_embeds = torch.cat(text_all, dim=0)
         query_len = text_embeds.shape[0]
-        hits = recall_from_embeddings(text_embeds, video_embeds)
-        r1, r5, r10 = hits[1] / query_len, hits[5] / query_len, hits[10] / query_len
-        mean_recall = (r1 + r5 + r10) / 3.0
-        print("r1_num:" + str(hits[1]), "r5_num:" + str(hits[5]), "r10_num:" + str(hits[10]), "query_num:" + str(query_len))
-        print("r1(%):" + str(r1 * 100), "r5(%):" + str(r5 * 100), "r10(%):" + str(r10 * 100), "mean_recall(%):" + str(mean_recall * 100))
-        print("Inference time = {:.2f}s, [{:.4f} ms / sample] ".format(total_spent_time, total_spent_time * 1000 / max(1, query_len)))
-        return [("mean_recall", mean_recall)]
+        return summarize_recall(recall_from_embeddings(text_embeds, video_embeds), query_len, total_spent_time)

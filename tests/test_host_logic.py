@@ -134,3 +134,14 @@ def test_split_score_error_bound():
         assert torch.equal(got < k, exact < k)
     lo = ((s64 > thr64 + 4e-6) & other).sum(1); hi = ((s64 > thr64 - 4e-6) & other).sum(1)
     assert bool(((lo <= got) & (got <= hi)).all()) and 0.05 < (exact < 1).float().mean().item() < 0.95
+
+
+def test_recall_report_lines(capsys):
+    """the evaluators' shared report: return value and the reference's three printed lines (appzoo/clip/evaluator.py:62-70)"""
+    from easynlp_b200.appzoo.clip.evaluator import summarize_recall
+    out = summarize_recall({1: 3, 5: 4, 10: 8}, 8, 0.5)
+    assert out == [("mean_recall", (3 / 8 + 4 / 8 + 1.0) / 3.0)]
+    lines = capsys.readouterr().out.splitlines()
+    assert lines[0] == "r1_num:3 r5_num:4 r10_num:8 query_num:8"
+    assert lines[1] == "r1(%):" + str(3 / 8 * 100) + " r5(%):" + str(50.0) + " r10(%):" + str(100.0) + " mean_recall(%):" + str((3 / 8 + 4 / 8 + 1.0) / 3.0 * 100)
+    assert lines[2] == "Inference time = 0.50s, [62.5000 ms / sample] "
