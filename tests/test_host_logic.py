@@ -145,3 +145,26 @@ def test_recall_report_lines(capsys):
     assert lines[0] == "r1_num:3 r5_num:4 r10_num:8 query_num:8"
     assert lines[1] == "r1(%):" + str(3 / 8 * 100) + " r5(%):" + str(50.0) + " r10(%):" + str(100.0) + " mean_recall(%):" + str((3 / 8 + 4 / 8 + 1.0) / 3.0 * 100)
     assert lines[2] == "Inference time = 0.50s, [62.5000 ms / sample] "
+
+
+def test_bench_traffic_is_tied_to_the_library_build(tmp_path, monkeypatch):
+    """bench.py reports roofline.traffic from the committed ncu launch list ONLY when that profile was captured with the library that is
+    loaded now (sha256 recorded by tools/launch_summary.py); the committed profile matches the current sources' build stamp."""
+    import json
+    import bench
+    from easynlp_b200 import build as B
+    val, why = bench._ncu_gemm_traffic()
+    stamp = open(os.path.join(B.LIBDIR, "libclipk.sha256")).read().strip()
+    prof = json.load(open(os.path.join(bench.ROOT, bench.PROFILE_JSON)))
+    if prof["libclipk_sha256"] == stamp:
+        assert val == prof["gemm"]["dram_bytes_per_launch"] and 1e8 < val < 1e9 and "same libclipk.so" in why
+    else:
+        assert val is None and "refused" in why
+    # a profile of another build is refused
+    fake = dict(prof, libclipk_sha256="0" * 64)
+    p = tmp_path / "fake.json"; p.write_text(json.dumps(fake))
+    monkeypatch.setattr(bench, "PROFILE_JSON", os.path.relpath(str(p), bench.ROOT))
+    val, why = bench._ncu_gemm_traffic()
+    assert val is None and "refused" in why
+    # FLOP constants of the roofline (SURVEY.md 8d)
+    assert bench.FLOPS_FWD_PER_PAIR == 35_126_906_880 + 13_300_469_760 and bench.FLOPS_TRAIN_PER_PAIR == 145_282_129_920
